@@ -1,0 +1,148 @@
+/*
+ * flagstats_cuda.h -- C ABI of libflagstats_cuda.so, the B200 (sm_100a)
+ * implementation of libflagstats' flagstat hot path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in any signature
+ * (streams travel as void*).  Every entry point names the reference interface
+ * it replaces or extends; file:line are in mklarqvist/libflagstats @93f68238.
+ *
+ * Counter layout (unchanged from the reference, libflagstats.h:69-112,118-142):
+ *   flags[ 0..15]  QC-pass records, indexed by SAM bit number
+ *   flags[16..31]  QC-fail records
+ *   written slots: {2,6,7,8,10,11,12,13,14} in both halves, 25 (= n_fail) and
+ *   9 (= n_pass, the convention of the kernels FLAGSTATS_u16 dispatches to,
+ *   libflagstats.h:429,1212,1843).  All other slots are never touched.
+ * All FLAGSTAT_* entry points ACCUMULATE into flags (caller zeroes), like the
+ * reference kernels; POSPOPCNT_cuda_u16* ZERO out[] first, like
+ * STORM_pospopcnt_u16 (libalgebra.h:3497-3498).
+ *
+ * Return value: 0 on success (as every reference kernel), otherwise a negative
+ * FLAGSTAT_CUDA_E* code or a positive cudaError_t; on failure flags[] is left
+ * untouched.  Nothing here aborts or throws.  There is no CPU fallback: with no
+ * usable device every compute entry returns FLAGSTAT_CUDA_ENODEV.
+ */
+#ifndef FLAGSTATS_CUDA_H_
+#define FLAGSTATS_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLAGSTAT_CUDA_ENODEV (-1) /* no CUDA device / driver */
+#define FLAGSTAT_CUDA_EINVAL (-2) /* bad argument */
+#define FLAGSTAT_CUDA_ENOMEM (-3) /* host allocation failed */
+#define FLAGSTAT_CUDA_ESTATE (-4) /* stream handle used out of order */
+
+/* ---- the reference's plugin signature ---------------------------------- */
+
+/* Same type as FLAGSTATS_func, libflagstats.h:2970. */
+typedef int (*FLAGSTATS_cuda_func)(const uint16_t*, uint32_t, uint32_t*);
+
+/*
+ * Drop-in sibling of FLAGSTAT_scalar / _sse4 / _avx2 / _avx512
+ * (libflagstats.h:170,184,967,1646).  `array` may be a host pointer (pageable
+ * or pinned: staged over PCIe in overlapped chunks) or a device / managed
+ * pointer (kernel runs in place).  Any 2-byte alignment.  Synchronous.
+ * Counters wrap mod 2^32 exactly like the reference's `++`.
+ */
+int FLAGSTAT_cuda(const uint16_t* array, uint32_t len, uint32_t* flags);
+
+/* Same, with 64-bit length and counters (the reference cannot express
+ * len >= 2^32 or counts >= 2^32; libflagstats.h:170 uses uint32_t). */
+int FLAGSTAT_cuda_u64(const uint16_t* array, uint64_t len, uint64_t* flags);
+
+/*
+ * Device-resident, asynchronous form: d_array and d_flags (uint64_t[32]) are
+ * device pointers on the current device, `stream` is a cudaStream_t (NULL =
+ * legacy default stream).  Enqueues the kernel and returns; accumulates.
+ * This is what a caller holding the FLAG column in HBM uses, and what the
+ * multi-GPU path runs per shard before the 32-counter all-reduce.
+ */
+int FLAGSTAT_cuda_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, void* stream);
+
+/* Run-time half of the dispatch test the reference does with cpuid
+ * (libflagstats.h:3000-3019): number of usable CUDA devices (0 = none). */
+int FLAGSTAT_cuda_available(void);
+
+/* Length at or above which FLAGSTATS_get_function should pick FLAGSTAT_cuda for
+ * HOST data (the analogue of the 1024/512/256 thresholds, :3000,3006,3016).
+ * Defaults to 65536; env FLAGSTAT_CUDA_MIN_LEN or the setter override it. */
+uint32_t FLAGSTAT_cuda_min_len(void);
+void FLAGSTAT_cuda_set_min_len(uint32_t n);
+
+/* ---- raw positional popcount (STORM_pospopcnt_u16, libalgebra.h:3496) ---- */
+
+int POSPOPCNT_cuda_u16(const uint16_t* data, size_t len, uint32_t* out /*[16]*/);
+int POSPOPCNT_cuda_u16_u64(const uint16_t* data, uint64_t len, uint64_t* out /*[16]*/);
+/* async, device pointers, ACCUMULATES into d_out[16] (caller zeroes) */
+int POSPOPCNT_cuda_device(const uint16_t* d_data, uint64_t len, uint64_t* d_out, void* stream);
+
+/* ---- block streaming (caller pattern of benchmark/flagstats.cpp:288-358:
+ *      one shared counters[32] accumulated over 1,024,000-byte blocks) ------- */
+
+typedef struct FLAGSTAT_cuda_stream FLAGSTAT_cuda_stream;
+
+/* device: CUDA ordinal; block_records: capacity of one slot (512000 for the
+ * reference's block); n_slots: pinned ring depth (>= 2; 0 = default 4). */
+int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** s, int device, uint32_t block_records,
+                              int n_slots);
+/* Zero-copy producer API: get the next pinned slot (blocks until the slot's
+ * previous transfer has finished), fill it, then submit n records. */
+uint16_t* FLAGSTAT_cuda_stream_acquire(FLAGSTAT_cuda_stream* s);
+int FLAGSTAT_cuda_stream_submit(FLAGSTAT_cuda_stream* s, uint32_t n_records);
+/* Convenience: acquire + memcpy from any host pointer + submit. */
+int FLAGSTAT_cuda_stream_push(FLAGSTAT_cuda_stream* s, const uint16_t* block, uint32_t n_records);
+/* Wait for everything submitted so far, ADD the totals into flags[32] and
+ * reset the device accumulator.  The handle stays usable. */
+int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags);
+int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s);
+
+/* ---- several GPUs from one process (range shards, host-side sum) --------- */
+
+/* Splits [0,len) into n_devices contiguous ranges (boundaries on 8-record
+ * multiples), runs one shard per device concurrently and sums the 32 counters
+ * on the host.  array must be a HOST pointer.  The one-process-per-GPU form
+ * with an NCCL all-reduce lives in libflagstats_b200/sharded.py on top of
+ * FLAGSTAT_cuda_device. */
+int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags, int n_devices);
+
+/* ---- diagnostics / test & bench support ---------------------------------- */
+
+const char* FLAGSTAT_cuda_strerror(int code);
+const char* FLAGSTAT_cuda_version(void);
+/* Kernels this library has launched in this process (all threads). */
+uint64_t FLAGSTAT_cuda_launch_count(void);
+/* Select a kernel variant for A/B tests (0 = default).  Returns the previous. */
+int FLAGSTAT_cuda_set_variant(int variant);
+/* Persistent-grid size override: CTAs per SM (0 = default). */
+int FLAGSTAT_cuda_set_ctas_per_sm(int n);
+
+/* Deterministic synthetic FLAG columns, pure functions of the GLOBAL record
+ * index.  Device twins of oracle_synth_uniform/_hiseqx; d_out is
+ * a device pointer; async on `stream`. */
+int FLAGSTAT_cuda_synth_uniform(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,
+                                uint16_t mask, void* stream);
+int FLAGSTAT_cuda_synth_hiseqx(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,
+                               uint32_t qcfail_ppm, void* stream);
+
+/* Minimal device-memory helpers so C callers need no CUDA headers. */
+void* FLAGSTAT_cuda_malloc(size_t bytes);
+void* FLAGSTAT_cuda_malloc_host(size_t bytes); /* pinned */
+int FLAGSTAT_cuda_free(void* p);
+int FLAGSTAT_cuda_free_host(void* p);
+int FLAGSTAT_cuda_memcpy_h2d(void* d, const void* h, size_t bytes);
+int FLAGSTAT_cuda_memcpy_d2h(void* h, const void* d, size_t bytes);
+int FLAGSTAT_cuda_memset(void* d, int value, size_t bytes);
+int FLAGSTAT_cuda_sync(void);
+/* Times `iters` back-to-back device-resident launches with CUDA events on an
+ * internal stream; returns 0 and the mean milliseconds per launch. */
+int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
+                              int pospopcnt_mode, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAGSTATS_CUDA_H_ */

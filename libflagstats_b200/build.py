@@ -1,0 +1,62 @@
+"""In-tree build of libflagstats_cuda.so for sm_100a.
+
+    python -m libflagstats_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the .so lands next to this file
+(libflagstats_b200/libflagstats_cuda.so), is git-ignored and travels to the
+GPU box inside the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libflagstats_cuda.so")
+
+SOURCES = ["flagstat_capi.cu"]
+HEADERS = ["flagstat_kernels.cuh", "bitcounter.cuh", "synth.cuh",
+           os.path.join("..", "..", "include", "flagstats_cuda.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "-shared", "-cudart", "shared",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return SO
+    cmd = [nvcc()] + NVCC_FLAGS
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    print(SO)

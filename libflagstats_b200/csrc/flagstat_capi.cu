@@ -1,0 +1,609 @@
+// flagstat_capi.cu -- C ABI of libflagstats_cuda.so (include/flagstats_cuda.h).
+//
+// Host-side plumbing only: pointer classification, staging of host data over
+// PCIe in overlapped chunks, the pinned block ring of the streaming API, the
+// per-device contexts.  All counting happens in flagstat_kernels.cuh.
+// There is deliberately NO CPU implementation behind these entry points: if no
+// device is usable they return FLAGSTAT_CUDA_ENODEV.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/flagstats_cuda.h"
+#include "flagstat_kernels.cuh"
+#include "synth.cuh"
+
+namespace {
+
+using namespace fsb200;
+
+constexpr int kMaxDevices = 64;
+constexpr size_t kChunkBytes = 32u << 20;  // staging chunk for host data
+constexpr int kStages = 3;
+
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_variant{0};
+std::atomic<int> g_ctas_per_sm{0};
+std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
+
+#define CK(expr)                              \
+    do {                                      \
+        cudaError_t e_ = (expr);              \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+struct DeviceInfo {
+    int sms = 0;
+    int occ[2][2] = {{0, 0}, {0, 0}};  // [mode][variant] resident CTAs per SM
+    bool ok = false;
+};
+
+std::mutex g_mu;
+int g_ndev = -2;  // -2 = not probed
+DeviceInfo g_dev[kMaxDevices];
+
+int probe_devices()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ndev != -2) return g_ndev;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (n > kMaxDevices) n = kMaxDevices;
+    g_ndev = n;
+    return n;
+}
+
+template <int MODE, int VARIANT>
+int occupancy()
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flagstat_kernel<MODE, VARIANT>, kThreads,
+                                                      0) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 2;
+    }
+    return nb < 1 ? 1 : nb;
+}
+
+int device_info(int dev, DeviceInfo** out)
+{
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (dev < 0 || dev >= g_ndev) return FLAGSTAT_CUDA_EINVAL;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceInfo& d = g_dev[dev];
+    if (!d.ok) {
+        int cur = -1;
+        CK(cudaGetDevice(&cur));
+        if (cur != dev) CK(cudaSetDevice(dev));
+        CK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        d.occ[0][0] = occupancy<kFlagstat, 0>();
+        d.occ[0][1] = occupancy<kFlagstat, 1>();
+        d.occ[1][0] = occupancy<kPospopcnt, 0>();
+        d.occ[1][1] = d.occ[1][0];
+        if (cur != dev && cur >= 0) CK(cudaSetDevice(cur));
+        d.ok = true;
+    }
+    *out = &d;
+    return 0;
+}
+
+// Enqueue one kernel on the current device.
+int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaStream_t st)
+{
+    if ((reinterpret_cast<uintptr_t>(d_array) & 1u) != 0) return FLAGSTAT_CUDA_EINVAL;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    DeviceInfo* di = nullptr;
+    int rc = device_info(dev, &di);
+    if (rc) return rc;
+    const int variant = g_variant.load() == 1 ? 1 : 0;
+
+    const uint64_t addr = reinterpret_cast<uintptr_t>(d_array);
+    uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
+    if (head > n) head = n;
+    const uint64_t nb = ((n - head) >> 3) / kVecPerBatch;
+    int per_sm = g_ctas_per_sm.load();
+    if (per_sm <= 0) per_sm = di->occ[mode][variant];
+    uint64_t grid = (uint64_t)per_sm * (uint64_t)di->sms;
+    if (grid > nb + 1) grid = nb + 1;
+
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(d_out);
+    const dim3 g((unsigned)grid), b(kThreads);
+    if (mode == kPospopcnt) {
+        flagstat_kernel<kPospopcnt, 0><<<g, b, 0, st>>>(d_array, n, out);
+    } else if (variant == 1) {
+        flagstat_kernel<kFlagstat, 1><<<g, b, 0, st>>>(d_array, n, out);
+    } else {
+        flagstat_kernel<kFlagstat, 0><<<g, b, 0, st>>>(d_array, n, out);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-call working set for synchronous entry points (pooled per device)
+// ---------------------------------------------------------------------------
+struct Lane {
+    int dev = -1;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    uint64_t* d_flags = nullptr;  // 32 x u64
+    uint64_t* h_flags = nullptr;  // pinned
+    uint16_t* stage[kStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t copied[kStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t consumed[kStages] = {nullptr, nullptr, nullptr};
+    bool staged = false;
+};
+
+std::mutex g_pool_mu;
+std::vector<Lane*> g_pool[kMaxDevices];
+
+int lane_create(int dev, Lane** out)
+{
+    Lane* l = new (std::nothrow) Lane();
+    if (!l) return FLAGSTAT_CUDA_ENOMEM;
+    l->dev = dev;
+    CK(cudaStreamCreateWithFlags(&l->copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&l->comp, cudaStreamNonBlocking));
+    CK(cudaMalloc(&l->d_flags, 32 * sizeof(uint64_t)));
+    CK(cudaMallocHost(&l->h_flags, 32 * sizeof(uint64_t)));
+    *out = l;
+    return 0;
+}
+
+int lane_ensure_staging(Lane* l)
+{
+    if (l->staged) return 0;
+    for (int i = 0; i < kStages; ++i) {
+        CK(cudaMalloc(&l->stage[i], kChunkBytes));
+        CK(cudaEventCreateWithFlags(&l->copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l->consumed[i], cudaEventDisableTiming));
+    }
+    l->staged = true;
+    return 0;
+}
+
+int lane_acquire(int dev, Lane** out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool[dev].empty()) {
+            *out = g_pool[dev].back();
+            g_pool[dev].pop_back();
+            return 0;
+        }
+    }
+    return lane_create(dev, out);
+}
+
+void lane_release(Lane* l)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool[l->dev].push_back(l);
+}
+
+// Synchronous run on the CURRENT device; array may be host or device memory.
+// totals: 32 (flagstat) or 16 (pospopcnt) u64, overwritten.
+int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
+{
+    const int nout = mode == kPospopcnt ? 16 : 32;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (!array && len) return FLAGSTAT_CUDA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(array) & 1u) != 0) return FLAGSTAT_CUDA_EINVAL;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+
+    bool on_device = false;
+    if (len) {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, array);
+        if (e == cudaSuccess) {
+            on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+        } else {
+            cudaGetLastError();  // plain malloc memory on old drivers
+        }
+    }
+
+    Lane* l = nullptr;
+    int rc = lane_acquire(dev, &l);
+    if (rc) return rc;
+    struct Release {
+        Lane* l;
+        ~Release() { lane_release(l); }
+    } rel{l};
+
+    CK(cudaMemsetAsync(l->d_flags, 0, 32 * sizeof(uint64_t), l->comp));
+    if (on_device || len == 0) {
+        rc = launch(mode, array, len, l->d_flags, l->comp);
+        if (rc) return rc;
+    } else {
+        rc = lane_ensure_staging(l);
+        if (rc) return rc;
+        const uint64_t chunk_rec = kChunkBytes / sizeof(uint16_t);
+        uint64_t off = 0;
+        for (uint64_t c = 0; off < len; ++c) {
+            const int s = (int)(c % kStages);
+            const uint64_t n = (len - off < chunk_rec) ? (len - off) : chunk_rec;
+            if (c >= (uint64_t)kStages) CK(cudaStreamWaitEvent(l->copy, l->consumed[s], 0));
+            CK(cudaMemcpyAsync(l->stage[s], array + off, n * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, l->copy));
+            CK(cudaEventRecord(l->copied[s], l->copy));
+            CK(cudaStreamWaitEvent(l->comp, l->copied[s], 0));
+            rc = launch(mode, l->stage[s], n, l->d_flags, l->comp);
+            if (rc) return rc;
+            CK(cudaEventRecord(l->consumed[s], l->comp));
+            off += n;
+        }
+    }
+    CK(cudaMemcpyAsync(l->h_flags, l->d_flags, nout * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       l->comp));
+    CK(cudaStreamSynchronize(l->comp));
+    std::memcpy(totals, l->h_flags, nout * sizeof(uint64_t));
+    return 0;
+}
+
+uint32_t min_len_init()
+{
+    uint32_t v = g_min_len.load();
+    if (v) return v;
+    v = 65536u;
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_MIN_LEN")) {
+        const unsigned long long t = std::strtoull(e, nullptr, 10);
+        if (t > 0 && t <= 0xFFFFFFFFull) v = (uint32_t)t;
+    }
+    g_min_len.store(v);
+    return v;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// streaming handle
+// ---------------------------------------------------------------------------
+struct FLAGSTAT_cuda_stream {
+    int dev = 0;
+    uint32_t block_records = 0;
+    int n_slots = 0;
+    int next = 0;        // slot handed out by the next acquire
+    int acquired = -1;   // slot currently owned by the producer
+    std::vector<uint16_t*> h;  // pinned
+    std::vector<uint16_t*> d;
+    std::vector<cudaStream_t> st;
+    std::vector<cudaEvent_t> done;
+    std::vector<char> busy;
+    uint64_t* d_flags = nullptr;
+    uint64_t* h_flags = nullptr;
+};
+
+extern "C" {
+
+int FLAGSTAT_cuda_available(void) { return probe_devices() > 0 ? probe_devices() : 0; }
+
+uint32_t FLAGSTAT_cuda_min_len(void) { return min_len_init(); }
+void FLAGSTAT_cuda_set_min_len(uint32_t n) { g_min_len.store(n ? n : 1u); }
+
+int FLAGSTAT_cuda_u64(const uint16_t* array, uint64_t len, uint64_t* flags)
+{
+    if (!flags) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[32];
+    const int rc = run_sync(kFlagstat, array, len, t);
+    if (rc) return rc;
+    for (int i = 0; i < 32; ++i) flags[i] += t[i];
+    return 0;
+}
+
+int FLAGSTAT_cuda(const uint16_t* array, uint32_t len, uint32_t* flags)
+{
+    if (!flags) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[32];
+    const int rc = run_sync(kFlagstat, array, len, t);
+    if (rc) return rc;
+    for (int i = 0; i < 32; ++i) flags[i] += (uint32_t)t[i];  // wraps like the reference's ++
+    return 0;
+}
+
+int FLAGSTAT_cuda_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, void* stream)
+{
+    if (!d_flags || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    return launch(kFlagstat, d_array, len, d_flags, static_cast<cudaStream_t>(stream));
+}
+
+int POSPOPCNT_cuda_u16_u64(const uint16_t* data, uint64_t len, uint64_t* out)
+{
+    if (!out) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[16];
+    const int rc = run_sync(kPospopcnt, data, len, t);
+    if (rc) return rc;
+    for (int i = 0; i < 16; ++i) out[i] = t[i];  // zero-then-count, libalgebra.h:3498
+    return 0;
+}
+
+int POSPOPCNT_cuda_u16(const uint16_t* data, size_t len, uint32_t* out)
+{
+    if (!out) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[16];
+    const int rc = run_sync(kPospopcnt, data, len, t);
+    if (rc) return rc;
+    for (int i = 0; i < 16; ++i) out[i] = (uint32_t)t[i];
+    return 0;
+}
+
+int POSPOPCNT_cuda_device(const uint16_t* d_data, uint64_t len, uint64_t* d_out, void* stream)
+{
+    if (!d_out || (!d_data && len)) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    return launch(kPospopcnt, d_data, len, d_out, static_cast<cudaStream_t>(stream));
+}
+
+// ---- streaming -------------------------------------------------------------
+
+int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** out, int device, uint32_t block_records,
+                              int n_slots)
+{
+    if (!out || block_records == 0) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (device < 0 || device >= g_ndev) return FLAGSTAT_CUDA_EINVAL;
+    if (n_slots == 0) n_slots = 4;
+    if (n_slots < 2 || n_slots > 64) return FLAGSTAT_CUDA_EINVAL;
+    CK(cudaSetDevice(device));
+    FLAGSTAT_cuda_stream* s = new (std::nothrow) FLAGSTAT_cuda_stream();
+    if (!s) return FLAGSTAT_CUDA_ENOMEM;
+    s->dev = device;
+    s->block_records = block_records;
+    s->n_slots = n_slots;
+    s->h.assign(n_slots, nullptr);
+    s->d.assign(n_slots, nullptr);
+    s->st.assign(n_slots, nullptr);
+    s->done.assign(n_slots, nullptr);
+    s->busy.assign(n_slots, 0);
+    const size_t bytes = (size_t)block_records * sizeof(uint16_t);
+    for (int i = 0; i < n_slots; ++i) {
+        CK(cudaMallocHost(&s->h[i], bytes));
+        CK(cudaMalloc(&s->d[i], bytes));
+        CK(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming));
+    }
+    CK(cudaMalloc(&s->d_flags, 32 * sizeof(uint64_t)));
+    CK(cudaMallocHost(&s->h_flags, 32 * sizeof(uint64_t)));
+    CK(cudaMemset(s->d_flags, 0, 32 * sizeof(uint64_t)));
+    *out = s;
+    return 0;
+}
+
+uint16_t* FLAGSTAT_cuda_stream_acquire(FLAGSTAT_cuda_stream* s)
+{
+    if (!s || s->acquired >= 0) return nullptr;
+    const int i = s->next;
+    if (s->busy[i]) {
+        if (cudaEventSynchronize(s->done[i]) != cudaSuccess) return nullptr;
+        s->busy[i] = 0;
+    }
+    s->acquired = i;
+    return s->h[i];
+}
+
+int FLAGSTAT_cuda_stream_submit(FLAGSTAT_cuda_stream* s, uint32_t n_records)
+{
+    if (!s || s->acquired < 0) return FLAGSTAT_CUDA_ESTATE;
+    if (n_records > s->block_records) return FLAGSTAT_CUDA_EINVAL;
+    const int i = s->acquired;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != s->dev) CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(s->d[i], s->h[i], (size_t)n_records * sizeof(uint16_t),
+                       cudaMemcpyHostToDevice, s->st[i]));
+    const int rc = launch(kFlagstat, s->d[i], n_records, s->d_flags, s->st[i]);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->done[i], s->st[i]));
+    s->busy[i] = 1;
+    s->acquired = -1;
+    s->next = (i + 1) % s->n_slots;
+    return 0;
+}
+
+int FLAGSTAT_cuda_stream_push(FLAGSTAT_cuda_stream* s, const uint16_t* block, uint32_t n_records)
+{
+    if (!s || (!block && n_records)) return FLAGSTAT_CUDA_EINVAL;
+    if (n_records > s->block_records) return FLAGSTAT_CUDA_EINVAL;
+    uint16_t* dst = FLAGSTAT_cuda_stream_acquire(s);
+    if (!dst) return FLAGSTAT_CUDA_ESTATE;
+    std::memcpy(dst, block, (size_t)n_records * sizeof(uint16_t));
+    return FLAGSTAT_cuda_stream_submit(s, n_records);
+}
+
+int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags)
+{
+    if (!s || !flags) return FLAGSTAT_CUDA_EINVAL;
+    if (s->acquired >= 0) return FLAGSTAT_CUDA_ESTATE;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != s->dev) CK(cudaSetDevice(s->dev));
+    for (int i = 0; i < s->n_slots; ++i) {
+        CK(cudaStreamSynchronize(s->st[i]));
+        s->busy[i] = 0;
+    }
+    CK(cudaMemcpy(s->h_flags, s->d_flags, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(s->d_flags, 0, 32 * sizeof(uint64_t)));
+    for (int i = 0; i < 32; ++i) flags[i] += s->h_flags[i];
+    return 0;
+}
+
+int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s)
+{
+    if (!s) return FLAGSTAT_CUDA_EINVAL;
+    cudaSetDevice(s->dev);
+    for (int i = 0; i < s->n_slots; ++i) {
+        if (s->st[i]) cudaStreamSynchronize(s->st[i]);
+        if (s->done[i]) cudaEventDestroy(s->done[i]);
+        if (s->st[i]) cudaStreamDestroy(s->st[i]);
+        if (s->h[i]) cudaFreeHost(s->h[i]);
+        if (s->d[i]) cudaFree(s->d[i]);
+    }
+    if (s->d_flags) cudaFree(s->d_flags);
+    if (s->h_flags) cudaFreeHost(s->h_flags);
+    delete s;
+    return 0;
+}
+
+// ---- several GPUs, one process ----------------------------------------------
+
+int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags, int n_devices)
+{
+    if (!flags || (!array && len)) return FLAGSTAT_CUDA_EINVAL;
+    const int have = probe_devices();
+    if (have <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (n_devices <= 0 || n_devices > have) n_devices = have;
+    std::vector<std::thread> th;
+    std::vector<int> rcs(n_devices, 0);
+    std::vector<uint64_t> part((size_t)n_devices * 32, 0);
+    for (int g = 0; g < n_devices; ++g) {
+        const uint64_t lo = (g * (len / n_devices)) & ~7ull;
+        const uint64_t hi = (g == n_devices - 1) ? len : (((g + 1) * (len / n_devices)) & ~7ull);
+        th.emplace_back([=, &rcs, &part]() {
+            cudaError_t e = cudaSetDevice(g);
+            if (e != cudaSuccess) {
+                rcs[g] = (int)e;
+                return;
+            }
+            rcs[g] = run_sync(kFlagstat, array + lo, hi - lo, &part[(size_t)g * 32]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_devices; ++g)
+        if (rcs[g]) return rcs[g];
+    for (int g = 0; g < n_devices; ++g)
+        for (int i = 0; i < 32; ++i) flags[i] += part[(size_t)g * 32 + i];
+    return 0;
+}
+
+// ---- diagnostics / support ----------------------------------------------------
+
+const char* FLAGSTAT_cuda_strerror(int code)
+{
+    switch (code) {
+        case 0: return "success";
+        case FLAGSTAT_CUDA_ENODEV: return "no usable CUDA device";
+        case FLAGSTAT_CUDA_EINVAL: return "invalid argument";
+        case FLAGSTAT_CUDA_ENOMEM: return "host allocation failed";
+        case FLAGSTAT_CUDA_ESTATE: return "stream handle used out of order";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+const char* FLAGSTAT_cuda_version(void) { return "libflagstats_cuda 0.1 (sm_100a)"; }
+
+uint64_t FLAGSTAT_cuda_launch_count(void) { return g_launches.load(); }
+
+int FLAGSTAT_cuda_set_variant(int v) { return g_variant.exchange(v); }
+int FLAGSTAT_cuda_set_ctas_per_sm(int n) { return g_ctas_per_sm.exchange(n); }
+
+int FLAGSTAT_cuda_synth_uniform(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,
+                                uint16_t mask, void* stream)
+{
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 255) / 256 > 148u * 64u ? 148u * 64u : (n + 255) / 256);
+    synth_uniform_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_out, start, n,
+                                                                               seed, mask);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int FLAGSTAT_cuda_synth_hiseqx(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,
+                               uint32_t qcfail_ppm, void* stream)
+{
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 255) / 256 > 148u * 64u ? 148u * 64u : (n + 255) / 256);
+    synth_hiseqx_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_out, start, n, seed,
+                                                                              qcfail_ppm);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+void* FLAGSTAT_cuda_malloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (probe_devices() <= 0) return nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void* FLAGSTAT_cuda_malloc_host(size_t bytes)
+{
+    void* p = nullptr;
+    if (probe_devices() <= 0) return nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+int FLAGSTAT_cuda_free(void* p) { CK(cudaFree(p)); return 0; }
+int FLAGSTAT_cuda_free_host(void* p) { CK(cudaFreeHost(p)); return 0; }
+int FLAGSTAT_cuda_memcpy_h2d(void* d, const void* h, size_t bytes)
+{
+    CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int FLAGSTAT_cuda_memcpy_d2h(void* h, const void* d, size_t bytes)
+{
+    CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int FLAGSTAT_cuda_memset(void* d, int value, size_t bytes)
+{
+    CK(cudaMemset(d, value, bytes));
+    return 0;
+}
+int FLAGSTAT_cuda_sync(void)
+{
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
+                              int pospopcnt_mode, float* ms_per_launch)
+{
+    if (!d_flags || !ms_per_launch || iters <= 0) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    cudaStream_t st;
+    cudaEvent_t e0, e1;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int rc = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters && rc == 0; ++i)
+        rc = launch(pospopcnt_mode ? kPospopcnt : kFlagstat, d_array, len, d_flags, st);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / (float)iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// flagstat_kernels.cuh -- the sm_100a flagstat / pospopcnt kernels.
+//
+// What is computed is the reference's per-record rule
+// (libflagstats.h:118-142, FLAGSTAT_scalar_update) plus the QC-pass record
+// count convention of the kernels FLAGSTATS_u16 dispatches to (:429,1212,1843).
+// How it is computed is B200-specific and shares nothing with the reference's
+// SSE/AVX code:
+//
+//   * two FLAG records stay packed in one 32-bit register from the 128-bit load
+//     to the counters -- nothing is ever unpacked;
+//   * the samtools if / else-if chain is folded into ONE word Y per register by
+//     "mask select": two fp16x2 equality compares on the masked word produce
+//     full-halfword masks directly (they run on the half/FMA pipe and leave the
+//     integer ALU pipe, the real bottleneck, to the LOP3s), the keep-mask is one
+//     LOP3 and applying it a second one;
+//   * Y is fed to a bit-sliced carry-save counter (bitcounter.cuh); a second
+//     counter takes Y & failmask.  QC-pass = all - fail, so the pass side is
+//     never materialised, and the second counter is skipped for every warp
+//     batch that holds no QC-fail record (always, in real data);
+//   * position -> counter mapping happens once per CTA at the very end.
+//
+// Y layout per 16-bit record (positions not listed carry garbage that is
+// simply never read back):
+//   0  G  = PAIRED & ~SEC & ~SUPP & ~UNMAP        (n_pair_map = N(G) - N(pos 3))
+//   1  PROPER & G                                  -> slot 12 n_pair_good
+//   2  UNMAP                                       -> slot 2
+//   3  MUNMAP & G                                  -> slot 13 n_sgltn
+//   6  READ1 & K,  7  READ2 & K   (K = PAIRED & ~SEC & ~SUPP) -> slots 6, 7
+//   8  SECONDARY                                   -> slot 8
+//   9  QCFAIL                                      -> slot 25 (and 9 = n - fail)
+//   10 DUP                                         -> slot 10
+//   11 SUPPLEMENTARY & ~SECONDARY                  -> slot 11
+// Bits 12..15 of the input are ignored, as the scalar reference ignores them.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "bitcounter.cuh"
+
+namespace fsb200 {
+
+constexpr int kThreads = 256;              // threads per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kU = 4;                      // 128-bit loads per thread per batch
+constexpr int kVecPerBatch = kThreads * kU;  // uint4 per CTA batch (16 KiB)
+
+enum Mode { kFlagstat = 0, kPospopcnt = 1 };
+
+// ---------------------------------------------------------------------------
+// mask select
+// ---------------------------------------------------------------------------
+
+// per-halfword equality of two packed fp16 pairs -> 0xFFFF / 0x0000 per half.
+// No .ftz: the operands are subnormal bit patterns and must compare exactly.
+__device__ __forceinline__ uint32_t eq2_mask(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("set.eq.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t ne2_mask(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("set.ne.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// explicit LOP3 with an immediate truth table (a = 0xF0, b = 0xCC, c = 0xAA);
+// spelled out so ptxas keeps the intended 3-input grouping
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
+// Variant H (default): half-pipe compares.  Four ALU-pipe LOP3 per packed pair;
+// the two compares and the shift run on the half / FMA pipes.
+__device__ __forceinline__ uint32_t mask_select_h(uint32_t w)
+{
+    // PAIRED(0) UNMAP(2) SEC(8) SUPP(11) of both records
+    const uint32_t q = w & 0x09050905u;
+    const uint32_t gm = eq2_mask(q, 0x00010001u);  // G: paired, mapped, primary
+    const uint32_t xm = eq2_mask(q, 0x00050005u);  // K & UNMAP: paired, unmapped, primary
+    // G keeps everything, K & UNMAP keeps READ1/READ2 only:  e = gm | (xm & 0x00C0)
+    const uint32_t e = lop3<0xF8>(gm, xm, 0x00C000C0u);
+    // SUPP only counts when not SEC:  wf = w & ~((w << 3) & 0x0800)
+    const uint32_t wf = lop3<0x70>(w, w << 3, 0x08000800u);
+    // always kept: UNMAP SEC QCFAIL DUP SUPP':  y = wf & (e | 0x0F04)
+    return lop3<0xE0>(wf, e, 0x0F040F04u);
+}
+
+__device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
+{
+    return ne2_mask(w & 0x02000200u, 0u);
+}
+
+// Variant I: integer-only formulation (A/B reference for the one above and a
+// safety net should a future toolchain change fp16 subnormal semantics).
+__device__ __forceinline__ uint32_t mask_select_i(uint32_t w)
+{
+    const uint32_t k0 = w & ~(w >> 8) & ~(w >> 11);      // bit0 of each half: K
+    const uint32_t g0 = k0 & ~(w >> 2) & 0x00010001u;    // bit0: G
+    const uint32_t e = (k0 & 0x00010001u) * 0x00C0u + g0 * 0x000Bu;  // K->{6,7} G->{0,1,3}
+    const uint32_t s11 = (w << 3) & 0x08000800u;
+    const uint32_t wf = w & ~s11;
+    return wf & (e | 0x0F040F04u);
+}
+
+__device__ __forceinline__ uint32_t fail_mask_i(uint32_t w)
+{
+    return ((w >> 9) & 0x00010001u) * 0xFFFFu;
+}
+
+template <int VARIANT>
+__device__ __forceinline__ uint32_t mask_select(uint32_t w)
+{
+    return VARIANT == 1 ? mask_select_i(w) : mask_select_h(w);
+}
+
+template <int VARIANT>
+__device__ __forceinline__ uint32_t fail_mask(uint32_t w)
+{
+    return VARIANT == 1 ? fail_mask_i(w) : fail_mask_h(w);
+}
+
+// ---------------------------------------------------------------------------
+// loads
+// ---------------------------------------------------------------------------
+
+// streaming 128-bit load: read-only path, no L1 allocation (every byte is used
+// exactly once)
+__device__ __forceinline__ uint4 ld_stream(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// per-thread state and the batch step
+// ---------------------------------------------------------------------------
+
+using Counter = BitCounter<2, 8>;  // 14 planes: 16 * (2^10 - 2) words per epoch
+
+template <int MODE, int VARIANT>
+struct Lanes {
+    Counter all;
+    Counter fail;   // unused in pospopcnt mode (dead-code eliminated)
+    uint32_t nfail;  // batches absorbed by `fail` this epoch (warp-uniform)
+
+    __device__ __forceinline__ void clear()
+    {
+        all.clear();
+        if (MODE == kFlagstat) fail.clear();
+        nfail = 0u;
+    }
+
+    // one batch = 16 packed words; b = batches absorbed by `all` this epoch
+    __device__ __forceinline__ void step(const uint32_t (&w)[16], uint32_t b)
+    {
+        if (MODE == kPospopcnt) {
+            all.absorb16(w, b);
+            return;
+        }
+        uint32_t y[16];
+        uint32_t any = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            y[i] = mask_select<VARIANT>(w[i]);
+            any |= w[i];
+        }
+        all.absorb16(y, b);
+        // Warp-uniform: does any record of this warp batch have QCFAIL set?  In
+        // real data none has, and the whole second counter is skipped.
+        if (__any_sync(0xffffffffu, (any & 0x02000200u) != 0u)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] &= fail_mask<VARIANT>(w[i]);
+            fail.absorb16(y, nfail);
+            ++nfail;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void unpack4(const uint4 (&v)[kU], uint32_t (&w)[16])
+{
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        w[4 * u + 0] = v[u].x;
+        w[4 * u + 1] = v[u].y;
+        w[4 * u + 2] = v[u].z;
+        w[4 * u + 3] = v[u].w;
+    }
+}
+
+__device__ __forceinline__ void load_batch(uint4 (&v)[kU], const uint4* p)
+{
+#pragma unroll
+    for (int u = 0; u < kU; ++u) v[u] = ld_stream(p + u * kThreads);
+}
+
+// position (within a 16-bit record) -> primary output slot, -1 = not a counter
+__device__ __forceinline__ int slot_of_position(int p)
+{
+    switch (p) {
+        case 0: return 14;  // G; position 3 is subtracted below
+        case 1: return 12;
+        case 2: return 2;
+        case 3: return 13;
+        case 6: return 6;
+        case 7: return 7;
+        case 8: return 8;
+        case 10: return 10;
+        case 11: return 11;
+        default: return -1;
+    }
+}
+
+// Persistent, grid-strided over 16 KiB CTA batches.  out = uint64_t[32]
+// (flagstat) or uint64_t[16] (pospopcnt), ACCUMULATED with 64-bit atomics.
+//
+// Work split: records [0, head) bring the base up to 16-byte alignment, V full
+// 128-bit vectors follow, then < 8 tail records.  NB = V / kVecPerBatch full CTA
+// batches are strided over the grid; the CTA that would own batch NB also takes
+// the < kVecPerBatch left-over vectors (zero padded) and the <= 14 ragged
+// records, as two extra batches in front of its main loop.
+template <int MODE, int VARIANT>
+__global__ void __launch_bounds__(kThreads, 2)
+flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long long* __restrict__ out)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t addr = reinterpret_cast<uint64_t>(base);
+    uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
+    if (head > n) head = n;
+    const uint4* __restrict__ body = reinterpret_cast<const uint4*>(base + head);
+    const uint64_t V = (n - head) >> 3;
+    const uint64_t tail_start = head + (V << 3);
+    const uint64_t ntail = n - tail_start;
+    const uint64_t NB = V / kVecPerBatch;
+    const uint64_t G = gridDim.x;
+
+    Lanes<MODE, VARIANT> st;
+    st.clear();
+    uint32_t b = 0;
+    unsigned long long acc_all = 0ull, acc_fail = 0ull;  // lane j: total of position j
+
+    if (blockIdx.x == (uint32_t)(NB % G)) {
+        uint32_t w[16];
+        {
+            uint4 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const uint64_t idx = NB * kVecPerBatch + (uint64_t)u * kThreads + tid;
+                v[u] = (idx < V) ? ld_stream(body + idx) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            unpack4(v, w);
+        }
+        st.step(w, b);
+        ++b;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+        if (tid < head) w[0] = base[tid];
+        else if (tid - head < ntail) w[0] = base[tail_start + (tid - head)];
+        st.step(w, b);
+        ++b;
+    }
+
+    uint64_t bb = blockIdx.x;
+    uint4 bufA[kU], bufB[kU];
+    const uint4* __restrict__ tp = body + tid;
+    if (bb < NB) load_batch(bufA, tp + bb * kVecPerBatch);
+
+    do {
+        // one epoch: at most Counter::kMaxBatches batches, then expand
+        for (;;) {
+            if (bb >= NB || b >= Counter::kMaxBatches) break;
+            {
+                const uint64_t nb = bb + G;
+                if (nb < NB) load_batch(bufB, tp + nb * kVecPerBatch);
+                uint32_t w[16];
+                unpack4(bufA, w);
+                st.step(w, b);
+                ++b;
+                bb = nb;
+            }
+            if (bb >= NB) break;
+            {
+                const uint64_t nb = bb + G;
+                if (nb < NB) load_batch(bufA, tp + nb * kVecPerBatch);
+                uint32_t w[16];
+                unpack4(bufB, w);
+                st.step(w, b);
+                ++b;
+                bb = nb;
+            }
+        }
+        acc_all += st.all.flush_warp(b, lane);
+        if (MODE == kFlagstat && st.nfail != 0u) acc_fail += st.fail.flush_warp(st.nfail, lane);
+        st.clear();
+        b = 0;
+    } while (bb < NB);
+
+    // CTA reduction: lanes hold per-position totals of their warp
+    __shared__ unsigned long long s_all[kWarps][32];
+    __shared__ unsigned long long s_fail[kWarps][32];
+    s_all[warp][lane] = acc_all;
+    s_fail[warp][lane] = acc_fail;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long a = 0ull, f = 0ull;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+            a += s_all[i][lane];
+            f += s_fail[i][lane];
+        }
+        // fold the high-halfword record onto the low one
+        a += __shfl_down_sync(0xffffffffu, a, 16);
+        f += __shfl_down_sync(0xffffffffu, f, 16);
+        if (lane < 16) {
+            if (MODE == kPospopcnt) {
+                if (a) atomicAdd(out + lane, a);
+            } else {
+                const int slot = slot_of_position((int)lane);
+                if (slot >= 0) {
+                    if (a - f) atomicAdd(out + slot, a - f);
+                    if (f) atomicAdd(out + 16 + slot, f);
+                    if (lane == 3) {  // n_pair_map = N(G) - N(G & MUNMAP)
+                        if (a - f) atomicAdd(out + 14, 0ull - (a - f));
+                        if (f) atomicAdd(out + 30, 0ull - f);
+                    }
+                } else if (lane == 9) {  // a == number of QC-fail records
+                    unsigned long long pass = 0ull - a;
+                    if (blockIdx.x == 0) pass += n;
+                    if (a) atomicAdd(out + 25, a);
+                    if (pass) atomicAdd(out + 9, pass);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace fsb200

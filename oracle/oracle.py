@@ -1,0 +1,315 @@
+"""ctypes front-end of the test oracle.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Nothing under
+libflagstats_b200/ may import this module.
+
+Two back-ends:
+
+* ``liboracle.so``  -- our C restatement (oracle/flagstat_oracle.c).  Built on
+  demand with the host gcc; needs nothing outside this repo.
+* ``oracle/_ref/libflagstats_ref_*.so`` -- the UNMODIFIED reference compiled
+  from /root/reference by oracle/Makefile.  Prebuilt in the dev container and
+  shipped to the GPU box; absent => ``reference()`` returns None and callers
+  fall back to the restatement (kind "port").
+
+A third, numpy-vectorised restatement (`numpy_flagstat`) is kept as an
+independent cross-check that is fast enough for 10^8..10^9 records.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+_u16p = C.POINTER(C.c_uint16)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+CORE19 = (2, 6, 7, 8, 10, 11, 12, 13, 14, 18, 22, 23, 24, 25, 26, 27, 28, 29, 30)
+"""Slots every correct reference kernel agrees on (SURVEY.md section 8a)."""
+CORE20 = CORE19 + (9,)
+"""CORE19 plus slot 9 under the SIMD convention -- what FLAGSTAT_cuda writes."""
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def _as_u16(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint16)
+    return a
+
+
+# --------------------------------------------------------------------------
+# restatement
+# --------------------------------------------------------------------------
+_oracle = None
+
+
+def build_oracle(force: bool = False) -> str:
+    so = os.path.join(HERE, "liboracle.so")
+    src = os.path.join(HERE, "flagstat_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(
+            ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", so, src]
+        )
+    return so
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        for name in ("oracle_flagstat_scalar_u64", "oracle_flagstat_simd_u64",
+                     "oracle_flagstat_maskselect_u64"):
+            f = getattr(lib, name)
+            f.argtypes = [_u16p, C.c_uint64, _u64p]
+            f.restype = C.c_int
+        for name in ("oracle_flagstat_scalar_u32", "oracle_flagstat_simd_u32"):
+            f = getattr(lib, name)
+            f.argtypes = [_u16p, C.c_uint32, _u32p]
+            f.restype = C.c_int
+        lib.oracle_mask_select.argtypes = [C.c_uint16]
+        lib.oracle_mask_select.restype = C.c_uint16
+        lib.oracle_pospopcnt_u16_u64.argtypes = [_u16p, C.c_uint64, _u64p]
+        lib.oracle_pospopcnt_u16.argtypes = [_u16p, C.c_size_t, _u32p]
+        lib.oracle_synth_uniform.argtypes = [_u16p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint16]
+        lib.oracle_synth_uniform.restype = None
+        lib.oracle_synth_hiseqx.argtypes = [_u16p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+        lib.oracle_synth_hiseqx.restype = None
+        lib.oracle_hiseqx_n.restype = C.c_uint64
+        lib.oracle_hiseqx_m.restype = C.c_uint64
+        _oracle = lib
+    return _oracle
+
+
+def flagstat_scalar(a, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    """Scalar convention, libflagstats.h:170-176 (slot 9 untouched)."""
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint64) if flags is None else flags
+    oracle().oracle_flagstat_scalar_u64(_ptr(a, _u16p), a.size, _ptr(f, _u64p))
+    return f
+
+
+def flagstat_simd(a, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    """SIMD convention (slot 9 += n_pass), libflagstats.h:429,1212,1843."""
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint64) if flags is None else flags
+    oracle().oracle_flagstat_simd_u64(_ptr(a, _u16p), a.size, _ptr(f, _u64p))
+    return f
+
+
+def flagstat_simd_u32(a, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint32) if flags is None else flags
+    oracle().oracle_flagstat_simd_u32(_ptr(a, _u16p), a.size, _ptr(f, _u32p))
+    return f
+
+
+def flagstat_maskselect(a) -> np.ndarray:
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint64)
+    oracle().oracle_flagstat_maskselect_u64(_ptr(a, _u16p), a.size, _ptr(f, _u64p))
+    return f
+
+
+def mask_select(v: int) -> int:
+    return int(oracle().oracle_mask_select(int(v) & 0xFFFF))
+
+
+def pospopcnt(a) -> np.ndarray:
+    a = _as_u16(a)
+    out = np.empty(16, np.uint64)
+    oracle().oracle_pospopcnt_u16_u64(_ptr(a, _u16p), a.size, _ptr(out, _u64p))
+    return out
+
+
+def synth_uniform(start: int, n: int, seed: int = 0, mask: int = 0x0FFF) -> np.ndarray:
+    out = np.empty(n, np.uint16)
+    oracle().oracle_synth_uniform(_ptr(out, _u16p), start, n, seed, mask)
+    return out
+
+
+def synth_hiseqx(start: int, n: int, seed: int = 0, qcfail_ppm: int = 0) -> np.ndarray:
+    out = np.empty(n, np.uint16)
+    oracle().oracle_synth_hiseqx(_ptr(out, _u16p), start, n, seed, qcfail_ppm)
+    return out
+
+
+HISEQX_N = 824_541_892
+
+
+def numpy_flagstat(a) -> np.ndarray:
+    """Vectorised restatement of libflagstats.h:118-142 + the slot-9 rule
+    (:429).  Independent of the C code above; used as a cross-check and for
+    arrays too large for the scalar loop."""
+    a = _as_u16(a)
+    out = np.zeros(32, np.uint64)
+    step = 1 << 24
+    for lo in range(0, a.size, step):
+        x = a[lo:lo + step]
+        bit = lambda b: (x >> b) & 1 == 1  # noqa: E731
+        fail = bit(9)
+        sec, supp, paired = bit(8), bit(11), bit(0)
+        unmap, munmap = bit(2), bit(3)
+        third = ~sec & ~supp & paired
+        ind = {
+            2: unmap, 10: bit(10), 8: sec, 11: ~sec & supp,
+            12: third & bit(1) & ~unmap, 6: third & bit(6), 7: third & bit(7),
+            13: third & munmap & ~unmap, 14: third & ~unmap & ~munmap,
+        }
+        for j, m in ind.items():
+            nf = int(np.count_nonzero(m & fail))
+            out[16 + j] += np.uint64(nf)
+            out[j] += np.uint64(int(np.count_nonzero(m)) - nf)
+        nfail = int(np.count_nonzero(fail))
+        out[25] += np.uint64(nfail)
+        out[9] += np.uint64(x.size - nfail)
+    return out
+
+
+# --------------------------------------------------------------------------
+# the real reference, when its prebuilt shim is available
+# --------------------------------------------------------------------------
+_ref = None
+_ref_tried = False
+
+
+def _cpu_flags() -> set:
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+_V3 = {"avx", "avx2", "bmi1", "bmi2", "f16c", "fma", "abm", "movbe"}
+_V4 = _V3 | {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"}
+
+
+def reference_path() -> Optional[str]:
+    flags = _cpu_flags()
+    order = []
+    if _V4 <= flags:
+        order.append("v4")
+    if _V3 <= flags:
+        order.append("v3")
+    order.append("generic")
+    for v in order:
+        p = os.path.join(REF_DIR, f"libflagstats_ref_{v}.so")
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def build_reference() -> bool:
+    """(Re)build oracle/_ref from /root/reference when that tree is present."""
+    if not os.path.exists("/root/reference/libflagstats.h"):
+        return False
+    subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    return True
+
+
+def reference():
+    """ctypes handle of the unmodified reference, or None if not prebuilt."""
+    global _ref, _ref_tried
+    if _ref_tried:
+        return _ref
+    _ref_tried = True
+    p = reference_path()
+    if p is None:
+        return None
+    lib = C.CDLL(p)
+    lib.ref_flagstat.argtypes = [C.c_char_p, _u16p, C.c_uint32, _u32p]
+    lib.ref_flagstat.restype = C.c_int
+    lib.ref_FLAGSTATS_u16.argtypes = [_u16p, C.c_uint32, _u32p]
+    lib.ref_FLAGSTATS_u16.restype = C.c_uint64
+    lib.ref_dispatch_name.argtypes = [C.c_uint32]
+    lib.ref_dispatch_name.restype = C.c_char_p
+    lib.ref_pospopcnt_u16.argtypes = [_u16p, C.c_size_t, _u32p]
+    lib.ref_pospopcnt_u16.restype = C.c_int
+    lib.ref_kernel_name.argtypes = [C.c_int]
+    lib.ref_kernel_name.restype = C.c_char_p
+    lib.ref_kernel_runnable.argtypes = [C.c_char_p]
+    lib.ref_flagstat_mt.argtypes = [C.c_char_p, _u16p, C.c_uint64, C.c_int, _u64p,
+                                    C.POINTER(C.c_double)]
+    lib.ref_flagstat_mt.restype = C.c_int
+    lib._path = p
+    _ref = lib
+    return _ref
+
+
+REF_CORRECT_KERNELS = ("scalar", "sse4", "sse4_improved", "sse4_improved2", "avx2", "avx512",
+                       "avx512_improved", "avx512_improved2", "avx512_improved3")
+"""Kernels that agree with FLAGSTAT_scalar on CORE19 (SURVEY.md section 2.2);
+avx2_improved{,2} and avx512_improved4 are reference defects."""
+
+
+def ref_kernels(runnable_only: bool = True):
+    lib = reference()
+    if lib is None:
+        return []
+    names = [lib.ref_kernel_name(i).decode() for i in range(lib.ref_num_kernels())]
+    if runnable_only:
+        names = [n for n in names if lib.ref_kernel_runnable(n.encode())]
+    return names
+
+
+def ref_flagstat(name: str, a, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    lib = reference()
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint32) if flags is None else flags
+    rc = lib.ref_flagstat(name.encode(), _ptr(a, _u16p), a.size, _ptr(f, _u32p))
+    if rc != 0:
+        raise RuntimeError(f"reference kernel {name!r}: rc={rc}")
+    return f
+
+
+def ref_flagstats_u16(a, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    lib = reference()
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint32) if flags is None else flags
+    lib.ref_FLAGSTATS_u16(_ptr(a, _u16p), a.size, _ptr(f, _u32p))
+    return f
+
+
+def ref_dispatch_name(n: int) -> str:
+    return reference().ref_dispatch_name(n).decode()
+
+
+def ref_pospopcnt(a) -> np.ndarray:
+    lib = reference()
+    a = _as_u16(a)
+    out = np.full(16, 0xDEADBEEF, np.uint32)  # the reference memsets it
+    lib.ref_pospopcnt_u16(_ptr(a, _u16p), a.size, _ptr(out, _u32p))
+    return out
+
+
+def ref_flagstat_mt(name: str, a, nthreads: int):
+    """(flags u64[32], seconds) of the range-sharded pthread wrapper."""
+    lib = reference()
+    a = _as_u16(a)
+    f = np.zeros(32, np.uint64)
+    sec = C.c_double(0.0)
+    rc = lib.ref_flagstat_mt(name.encode(), _ptr(a, _u16p), a.size, nthreads,
+                             _ptr(f, _u64p), C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"reference kernel {name!r}: rc={rc}")
+    return f, sec.value
+
+
+def best_reference_kernel() -> Optional[str]:
+    """What FLAGSTATS_get_function returns for a large block on this CPU."""
+    if reference() is None:
+        return None
+    return ref_dispatch_name(1 << 20)

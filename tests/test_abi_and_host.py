@@ -1,0 +1,103 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every
+symbol include/flagstats_cuda.h declares, refuses to compute without a device
+(no CPU fallback), and the Python host mirror behaves like pyflagstats."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fs():
+    from libflagstats_b200 import build
+    build.build()
+    import libflagstats_b200 as m
+    return m
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "flagstats_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b((?:FLAGSTAT|POSPOPCNT)_cuda\w*)\s*\(", src)
+    return sorted(set(n for n in names if n != "FLAGSTATS_cuda_func"))
+
+
+def test_library_exports_every_declared_symbol(fs):
+    from libflagstats_b200 import _capi
+    names = declared_symbols()
+    assert len(names) >= 30
+    handle = C.CDLL(_capi.SO_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/flagstats_cuda.h but not exported"
+    assert sorted(_capi.SIGNATURES) == names, "ctypes table and header drifted apart"
+    assert b"sm_100a" in fs.lib().FLAGSTAT_cuda_version()
+
+
+def test_no_cpu_fallback_without_a_device(fs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert fs.available() == 0
+    a = np.arange(4096, dtype=np.uint16)
+    with pytest.raises(fs.FlagstatCudaError) as ei:
+        fs.flagstat_u64(a)
+    assert ei.value.code == -1
+    f = np.full(32, 5, np.uint32)
+    assert fs.lib().FLAGSTAT_cuda(a.ctypes.data, a.size, f.ctypes.data_as(C.POINTER(C.c_uint32))) == -1
+    assert (f == 5).all()  # flags untouched on failure
+    assert fs.lib().FLAGSTAT_cuda_strerror(-1) == b"no usable CUDA device"
+    with pytest.raises(fs.FlagstatCudaError):
+        fs.BlockStream(0)
+
+
+def test_python_surface_mirrors_pyflagstats_errors(fs):
+    # python/libflagstats.pyx:9-13: type and dtype are checked before anything else
+    with pytest.raises(ValueError, match="numpy.ndarray"):
+        fs.flagstats([1, 2, 3])
+    with pytest.raises(ValueError, match="uint16"):
+        fs.flagstats(np.arange(10, dtype=np.int16))
+
+
+def test_result_dict_schema_matches_pyx(fs, golden):
+    e = golden["kat_e"]
+    f = np.array(e["cuda_expected"], np.uint64)
+    d = fs.counters_to_dict(f, e["spec"]["n"])
+    assert list(d) == ["n_values", "passed", "failed"]
+    assert list(d["passed"])[:15] == fs.SAM_FLAG_NAMES and list(d["failed"]) == fs.SAM_FLAG_NAMES
+    assert int(d["passed"]["mapped"]) == e["readme"]["mapped"]
+    assert int(d["passed"]["paired_in_seq"]) == e["readme"]["paired"]
+    rep = fs.samtools_report(f).splitlines()
+    # README.md:179-189, the FLAG-derivable lines
+    assert rep[0] == "824541892 + 0 in total (QC-passed reads + QC-failed reads)"
+    assert rep[1] == "0 + 0 secondary" and rep[2] == "5393628 + 0 supplementary"
+    assert rep[3] == "0 + 0 duplicates" and rep[4] == "805383403 + 0 mapped (97.68% : N/A)"
+    assert rep[5] == "819148264 + 0 paired in sequencing"
+    assert rep[6] == "409574132 + 0 read1" and rep[7] == "409574132 + 0 read2"
+    assert rep[8] == "781085884 + 0 properly paired (95.35% : N/A)"
+    assert rep[9] == "797950890 + 0 with itself and mate mapped"
+    assert rep[10] == "2038885 + 0 singletons (0.25% : N/A)"
+
+
+def test_shard_ranges_tile_the_column():
+    from libflagstats_b200.sharded import shard_range
+    for n in (0, 1, 7, 8, 9, 1000, 824541892, 2 ** 34, 2 ** 34 + 5):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_range(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (a, b), (c, d) in zip(edges, edges[1:]):
+                assert b == c and a <= b
+            assert all(lo % 8 == 0 for lo, _ in edges)
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_kat_e_shards_in_golden_use_the_same_ranges(golden):
+    from libflagstats_b200.sharded import shard_range
+    n = golden["kat_e"]["spec"]["n"]
+    for r, s in enumerate(golden["kat_e"]["shards8"]):
+        lo, hi = shard_range(n, 8, r)
+        assert (lo, hi - lo) == (s["start"], s["n"])
