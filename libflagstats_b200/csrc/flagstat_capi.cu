@@ -203,11 +203,20 @@ int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
     CK(cudaGetDevice(&dev));
 
     bool on_device = false;
+    struct Restore {  // device-resident input runs on the device that owns it
+        int dev = -1;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore;
     if (len) {
         cudaPointerAttributes attr;
         cudaError_t e = cudaPointerGetAttributes(&attr, array);
         if (e == cudaSuccess) {
             on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+            if (attr.type == cudaMemoryTypeDevice && attr.device != dev) {
+                CK(cudaSetDevice(attr.device));
+                restore.dev = dev;
+                dev = attr.device;
+            }
         } else {
             cudaGetLastError();  // plain malloc memory on old drivers
         }
@@ -221,9 +230,15 @@ int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
         ~Release() { lane_release(l); }
     } rel{l};
 
-    CK(cudaMemsetAsync(l->d_flags, 0, 32 * sizeof(uint64_t), l->comp));
+    // Device-resident input: the caller's producer kernels were enqueued on
+    // streams this library knows nothing about.  Run on the LEGACY default
+    // stream, which is ordered after all prior work on blocking streams (the
+    // semantics a synchronous C call on a device pointer is expected to have).
+    // Host input is ready by definition, so it uses the lane's private streams.
+    cudaStream_t comp = (on_device && len) ? cudaStreamLegacy : l->comp;
+    CK(cudaMemsetAsync(l->d_flags, 0, 32 * sizeof(uint64_t), comp));
     if (on_device || len == 0) {
-        rc = launch(mode, array, len, l->d_flags, l->comp);
+        rc = launch(mode, array, len, l->d_flags, comp);
         if (rc) return rc;
     } else {
         rc = lane_ensure_staging(l);
@@ -237,16 +252,16 @@ int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
             CK(cudaMemcpyAsync(l->stage[s], array + off, n * sizeof(uint16_t),
                                cudaMemcpyHostToDevice, l->copy));
             CK(cudaEventRecord(l->copied[s], l->copy));
-            CK(cudaStreamWaitEvent(l->comp, l->copied[s], 0));
-            rc = launch(mode, l->stage[s], n, l->d_flags, l->comp);
+            CK(cudaStreamWaitEvent(comp, l->copied[s], 0));
+            rc = launch(mode, l->stage[s], n, l->d_flags, comp);
             if (rc) return rc;
-            CK(cudaEventRecord(l->consumed[s], l->comp));
+            CK(cudaEventRecord(l->consumed[s], comp));
             off += n;
         }
     }
     CK(cudaMemcpyAsync(l->h_flags, l->d_flags, nout * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                       l->comp));
-    CK(cudaStreamSynchronize(l->comp));
+                       comp));
+    CK(cudaStreamSynchronize(comp));
     std::memcpy(totals, l->h_flags, nout * sizeof(uint64_t));
     return 0;
 }

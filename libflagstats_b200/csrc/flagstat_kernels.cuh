@@ -93,9 +93,12 @@ __device__ __forceinline__ uint32_t mask_select_h(uint32_t w)
     return lop3<0xE0>(wf, e, 0x0F040F04u);
 }
 
+// QCFAIL (bit 9) of each record spread over its whole halfword: the shift (FMA
+// pipe) puts the bit in the sign position of the odd bytes, PRMT's
+// sign-replicate mode (selector nibbles 0x9 / 0xB) does the broadcast.
 __device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
 {
-    return ne2_mask(w & 0x02000200u, 0u);
+    return __byte_perm(w << 6, 0u, 0xBB99u);
 }
 
 // Variant I: integer-only formulation (A/B reference for the one above and a
