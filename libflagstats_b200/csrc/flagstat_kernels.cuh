@@ -98,7 +98,10 @@ __device__ __forceinline__ uint32_t mask_select_h(uint32_t w)
 // sign-replicate mode (selector nibbles 0x9 / 0xB) does the broadcast.
 __device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
 {
-    return __byte_perm(w << 6, 0u, 0xBB99u);
+    // inline PTX: __byte_perm() documents selector bit 3 as ignored, prmt.b32 does not
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w << 6), "r"(0u), "r"(0xBB99u));
+    return d;
 }
 
 // Variant I: integer-only formulation (A/B reference for the one above and a

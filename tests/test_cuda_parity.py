@@ -173,16 +173,16 @@ def test_kat_e_full_hiseqx_on_device(cuda_lib, golden):
 
 
 def test_more_than_2_pow_32_records_and_epoch_flush(cuda_lib, golden):
-    """5 x 824,541,892 = 4,122,709,460 records (> 2^32, 8.2 GB): the generator is
-    periodic, so the answer is exactly 5 x KAT-E; per-thread input exceeds one
+    """6 x 824,541,892 = 4,947,251,352 records (> 2^32, 9.9 GB): the generator is
+    periodic, so the answer is exactly 6 x KAT-E; per-thread input exceeds one
     counter epoch, exercising the in-kernel flush; u64 length entry."""
     fs = cuda_lib
     from libflagstats_b200 import synth
-    n = 5 * O.HISEQX_N
+    n = 6 * O.HISEQX_N
     assert n > 2 ** 32
     d = synth.hiseqx_device(n)
     got = fs.flagstat_u64(d)
-    assert got.tolist() == [5 * x for x in golden["kat_e"]["cuda_expected"]]
+    assert got.tolist() == [6 * x for x in golden["kat_e"]["cuda_expected"]]
     prev = fs.lib().FLAGSTAT_cuda_set_ctas_per_sm(1)
     try:
         assert fs.flagstat_u64(d).tolist() == got.tolist()
