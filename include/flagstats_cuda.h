@@ -69,7 +69,8 @@ int FLAGSTAT_cuda_available(void);
 
 /* Length at or above which FLAGSTATS_get_function should pick FLAGSTAT_cuda for
  * HOST data (the analogue of the 1024/512/256 thresholds, :3000,3006,3016).
- * Defaults to 65536; env FLAGSTAT_CUDA_MIN_LEN or the setter override it. */
+ * Defaults to 262144 (where one PCIe round trip starts to beat one AVX-512 core);
+ * env FLAGSTAT_CUDA_MIN_LEN or the setter override it. */
 uint32_t FLAGSTAT_cuda_min_len(void);
 void FLAGSTAT_cuda_set_min_len(uint32_t n);
 

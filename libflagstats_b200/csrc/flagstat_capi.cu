@@ -270,7 +270,7 @@ uint32_t min_len_init()
 {
     uint32_t v = g_min_len.load();
     if (v) return v;
-    v = 65536u;
+    v = 262144u;
     if (const char* e = std::getenv("FLAGSTAT_CUDA_MIN_LEN")) {
         const unsigned long long t = std::strtoull(e, nullptr, 10);
         if (t > 0 && t <= 0xFFFFFFFFull) v = (uint32_t)t;
