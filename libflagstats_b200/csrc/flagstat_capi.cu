@@ -17,6 +17,7 @@
 
 #include "../../include/flagstats_cuda.h"
 #include "flagstat_kernels.cuh"
+#include "flagstat_kernel_tma.cuh"
 #include "synth.cuh"
 
 namespace {
@@ -38,9 +39,40 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
         if (e_ != cudaSuccess) return (int)e_; \
     } while (0)
 
+// Kernel variants (FLAGSTAT_cuda_set_variant):
+//   0  register-staged LDG.128 double buffer, fp16x2-compare mask select (default)
+//   1  same loads, integer-only mask select (A/B reference)
+//   2  TMA (cp.async.bulk) shared-memory ring, 4 stages
+//   3  TMA ring, 6 stages
+//   4  TMA ring, 4 stages, registers capped for 3 CTAs/SM
+//   5  TMA ring, 3 stages, registers capped for 3 CTAs/SM
+constexpr int kNumVariants = 6;
+using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*);
+
+struct KernelCfg {
+    KernelFn fn[2];   // [mode]
+    int threads;
+    size_t smem;
+};
+
+constexpr size_t tma_smem(int stages) { return (size_t)stages * kStageBytes + 2u * stages * 8u; }
+
+const KernelCfg kKernels[kNumVariants] = {
+    {{flagstat_kernel<kFlagstat, 0>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
+    {{flagstat_kernel<kFlagstat, 1>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
+    {{flagstat_kernel_tma<kFlagstat, 0, 4, 2>, flagstat_kernel_tma<kPospopcnt, 0, 4, 2>},
+     kThreads + 32, tma_smem(4)},
+    {{flagstat_kernel_tma<kFlagstat, 0, 6, 2>, flagstat_kernel_tma<kPospopcnt, 0, 6, 2>},
+     kThreads + 32, tma_smem(6)},
+    {{flagstat_kernel_tma<kFlagstat, 0, 4, 3>, flagstat_kernel_tma<kPospopcnt, 0, 4, 3>},
+     kThreads + 32, tma_smem(4)},
+    {{flagstat_kernel_tma<kFlagstat, 0, 3, 3>, flagstat_kernel_tma<kPospopcnt, 0, 3, 3>},
+     kThreads + 32, tma_smem(3)},
+};
+
 struct DeviceInfo {
     int sms = 0;
-    int occ[2][2] = {{0, 0}, {0, 0}};  // [mode][variant] resident CTAs per SM
+    int occ[kNumVariants][2];  // resident CTAs per SM
     bool ok = false;
 };
 
@@ -62,18 +94,6 @@ int probe_devices()
     return n;
 }
 
-template <int MODE, int VARIANT>
-int occupancy()
-{
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flagstat_kernel<MODE, VARIANT>, kThreads,
-                                                      0) != cudaSuccess) {
-        cudaGetLastError();
-        nb = 2;
-    }
-    return nb < 1 ? 1 : nb;
-}
-
 int device_info(int dev, DeviceInfo** out)
 {
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
@@ -85,10 +105,22 @@ int device_info(int dev, DeviceInfo** out)
         CK(cudaGetDevice(&cur));
         if (cur != dev) CK(cudaSetDevice(dev));
         CK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-        d.occ[0][0] = occupancy<kFlagstat, 0>();
-        d.occ[0][1] = occupancy<kFlagstat, 1>();
-        d.occ[1][0] = occupancy<kPospopcnt, 0>();
-        d.occ[1][1] = d.occ[1][0];
+        for (int v = 0; v < kNumVariants; ++v)
+            for (int m = 0; m < 2; ++m) {
+                const KernelCfg& k = kKernels[v];
+                if (k.smem > 48u * 1024u)
+                    CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(k.fn[m]),
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)k.smem));
+                int nb = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &nb, reinterpret_cast<const void*>(k.fn[m]), k.threads, k.smem) !=
+                    cudaSuccess) {
+                    cudaGetLastError();
+                    nb = 2;
+                }
+                d.occ[v][m] = nb < 1 ? 1 : nb;
+            }
         if (cur != dev && cur >= 0) CK(cudaSetDevice(cur));
         d.ok = true;
     }
@@ -105,26 +137,21 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
     DeviceInfo* di = nullptr;
     int rc = device_info(dev, &di);
     if (rc) return rc;
-    const int variant = g_variant.load() == 1 ? 1 : 0;
+    int variant = g_variant.load();
+    if (variant < 0 || variant >= kNumVariants) variant = 0;
+    const KernelCfg& k = kKernels[variant];
 
     const uint64_t addr = reinterpret_cast<uintptr_t>(d_array);
     uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
     if (head > n) head = n;
     const uint64_t nb = ((n - head) >> 3) / kVecPerBatch;
     int per_sm = g_ctas_per_sm.load();
-    if (per_sm <= 0) per_sm = di->occ[mode][variant];
+    if (per_sm <= 0) per_sm = di->occ[variant][mode];
     uint64_t grid = (uint64_t)per_sm * (uint64_t)di->sms;
     if (grid > nb + 1) grid = nb + 1;
 
-    unsigned long long* out = reinterpret_cast<unsigned long long*>(d_out);
-    const dim3 g((unsigned)grid), b(kThreads);
-    if (mode == kPospopcnt) {
-        flagstat_kernel<kPospopcnt, 0><<<g, b, 0, st>>>(d_array, n, out);
-    } else if (variant == 1) {
-        flagstat_kernel<kFlagstat, 1><<<g, b, 0, st>>>(d_array, n, out);
-    } else {
-        flagstat_kernel<kFlagstat, 0><<<g, b, 0, st>>>(d_array, n, out);
-    }
+    k.fn[mode]<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
+        d_array, n, reinterpret_cast<unsigned long long*>(d_out));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
     return 0;

@@ -231,6 +231,36 @@ __device__ __forceinline__ int slot_of_position(int p)
     }
 }
 
+// Lanes 0..15 of one warp hold the CTA totals of tree position `lane`
+// (a = all records, f = QC-fail records).  Map positions to the reference's
+// counter slots and add them to out[] with 64-bit atomics; differences are
+// taken mod 2^64, which is exact for sums of non-negative counts.
+template <int MODE>
+__device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ out, uint32_t lane,
+                                              unsigned long long a, unsigned long long f,
+                                              uint64_t n)
+{
+    if (lane >= 16) return;
+    if (MODE == kPospopcnt) {
+        if (a) atomicAdd(out + lane, a);
+        return;
+    }
+    const int slot = slot_of_position((int)lane);
+    if (slot >= 0) {
+        if (a - f) atomicAdd(out + slot, a - f);
+        if (f) atomicAdd(out + 16 + slot, f);
+        if (lane == 3) {  // n_pair_map = N(G) - N(G & MUNMAP)
+            if (a - f) atomicAdd(out + 14, 0ull - (a - f));
+            if (f) atomicAdd(out + 30, 0ull - f);
+        }
+    } else if (lane == 9) {  // a == number of QC-fail records
+        unsigned long long pass = 0ull - a;
+        if (blockIdx.x == 0) pass += n;  // slot 9 = n - n_fail, libflagstats.h:429
+        if (a) atomicAdd(out + 25, a);
+        if (pass) atomicAdd(out + 9, pass);
+    }
+}
+
 // Persistent, grid-strided over 16 KiB CTA batches.  out = uint64_t[32]
 // (flagstat) or uint64_t[16] (pospopcnt), ACCUMULATED with 64-bit atomics.
 //
@@ -331,26 +361,7 @@ flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long lon
         // fold the high-halfword record onto the low one
         a += __shfl_down_sync(0xffffffffu, a, 16);
         f += __shfl_down_sync(0xffffffffu, f, 16);
-        if (lane < 16) {
-            if (MODE == kPospopcnt) {
-                if (a) atomicAdd(out + lane, a);
-            } else {
-                const int slot = slot_of_position((int)lane);
-                if (slot >= 0) {
-                    if (a - f) atomicAdd(out + slot, a - f);
-                    if (f) atomicAdd(out + 16 + slot, f);
-                    if (lane == 3) {  // n_pair_map = N(G) - N(G & MUNMAP)
-                        if (a - f) atomicAdd(out + 14, 0ull - (a - f));
-                        if (f) atomicAdd(out + 30, 0ull - f);
-                    }
-                } else if (lane == 9) {  // a == number of QC-fail records
-                    unsigned long long pass = 0ull - a;
-                    if (blockIdx.x == 0) pass += n;
-                    if (a) atomicAdd(out + 25, a);
-                    if (pass) atomicAdd(out + 9, pass);
-                }
-            }
-        }
+        emit_counters<MODE>(out, lane, a, f, n);
     }
 }
 
