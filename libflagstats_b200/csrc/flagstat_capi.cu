@@ -29,7 +29,7 @@ constexpr size_t kChunkBytes = 32u << 20;  // staging chunk for host data
 constexpr int kStages = 3;
 
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_variant{0};
+std::atomic<int> g_variant{-1};
 std::atomic<int> g_ctas_per_sm{0};
 std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
 
@@ -39,14 +39,17 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
         if (e_ != cudaSuccess) return (int)e_; \
     } while (0)
 
-// Kernel variants (FLAGSTAT_cuda_set_variant):
-//   0  register-staged LDG.128 double buffer, fp16x2-compare mask select (default)
-//   1  same loads, integer-only mask select (A/B reference)
-//   2  TMA (cp.async.bulk) shared-memory ring, 4 stages
-//   3  TMA ring, 6 stages
-//   4  TMA ring, 4 stages, registers capped for 3 CTAs/SM
-//   5  TMA ring, 3 stages, registers capped for 3 CTAs/SM
-constexpr int kNumVariants = 6;
+// Kernel variants (FLAGSTAT_cuda_set_variant / env FLAGSTAT_CUDA_VARIANT).  All
+// compute the same thing; they differ in how bytes reach the registers and are
+// kept selectable for A/B measurement (profiles/, tools/perf_sweep.py):
+//   0  thread-private cp.async ring, depth 4 (64 KiB/CTA), fp16x2-compare mask  (default)
+//   1  same ring, integer-only mask select (cross-check of the fp16 compares)
+//   2  register-staged LDG.128 double buffer
+//   3  TMA (cp.async.bulk + mbarrier) shared-memory ring, 4 stages, producer warp
+//   4  TMA ring, 6 stages
+//   5  cp.async ring, depth 2
+//   6  cp.async ring, depth 4, registers capped for 3 CTAs/SM
+constexpr int kNumVariants = 7;
 using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*);
 
 struct KernelCfg {
@@ -58,16 +61,19 @@ struct KernelCfg {
 constexpr size_t tma_smem(int stages) { return (size_t)stages * kStageBytes + 2u * stages * 8u; }
 
 const KernelCfg kKernels[kNumVariants] = {
+    {{flagstat_kernel_ring<kFlagstat, 0, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+     kThreads, (size_t)4 * kStageBytes},
+    {{flagstat_kernel_ring<kFlagstat, 1, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+     kThreads, (size_t)4 * kStageBytes},
     {{flagstat_kernel<kFlagstat, 0>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
-    {{flagstat_kernel<kFlagstat, 1>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
     {{flagstat_kernel_tma<kFlagstat, 0, 4, 2>, flagstat_kernel_tma<kPospopcnt, 0, 4, 2>},
      kThreads + 32, tma_smem(4)},
     {{flagstat_kernel_tma<kFlagstat, 0, 6, 2>, flagstat_kernel_tma<kPospopcnt, 0, 6, 2>},
      kThreads + 32, tma_smem(6)},
-    {{flagstat_kernel_tma<kFlagstat, 0, 4, 3>, flagstat_kernel_tma<kPospopcnt, 0, 4, 3>},
-     kThreads + 32, tma_smem(4)},
-    {{flagstat_kernel_tma<kFlagstat, 0, 3, 3>, flagstat_kernel_tma<kPospopcnt, 0, 3, 3>},
-     kThreads + 32, tma_smem(3)},
+    {{flagstat_kernel_ring<kFlagstat, 0, 2, 2>, flagstat_kernel_ring<kPospopcnt, 0, 2, 2>},
+     kThreads, (size_t)2 * kStageBytes},
+    {{flagstat_kernel_ring<kFlagstat, 0, 4, 3>, flagstat_kernel_ring<kPospopcnt, 0, 4, 3>},
+     kThreads, (size_t)4 * kStageBytes},
 };
 
 struct DeviceInfo {
@@ -138,6 +144,11 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
     int rc = device_info(dev, &di);
     if (rc) return rc;
     int variant = g_variant.load();
+    if (variant == -1) {  // first launch: env FLAGSTAT_CUDA_VARIANT picks the default (A/B runs)
+        variant = 0;
+        if (const char* e = std::getenv("FLAGSTAT_CUDA_VARIANT")) variant = std::atoi(e);
+        g_variant.store(variant);
+    }
     if (variant < 0 || variant >= kNumVariants) variant = 0;
     const KernelCfg& k = kKernels[variant];
 
@@ -548,7 +559,11 @@ const char* FLAGSTAT_cuda_version(void) { return "libflagstats_cuda 0.1 (sm_100a
 
 uint64_t FLAGSTAT_cuda_launch_count(void) { return g_launches.load(); }
 
-int FLAGSTAT_cuda_set_variant(int v) { return g_variant.exchange(v); }
+int FLAGSTAT_cuda_set_variant(int v)
+{
+    const int prev = g_variant.exchange(v < 0 ? 0 : v);
+    return prev < 0 ? 0 : prev;
+}
 int FLAGSTAT_cuda_set_ctas_per_sm(int n) { return g_ctas_per_sm.exchange(n); }
 
 int FLAGSTAT_cuda_synth_uniform(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,

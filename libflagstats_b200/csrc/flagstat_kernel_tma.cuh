@@ -95,6 +95,8 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
     const uint64_t ntail = n - tail_start;
     const uint64_t NB = V / kVecPerBatch;
     const uint64_t G = gridDim.x;
+    const uint32_t my = (NB > blockIdx.x) ? (uint32_t)((NB - blockIdx.x + G - 1) / G) : 0u;
+    const uint64_t stride = G * (uint64_t)kVecPerBatch;
 
     if (tid == 0) {
 #pragma unroll
@@ -112,11 +114,12 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
         // ---------------- producer ----------------
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint64_t bb = blockIdx.x; bb < NB; bb += G) {
+            const uint4* src = body + (uint64_t)blockIdx.x * kVecPerBatch;
+            for (uint32_t it = 0; it < my; ++it) {
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], kStageBytes);
-                bulk_g2s(ring + (size_t)s * kVecPerBatch, body + bb * kVecPerBatch, kStageBytes,
-                         &full[s]);
+                bulk_g2s(ring + (size_t)s * kVecPerBatch, src, kStageBytes, &full[s]);
+                src += stride;
                 if (++s == STAGES) {
                     s = 0;
                     ph ^= 1u;
@@ -150,10 +153,9 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
             ++b;
         }
 
-        uint64_t bb = blockIdx.x;
-        uint32_t s = 0, ph = 0;
+        uint32_t it = 0, s = 0, ph = 0;
         do {
-            while (bb < NB && b < Counter::kMaxBatches) {
+            while (it < my && b < Counter::kMaxBatches) {
                 mbar_wait(&full[s], ph);
                 uint32_t w[16];
                 {
@@ -171,14 +173,14 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
                 }
                 st.step(w, b);
                 ++b;
-                bb += G;
+                ++it;
             }
             acc_all += st.all.flush_warp(b, lane);
             if (MODE == kFlagstat && st.nfail != 0u)
                 acc_fail += st.fail.flush_warp(st.nfail, lane);
             st.clear();
             b = 0;
-        } while (bb < NB);
+        } while (it < my);
     }
 
     __shared__ unsigned long long s_all[kWarps][32];
@@ -187,6 +189,141 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
         s_all[warp][lane] = acc_all;
         s_fail[warp][lane] = acc_fail;
     }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long a = 0ull, f = 0ull;
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) {
+            a += s_all[i][lane];
+            f += s_fail[i][lane];
+        }
+        a += __shfl_down_sync(0xffffffffu, a, 16);
+        f += __shfl_down_sync(0xffffffffu, f, 16);
+        emit_counters<MODE>(out, lane, a, f, n);
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// Thread-private cp.async ring (variants 6, 7)
+//
+// Every thread prefetches ITS OWN 4 x 16 bytes of the next DEPTH batches into a
+// private slice of shared memory with cp.async (SASS LDGSTS) and reads them back
+// with LDS.128 once cp.async.wait_group says its own copies have landed.  No
+// mbarrier, no producer warp, no CTA-wide synchronisation in the loop: a thread
+// only ever consumes what it fetched itself.  The bytes in flight live in
+// shared memory (DEPTH x 16 KiB per CTA), not in registers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int MODE, int VARIANT, int DEPTH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+flagstat_kernel_ring(const uint16_t* __restrict__ base, uint64_t n,
+                     unsigned long long* __restrict__ out)
+{
+    static_assert((DEPTH & (DEPTH - 1)) == 0, "DEPTH must be a power of two");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t addr = reinterpret_cast<uint64_t>(base);
+    uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
+    if (head > n) head = n;
+    const uint4* __restrict__ body = reinterpret_cast<const uint4*>(base + head);
+    const uint64_t V = (n - head) >> 3;
+    const uint64_t tail_start = head + (V << 3);
+    const uint64_t ntail = n - tail_start;
+    const uint64_t NB = V / kVecPerBatch;
+    const uint64_t G = gridDim.x;
+    const uint32_t my = (NB > blockIdx.x) ? (uint32_t)((NB - blockIdx.x + G - 1) / G) : 0u;
+    const uint64_t stride = G * (uint64_t)kVecPerBatch;
+
+    Lanes<MODE, VARIANT> st;
+    st.clear();
+    uint32_t b = 0;
+    unsigned long long acc_all = 0ull, acc_fail = 0ull;
+
+    if (blockIdx.x == (uint32_t)(NB % G)) {
+        uint32_t w[16];
+        {
+            uint4 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const uint64_t idx = NB * kVecPerBatch + (uint64_t)u * kThreads + tid;
+                v[u] = (idx < V) ? ld_stream(body + idx) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            unpack4(v, w);
+        }
+        st.step(w, b);
+        ++b;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+        if (tid < head) w[0] = base[tid];
+        else if (tid - head < ntail) w[0] = base[tail_start + (tid - head)];
+        st.step(w, b);
+        ++b;
+    }
+
+    // this thread's slice of stage s, load u:  ((s * kU + u) * kThreads + tid) * 16 bytes
+    const uint32_t my_smem = smem_u32(smem_raw) + tid * 16u;
+    const uint4* __restrict__ src = body + tid + (uint64_t)blockIdx.x * kVecPerBatch;
+
+    // prologue: DEPTH batches in flight (empty groups keep the group count uniform)
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+        if ((uint32_t)d < my) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                cp_async16(my_smem + (uint32_t)((d * kU + u) * kThreads * 16), src + u * kThreads);
+            src += stride;
+        }
+        cp_async_commit();
+    }
+
+    uint32_t it = 0;
+    do {
+        while (it < my && b < Counter::kMaxBatches) {
+            cp_async_wait<DEPTH - 1>();
+            const uint32_t stage = my_smem + (it & (uint32_t)(DEPTH - 1)) * (uint32_t)kStageBytes;
+            uint32_t w[16];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(w[4 * u]), "=r"(w[4 * u + 1]), "=r"(w[4 * u + 2]),
+                               "=r"(w[4 * u + 3])
+                             : "r"(stage + (uint32_t)(u * kThreads * 16)));
+            st.step(w, b);
+            // the registers have been consumed: this slot can take batch it + DEPTH
+            if (it + (uint32_t)DEPTH < my) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    cp_async16(stage + (uint32_t)(u * kThreads * 16), src + u * kThreads);
+                src += stride;
+            }
+            cp_async_commit();
+            ++b;
+            ++it;
+        }
+        acc_all += st.all.flush_warp(b, lane);
+        if (MODE == kFlagstat && st.nfail != 0u) acc_fail += st.fail.flush_warp(st.nfail, lane);
+        st.clear();
+        b = 0;
+    } while (it < my);
+    cp_async_wait<0>();
+
+    __shared__ unsigned long long s_all[kWarps][32];
+    __shared__ unsigned long long s_fail[kWarps][32];
+    s_all[warp][lane] = acc_all;
+    s_fail[warp][lane] = acc_fail;
     __syncthreads();
     if (warp == 0) {
         unsigned long long a = 0ull, f = 0ull;

@@ -96,6 +96,17 @@ __device__ __forceinline__ uint32_t mask_select_h(uint32_t w)
 // QCFAIL (bit 9) of each record spread over its whole halfword: the shift (FMA
 // pipe) puts the bit in the sign position of the odd bytes, PRMT's
 // sign-replicate mode (selector nibbles 0x9 / 0xB) does the broadcast.
+// Same, for a warp batch in which no record has SECONDARY set (all of real-world
+// HiSeqX data, README.md:180): SUPP needs no fix-up, one LOP3 and the shift less.
+__device__ __forceinline__ uint32_t mask_select_h_nosec(uint32_t w)
+{
+    const uint32_t q = w & 0x09050905u;
+    const uint32_t gm = eq2_mask(q, 0x00010001u);
+    const uint32_t xm = eq2_mask(q, 0x00050005u);
+    const uint32_t e = lop3<0xF8>(gm, xm, 0x00C000C0u);
+    return lop3<0xE0>(w, e, 0x0F040F04u);
+}
+
 __device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
 {
     // inline PTX: __byte_perm() documents selector bit 3 as ignored, prmt.b32 does not
@@ -152,7 +163,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p)
 // per-thread state and the batch step
 // ---------------------------------------------------------------------------
 
-using Counter = BitCounter<2, 8>;  // 14 planes: 16 * (2^10 - 2) words per epoch
+using Counter = BitCounter<4, 6>;  // 14 planes: 16 * (2^10 - 2) words per epoch
 
 template <int MODE, int VARIANT>
 struct Lanes {
@@ -174,17 +185,27 @@ struct Lanes {
             all.absorb16(w, b);
             return;
         }
-        uint32_t y[16];
-        uint32_t any = 0u;
+        // Warp-uniform view of the batch: OR of all 512 packed words (REDUX.OR).
+        uint32_t any = w[0];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            y[i] = mask_select<VARIANT>(w[i]);
-            any |= w[i];
+        for (int i = 1; i < 16; ++i) any |= w[i];
+        const uint32_t wany = __reduce_or_sync(0xffffffffu, any);
+
+        uint32_t y[16];
+        if (VARIANT == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = mask_select_i(w[i]);
+        } else if ((wany & 0x01000100u) == 0u) {  // no SECONDARY record in this warp batch
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = mask_select_h_nosec(w[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = mask_select_h(w[i]);
         }
         all.absorb16(y, b);
-        // Warp-uniform: does any record of this warp batch have QCFAIL set?  In
-        // real data none has, and the whole second counter is skipped.
-        if (__any_sync(0xffffffffu, (any & 0x02000200u) != 0u)) {
+        // Any QCFAIL record in this warp batch?  In real data there is none and
+        // the whole second counter is skipped.
+        if ((wany & 0x02000200u) != 0u) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] &= fail_mask<VARIANT>(w[i]);
             fail.absorb16(y, nfail);
@@ -310,40 +331,44 @@ flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long lon
         ++b;
     }
 
-    uint64_t bb = blockIdx.x;
+    // This CTA's batches are blockIdx.x, blockIdx.x + G, ...: a 32-bit trip count
+    // and one pointer bump per batch keep the loop bookkeeping off the ALU pipe.
+    const uint32_t my = (NB > blockIdx.x) ? (uint32_t)((NB - blockIdx.x + G - 1) / G) : 0u;
+    const uint64_t stride = G * (uint64_t)kVecPerBatch;
+    const uint4* __restrict__ p = body + tid + (uint64_t)blockIdx.x * kVecPerBatch;
     uint4 bufA[kU], bufB[kU];
-    const uint4* __restrict__ tp = body + tid;
-    if (bb < NB) load_batch(bufA, tp + bb * kVecPerBatch);
+    uint32_t it = 0;
+    if (my) load_batch(bufA, p);
 
     do {
         // one epoch: at most Counter::kMaxBatches batches, then expand
         for (;;) {
-            if (bb >= NB || b >= Counter::kMaxBatches) break;
+            if (it >= my || b >= Counter::kMaxBatches) break;
             {
-                const uint64_t nb = bb + G;
-                if (nb < NB) load_batch(bufB, tp + nb * kVecPerBatch);
+                p += stride;
+                if (it + 1 < my) load_batch(bufB, p);
                 uint32_t w[16];
                 unpack4(bufA, w);
                 st.step(w, b);
                 ++b;
-                bb = nb;
+                ++it;
             }
-            if (bb >= NB) break;
+            if (it >= my) break;
             {
-                const uint64_t nb = bb + G;
-                if (nb < NB) load_batch(bufA, tp + nb * kVecPerBatch);
+                p += stride;
+                if (it + 1 < my) load_batch(bufA, p);
                 uint32_t w[16];
                 unpack4(bufB, w);
                 st.step(w, b);
                 ++b;
-                bb = nb;
+                ++it;
             }
         }
         acc_all += st.all.flush_warp(b, lane);
         if (MODE == kFlagstat && st.nfail != 0u) acc_fail += st.fail.flush_warp(st.nfail, lane);
         st.clear();
         b = 0;
-    } while (bb < NB);
+    } while (it < my);
 
     // CTA reduction: lanes hold per-position totals of their warp
     __shared__ unsigned long long s_all[kWarps][32];

@@ -31,7 +31,7 @@ def _dev(a, off=0):
     return v
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
     fs = cuda_lib
     prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
