@@ -374,7 +374,8 @@ def ours(args) -> int:
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src,
-            "kernel": "fsb200::flagstat_kernel<0,0>", "kernel_ms": kernel_ms,
+            "kernel": "fsb200::" + (traffic or {}).get("kernel", "flagstat_kernel_ring<0, 0, 4, 2>"),
+            "kernel_ms": kernel_ms,
             "algorithmic_bytes_per_launch": 2 * n,
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),

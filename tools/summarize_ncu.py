@@ -68,7 +68,8 @@ if os.path.exists(rep):
                 "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                 "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
                 "algorithmic_bytes": 1649083784,
-                "source": f"profiles/{tag}_ncu_summary.md (ncu --set full, one launch of flagstat_kernel<0,0>)",
+                "source": f"profiles/{tag}_ncu_summary.md (ncu --set full, one launch of {r[idx['Kernel Name']].split('(')[0].replace('void ', '')})",
+                "kernel": r[idx['Kernel Name']].split('(')[0].replace('void ', ''),
             }
     with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
