@@ -34,7 +34,8 @@ extern "C" {
 #define FLAGSTAT_CUDA_ENODEV (-1) /* no CUDA device / driver */
 #define FLAGSTAT_CUDA_EINVAL (-2) /* bad argument */
 #define FLAGSTAT_CUDA_ENOMEM (-3) /* host allocation failed */
-#define FLAGSTAT_CUDA_ESTATE (-4) /* stream handle used out of order */
+#define FLAGSTAT_CUDA_ESTATE (-4) /* handle used out of order */
+#define FLAGSTAT_CUDA_ETIMEOUT (-5) /* a peer GPU never delivered its counters */
 
 /* ---- the reference's plugin signature ---------------------------------- */
 
@@ -109,6 +110,43 @@ int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s);
  * with an NCCL all-reduce lives in libflagstats_b200/sharded.py on top of
  * FLAGSTAT_cuda_device. */
 int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags, int n_devices);
+
+/* ---- one process (or thread) per GPU: fused count + counter exchange -------
+ *
+ * The reference has no multi-device code.  The FLAG column is
+ * range-sharded; each rank counts its shard and the 32 counters are summed
+ * across ranks.  FLAGSTAT_cuda_device_allreduce does both in ONE kernel launch
+ * per rank: the last CTA of each rank's kernel stores the rank's 32 totals
+ * straight into every peer's exchange buffer over NVLink (peer-mapped memory),
+ * waits for the peers' totals to land in its own buffer and writes the GLOBAL
+ * counters to d_flags.  No NCCL launch, no host round trip.
+ *
+ * Setup: every rank calls _create (current device = its GPU), the 64-byte
+ * handles are exchanged by whatever the host program uses to talk
+ * (torch.distributed in libflagstats_b200/sharded.py), then _connect maps the
+ * peers.  Ranks living in ONE process use _connect_local instead.
+ * Every rank must make the same sequence of *_allreduce calls (it is a
+ * collective).  world <= 16. */
+typedef struct FLAGSTAT_cuda_xchg FLAGSTAT_cuda_xchg;
+#define FLAGSTAT_CUDA_XCHG_HANDLE_BYTES 64
+int FLAGSTAT_cuda_xchg_create(FLAGSTAT_cuda_xchg** x, int rank, int world,
+                              void* handle_out /* 64 bytes, may be NULL when world == 1 */);
+int FLAGSTAT_cuda_xchg_connect(FLAGSTAT_cuda_xchg* x, const void* all_handles /* world x 64 B */);
+int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs /* [world], by rank */, int world);
+/* d_flags: uint64_t[32] on this rank's device, receives the GLOBAL counters:
+ * accumulate != 0 adds them (the FLAGSTAT_* contract), 0 overwrites (saves the
+ * caller a memset).  Asynchronous on `stream`; current device must be the
+ * handle's. */
+int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
+                                   uint64_t* d_flags, int accumulate, void* stream);
+int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
+                                    uint64_t* d_out /*[16]*/, int accumulate, void* stream);
+/* Peers that never show up: the kernel gives up after the timeout (default 20 s),
+ * leaves d_flags untouched and _status returns FLAGSTAT_CUDA_ETIMEOUT.
+ * _status synchronises with the device. */
+int FLAGSTAT_cuda_xchg_set_timeout_ms(FLAGSTAT_cuda_xchg* x, uint32_t ms);
+int FLAGSTAT_cuda_xchg_status(FLAGSTAT_cuda_xchg* x);
+int FLAGSTAT_cuda_xchg_destroy(FLAGSTAT_cuda_xchg* x);
 
 /* ---- diagnostics / test & bench support ---------------------------------- */
 

@@ -34,6 +34,16 @@ SIGNATURES = {
     "FLAGSTAT_cuda_stream_finish": (C.c_int, [C.c_void_p, u64p]),
     "FLAGSTAT_cuda_stream_close": (C.c_int, [C.c_void_p]),
     "FLAGSTAT_cuda_multi_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p, C.c_int]),
+    "FLAGSTAT_cuda_xchg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "FLAGSTAT_cuda_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                 C.c_int, C.c_void_p]),
+    "POSPOPCNT_cuda_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                  C.c_int, C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "FLAGSTAT_cuda_xchg_status": (C.c_int, [C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_destroy": (C.c_int, [C.c_void_p]),
     "FLAGSTAT_cuda_strerror": (C.c_char_p, [C.c_int]),
     "FLAGSTAT_cuda_version": (C.c_char_p, []),
     "FLAGSTAT_cuda_launch_count": (C.c_uint64, []),

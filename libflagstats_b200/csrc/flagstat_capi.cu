@@ -50,7 +50,7 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
 //   5  cp.async ring, depth 2
 //   6  cp.async ring, depth 4, registers capped for 3 CTAs/SM
 constexpr int kNumVariants = 7;
-using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*);
+using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*, const XchgArgs);
 
 struct KernelCfg {
     KernelFn fn[2];   // [mode]
@@ -135,7 +135,8 @@ int device_info(int dev, DeviceInfo** out)
 }
 
 // Enqueue one kernel on the current device.
-int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaStream_t st)
+int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaStream_t st,
+           const XchgArgs* xa = nullptr)
 {
     if ((reinterpret_cast<uintptr_t>(d_array) & 1u) != 0) return FLAGSTAT_CUDA_EINVAL;
     int dev = 0;
@@ -161,8 +162,10 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
     uint64_t grid = (uint64_t)per_sm * (uint64_t)di->sms;
     if (grid > nb + 1) grid = nb + 1;
 
+    XchgArgs none;
+    std::memset(&none, 0, sizeof(none));
     k.fn[mode]<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
-        d_array, n, reinterpret_cast<unsigned long long*>(d_out));
+        d_array, n, reinterpret_cast<unsigned long long*>(d_out), xa ? *xa : none);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
     return 0;
@@ -335,6 +338,21 @@ struct FLAGSTAT_cuda_stream {
     std::vector<char> busy;
     uint64_t* d_flags = nullptr;
     uint64_t* h_flags = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// fused counter exchange handle (one per rank)
+// ---------------------------------------------------------------------------
+struct FLAGSTAT_cuda_xchg {
+    int dev = 0;
+    int rank = 0;
+    int world = 1;
+    bool connected = false;
+    bool ipc = false;
+    unsigned long long* mine = nullptr;                 // this rank's buffer (cudaMalloc)
+    unsigned long long* peer[fsb200::kMaxRanks] = {};  // every rank's buffer as mapped here
+    uint64_t epoch = 0;
+    uint64_t timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
 };
 
 extern "C" {
@@ -539,6 +557,145 @@ int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags
     return 0;
 }
 
+// ---- fused count + counter exchange over peer memory ------------------------------
+
+int FLAGSTAT_cuda_xchg_create(FLAGSTAT_cuda_xchg** out, int rank, int world, void* handle_out)
+{
+    if (!out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+        return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    FLAGSTAT_cuda_xchg* x = new (std::nothrow) FLAGSTAT_cuda_xchg();
+    if (!x) return FLAGSTAT_CUDA_ENOMEM;
+    CK(cudaGetDevice(&x->dev));
+    x->rank = rank;
+    x->world = world;
+    CK(cudaMalloc(&x->mine, kXchgWords * sizeof(unsigned long long)));
+    CK(cudaMemset(x->mine, 0, kXchgWords * sizeof(unsigned long long)));
+    CK(cudaDeviceSynchronize());
+    x->peer[rank] = x->mine;
+    x->connected = world == 1;
+    if (handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == FLAGSTAT_CUDA_XCHG_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        std::memset(&h, 0, sizeof(h));
+        if (world > 1) CK(cudaIpcGetMemHandle(&h, x->mine));
+        std::memcpy(handle_out, &h, sizeof(h));
+    }
+    *out = x;
+    return 0;
+}
+
+int FLAGSTAT_cuda_xchg_connect(FLAGSTAT_cuda_xchg* x, const void* all_handles)
+{
+    if (!x || !all_handles) return FLAGSTAT_CUDA_EINVAL;
+    if (x->connected) return 0;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != x->dev) CK(cudaSetDevice(x->dev));
+    const char* hs = static_cast<const char*>(all_handles);
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[r] = static_cast<unsigned long long*>(p);
+    }
+    x->ipc = true;
+    x->connected = true;
+    if (cur != x->dev && cur >= 0) CK(cudaSetDevice(cur));
+    return 0;
+}
+
+int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs, int world)
+{
+    if (!xs || world < 1 || world > kMaxRanks) return FLAGSTAT_CUDA_EINVAL;
+    for (int r = 0; r < world; ++r)
+        if (!xs[r] || xs[r]->world != world || xs[r]->rank != r) return FLAGSTAT_CUDA_EINVAL;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    for (int a = 0; a < world; ++a) {
+        CK(cudaSetDevice(xs[a]->dev));
+        for (int b = 0; b < world; ++b) {
+            if (xs[b]->dev != xs[a]->dev) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, xs[a]->dev, xs[b]->dev));
+                if (!can) return FLAGSTAT_CUDA_ENODEV;
+                cudaError_t e = cudaDeviceEnablePeerAccess(xs[b]->dev, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return (int)e;
+            }
+            xs[a]->peer[b] = xs[b]->mine;  // UVA: the same pointer is valid on every device
+        }
+        xs[a]->connected = true;
+    }
+    if (cur >= 0) CK(cudaSetDevice(cur));
+    return 0;
+}
+
+static int xchg_launch(FLAGSTAT_cuda_xchg* x, int mode, const uint16_t* d_array, uint64_t len,
+                       uint64_t* d_out, int accumulate, void* stream)
+{
+    if (!x || !d_out || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
+    if (!x->connected) return FLAGSTAT_CUDA_ESTATE;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != x->dev) return FLAGSTAT_CUDA_EINVAL;  // the caller launches on the handle's device
+    XchgArgs xa;
+    std::memset(&xa, 0, sizeof(xa));
+    for (int r = 0; r < x->world; ++r) xa.buf[r] = x->peer[r];
+    xa.epoch = ++x->epoch;
+    xa.timeout_ns = x->timeout_ns;
+    xa.rank = x->rank;
+    xa.world = x->world;
+    xa.accumulate = accumulate ? 1 : 0;
+    return launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa);
+}
+
+int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
+                                   uint64_t* d_flags, int accumulate, void* stream)
+{
+    return xchg_launch(x, kFlagstat, d_array, len, d_flags, accumulate, stream);
+}
+
+int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
+                                    uint64_t* d_out, int accumulate, void* stream)
+{
+    return xchg_launch(x, kPospopcnt, d_data, len, d_out, accumulate, stream);
+}
+
+int FLAGSTAT_cuda_xchg_set_timeout_ms(FLAGSTAT_cuda_xchg* x, uint32_t ms)
+{
+    if (!x) return FLAGSTAT_CUDA_EINVAL;
+    x->timeout_ns = (uint64_t)ms * 1000000ull;
+    return 0;
+}
+
+int FLAGSTAT_cuda_xchg_status(FLAGSTAT_cuda_xchg* x)
+{
+    if (!x) return FLAGSTAT_CUDA_EINVAL;
+    int cur = -1;
+    CK(cudaGetDevice(&cur));
+    if (cur != x->dev) CK(cudaSetDevice(x->dev));
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, x->mine + kXchgErr, sizeof(err), cudaMemcpyDeviceToHost));
+    if (cur != x->dev && cur >= 0) CK(cudaSetDevice(cur));
+    return err ? FLAGSTAT_CUDA_ETIMEOUT : 0;
+}
+
+int FLAGSTAT_cuda_xchg_destroy(FLAGSTAT_cuda_xchg* x)
+{
+    if (!x) return FLAGSTAT_CUDA_EINVAL;
+    cudaSetDevice(x->dev);
+    cudaDeviceSynchronize();
+    if (x->ipc)
+        for (int r = 0; r < x->world; ++r)
+            if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->mine) cudaFree(x->mine);
+    delete x;
+    return 0;
+}
+
 // ---- diagnostics / support ----------------------------------------------------
 
 const char* FLAGSTAT_cuda_strerror(int code)
@@ -548,7 +705,8 @@ const char* FLAGSTAT_cuda_strerror(int code)
         case FLAGSTAT_CUDA_ENODEV: return "no usable CUDA device";
         case FLAGSTAT_CUDA_EINVAL: return "invalid argument";
         case FLAGSTAT_CUDA_ENOMEM: return "host allocation failed";
-        case FLAGSTAT_CUDA_ESTATE: return "stream handle used out of order";
+        case FLAGSTAT_CUDA_ESTATE: return "handle used out of order";
+        case FLAGSTAT_CUDA_ETIMEOUT: return "timed out waiting for a peer GPU's counters";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -78,7 +78,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int MODE, int VARIANT, int STAGES, int MINB>
 __global__ void __launch_bounds__(kThreads + 32, MINB)
 flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
-                    unsigned long long* __restrict__ out)
+                    unsigned long long* __restrict__ out, const __grid_constant__ XchgArgs xa)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* ring = reinterpret_cast<uint4*>(smem_raw);
@@ -183,24 +183,7 @@ flagstat_kernel_tma(const uint16_t* __restrict__ base, uint64_t n,
         } while (it < my);
     }
 
-    __shared__ unsigned long long s_all[kWarps][32];
-    __shared__ unsigned long long s_fail[kWarps][32];
-    if (warp < kWarps) {
-        s_all[warp][lane] = acc_all;
-        s_fail[warp][lane] = acc_fail;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long a = 0ull, f = 0ull;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) {
-            a += s_all[i][lane];
-            f += s_fail[i][lane];
-        }
-        a += __shfl_down_sync(0xffffffffu, a, 16);
-        f += __shfl_down_sync(0xffffffffu, f, 16);
-        emit_counters<MODE>(out, lane, a, f, n);
-    }
+    cta_epilogue<MODE>(out, acc_all, acc_fail, n, warp, lane, warp < kWarps, xa);
 }
 
 
@@ -229,7 +212,7 @@ __device__ __forceinline__ void cp_async_wait()
 template <int MODE, int VARIANT, int DEPTH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 flagstat_kernel_ring(const uint16_t* __restrict__ base, uint64_t n,
-                     unsigned long long* __restrict__ out)
+                     unsigned long long* __restrict__ out, const __grid_constant__ XchgArgs xa)
 {
     static_assert((DEPTH & (DEPTH - 1)) == 0, "DEPTH must be a power of two");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -320,22 +303,7 @@ flagstat_kernel_ring(const uint16_t* __restrict__ base, uint64_t n,
     } while (it < my);
     cp_async_wait<0>();
 
-    __shared__ unsigned long long s_all[kWarps][32];
-    __shared__ unsigned long long s_fail[kWarps][32];
-    s_all[warp][lane] = acc_all;
-    s_fail[warp][lane] = acc_fail;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long a = 0ull, f = 0ull;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) {
-            a += s_all[i][lane];
-            f += s_fail[i][lane];
-        }
-        a += __shfl_down_sync(0xffffffffu, a, 16);
-        f += __shfl_down_sync(0xffffffffu, f, 16);
-        emit_counters<MODE>(out, lane, a, f, n);
-    }
+    cta_epilogue<MODE>(out, acc_all, acc_fail, n, warp, lane, true, xa);
 }
 
 }  // namespace fsb200

@@ -282,6 +282,156 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
     }
 }
 
+// ---------------------------------------------------------------------------
+// fused counter exchange (multi-GPU): count -> push -> wait -> sum in ONE kernel
+// ---------------------------------------------------------------------------
+//
+// Every rank (GPU) owns one exchange buffer in its own HBM; all ranks map all
+// buffers (CUDA IPC across processes, peer access inside one process).  When
+// xa.world != 0 the CTAs of a launch add their per-CTA totals into xa.acc
+// instead of the caller's counters; the CTA that draws the last ticket then
+//   1. takes the rank's 32 totals out of xa.acc (and re-zeroes it),
+//   2. stores them into slot [epoch & 1][rank] of EVERY rank's buffer with
+//      plain 8-byte stores over NVLink, fences, and raises flag[epoch & 1][rank]
+//      = epoch there (st.release.sys),
+//   3. waits until all `world` flags in its OWN buffer carry this epoch
+//      (ld.acquire.sys), adds the `world` slots and writes the global counters.
+// The exchange is 256 bytes per peer and overlaps the tail of the slower ranks'
+// kernels; there is no separate collective launch.  Slots are double-buffered
+// by epoch parity: a rank can start epoch e+2 only after every rank finished
+// epoch e (it needs their e+1 data to finish e+1), so a slot is never rewritten
+// while a peer may still read it.
+constexpr int kMaxRanks = 16;
+constexpr int kXchgSlotWords = 32;
+// layout of one exchange buffer, in 8-byte words
+constexpr int kXchgSlots = 0;                                           // [2][kMaxRanks][32]
+constexpr int kXchgFlags = kXchgSlots + 2 * kMaxRanks * kXchgSlotWords;  // [2][kMaxRanks]
+constexpr int kXchgAcc = kXchgFlags + 2 * kMaxRanks;                     // [32] per-launch accumulator
+constexpr int kXchgTicket = kXchgAcc + 32;                               // [1]
+constexpr int kXchgErr = kXchgTicket + 1;                                // [1] != 0 after a timeout
+constexpr int kXchgWords = kXchgErr + 1;
+
+struct XchgArgs {
+    unsigned long long* buf[kMaxRanks];  // buf[r] = rank r's exchange buffer as mapped HERE
+    unsigned long long epoch;            // 1, 2, 3, ... (same on every rank for one collective call)
+    unsigned long long timeout_ns;       // give up waiting for peers after this long
+    int rank;
+    int world;                           // 0 = no exchange: plain accumulate into out
+    int accumulate;                      // 1: out[i] += total, 0: out[i] = total
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Executed by warp 0 of the CTA that drew the last ticket of a launch.
+template <int MODE>
+__device__ __noinline__ void xchg_last_cta(unsigned long long* __restrict__ out, uint32_t lane,
+                                           const XchgArgs& xa)
+{
+    constexpr uint32_t kOut = MODE == kPospopcnt ? 16u : 32u;
+    unsigned long long* mine = xa.buf[xa.rank];
+    __threadfence();  // the other CTAs' atomics into acc happen-before their ticket
+    unsigned long long v = 0ull;
+    if (lane < kOut) v = atomicExch(mine + kXchgAcc + lane, 0ull);
+    if (lane == 0) atomicExch(mine + kXchgTicket, 0ull);
+    const int world = xa.world;
+    if (world > 1) {
+        const uint32_t par = (uint32_t)(xa.epoch & 1ull);
+        const uint32_t slot = kXchgSlots + (par * kMaxRanks + (uint32_t)xa.rank) * kXchgSlotWords;
+        for (int r = 0; r < world; ++r)
+            if (lane < kOut) st_relaxed_sys(xa.buf[r] + slot + lane, v);
+        __threadfence_system();
+        __syncwarp();
+        if ((int)lane < world)
+            st_release_sys(xa.buf[lane] + kXchgFlags + par * kMaxRanks + (uint32_t)xa.rank, xa.epoch);
+        bool ok = true;
+        if ((int)lane < world) {
+            const unsigned long long* f = mine + kXchgFlags + par * kMaxRanks + lane;
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(f) != xa.epoch) {
+                if (global_timer_ns() - t0 > xa.timeout_ns) {
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        if (!__all_sync(0xffffffffu, ok)) {
+            if (lane == 0) atomicExch(mine + kXchgErr, xa.epoch);
+            return;  // out[] is left untouched on failure
+        }
+        __threadfence_system();
+        v = 0ull;
+        if (lane < kOut)
+            for (int r = 0; r < world; ++r)
+                v += ld_relaxed_sys(mine + kXchgSlots + (par * kMaxRanks + (uint32_t)r) * kXchgSlotWords + lane);
+    }
+    if (lane < kOut) out[lane] = xa.accumulate ? out[lane] + v : v;
+}
+
+// Common tail of every kernel variant: CTA reduction of the per-warp position
+// totals, mapping to counter slots, and either 64-bit atomics into out[] or
+// the fused exchange above.
+template <int MODE>
+__device__ __forceinline__ void cta_epilogue(unsigned long long* __restrict__ out,
+                                             unsigned long long acc_all, unsigned long long acc_fail,
+                                             uint64_t n, uint32_t warp, uint32_t lane, bool counting_warp,
+                                             const XchgArgs& xa)
+{
+    __shared__ unsigned long long s_all[kWarps][32];
+    __shared__ unsigned long long s_fail[kWarps][32];
+    if (counting_warp) {
+        s_all[warp][lane] = acc_all;
+        s_fail[warp][lane] = acc_fail;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    unsigned long long a = 0ull, f = 0ull;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) {
+        a += s_all[i][lane];
+        f += s_fail[i][lane];
+    }
+    // fold the high-halfword record onto the low one
+    a += __shfl_down_sync(0xffffffffu, a, 16);
+    f += __shfl_down_sync(0xffffffffu, f, 16);
+    if (xa.world == 0) {
+        emit_counters<MODE>(out, lane, a, f, n);
+        return;
+    }
+    unsigned long long* mine = xa.buf[xa.rank];
+    emit_counters<MODE>(mine + kXchgAcc, lane, a, f, n);
+    __threadfence();
+    __syncwarp();
+    unsigned long long t = 0ull;
+    if (lane == 0) t = atomicAdd(mine + kXchgTicket, 1ull);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t == (unsigned long long)gridDim.x - 1ull) xchg_last_cta<MODE>(out, lane, xa);
+}
+
 // Persistent, grid-strided over 16 KiB CTA batches.  out = uint64_t[32]
 // (flagstat) or uint64_t[16] (pospopcnt), ACCUMULATED with 64-bit atomics.
 //
@@ -292,7 +442,8 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 // records, as two extra batches in front of its main loop.
 template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(kThreads, 2)
-flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long long* __restrict__ out)
+flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long long* __restrict__ out,
+                const __grid_constant__ XchgArgs xa)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t addr = reinterpret_cast<uint64_t>(base);
@@ -370,24 +521,7 @@ flagstat_kernel(const uint16_t* __restrict__ base, uint64_t n, unsigned long lon
         b = 0;
     } while (it < my);
 
-    // CTA reduction: lanes hold per-position totals of their warp
-    __shared__ unsigned long long s_all[kWarps][32];
-    __shared__ unsigned long long s_fail[kWarps][32];
-    s_all[warp][lane] = acc_all;
-    s_fail[warp][lane] = acc_fail;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long a = 0ull, f = 0ull;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) {
-            a += s_all[i][lane];
-            f += s_fail[i][lane];
-        }
-        // fold the high-halfword record onto the low one
-        a += __shfl_down_sync(0xffffffffu, a, 16);
-        f += __shfl_down_sync(0xffffffffu, f, 16);
-        emit_counters<MODE>(out, lane, a, f, n);
-    }
+    cta_epilogue<MODE>(out, acc_all, acc_fail, n, warp, lane, true, xa);
 }
 
 }  // namespace fsb200
