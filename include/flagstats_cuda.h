@@ -91,6 +91,18 @@ typedef struct FLAGSTAT_cuda_stream FLAGSTAT_cuda_stream;
  * reference's block); n_slots: pinned ring depth (>= 2; 0 = default 4). */
 int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** s, int device, uint32_t block_records,
                               int n_slots);
+/* Same with the transport spelled out.  mode: how a block crosses PCIe --
+ * _DMA: cudaMemcpyAsync into a device twin of the ring, then the kernel;
+ * _ZEROCOPY: no device staging at all, the kernel's own asynchronous loads read
+ * the pinned block over PCIe (transfer and counting are one launch).
+ * coalesce: consecutive full blocks shipped per DMA + launch (1 = every block on
+ * its own; 0 = default 8: 97 % of the pinned-memcpy rate on a Gen5 x16 B200, profiles/r1l_stream.jsonl).  The ring then holds n_slots groups of `coalesce`
+ * blocks; a short block closes its group early.  Counters are only complete
+ * after _finish either way. */
+#define FLAGSTAT_CUDA_STREAM_DMA 0
+#define FLAGSTAT_CUDA_STREAM_ZEROCOPY 1
+int FLAGSTAT_cuda_stream_open_ex(FLAGSTAT_cuda_stream** s, int device, uint32_t block_records,
+                                 int n_slots, int mode, int coalesce);
 /* Zero-copy producer API: get the next pinned slot (blocks until the slot's
  * previous transfer has finished), fill it, then submit n records. */
 uint16_t* FLAGSTAT_cuda_stream_acquire(FLAGSTAT_cuda_stream* s);
@@ -101,6 +113,12 @@ int FLAGSTAT_cuda_stream_push(FLAGSTAT_cuda_stream* s, const uint16_t* block, ui
  * reset the device accumulator.  The handle stays usable. */
 int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags);
 int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s);
+/* Measurement aid: re-submits the ring's current contents as n_blocks full blocks
+ * (acquire + submit, no host-side fill -- the producer-already-wrote-the-slot
+ * case), finishes into flags[32] and returns the wall-clock seconds of the
+ * whole loop including the final synchronisation. */
+int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, uint64_t* flags,
+                                  double* seconds);
 
 /* ---- several GPUs from one process (range shards, host-side sum) --------- */
 

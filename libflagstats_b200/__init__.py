@@ -225,11 +225,19 @@ class BlockStream:
     of block k on separate CUDA streams; one device-side counter set is shared
     by all blocks (like the reference's shared counters[32], flagstats.cpp:304)."""
 
-    def __init__(self, device: int = 0, block_records: int = BLOCK_RECORDS, n_slots: int = 4):
+    DMA, ZEROCOPY = 0, 1
+
+    def __init__(self, device: int = 0, block_records: int = BLOCK_RECORDS, n_slots: int = 4,
+                 mode: Optional[int] = None, coalesce: int = 0):
         self._h = C.c_void_p()
         self.block_records = int(block_records)
-        check(lib().FLAGSTAT_cuda_stream_open(C.byref(self._h), device, self.block_records,
-                                              n_slots), "FLAGSTAT_cuda_stream_open")
+        if mode is None:
+            check(lib().FLAGSTAT_cuda_stream_open(C.byref(self._h), device, self.block_records,
+                                                  n_slots), "FLAGSTAT_cuda_stream_open")
+        else:
+            check(lib().FLAGSTAT_cuda_stream_open_ex(C.byref(self._h), device, self.block_records,
+                                                     n_slots, int(mode), int(coalesce)),
+                  "FLAGSTAT_cuda_stream_open_ex")
 
     def acquire(self) -> np.ndarray:
         """Next pinned slot as a writable uint16 view (zero-copy producer)."""
@@ -254,6 +262,15 @@ class BlockStream:
         check(lib().FLAGSTAT_cuda_stream_finish(self._h, f.ctypes.data_as(_capi.u64p)),
               "FLAGSTAT_cuda_stream_finish")
         return f
+
+    def selftime(self, n_blocks: int):
+        """(counters, seconds) of re-submitting the ring's contents as n_blocks full
+        blocks from C (FLAGSTAT_cuda_stream_selftime)."""
+        f = np.zeros(32, np.uint64)
+        sec = C.c_double()
+        check(lib().FLAGSTAT_cuda_stream_selftime(self._h, int(n_blocks), f.ctypes.data_as(_capi.u64p),
+                                                  C.byref(sec)), "FLAGSTAT_cuda_stream_selftime")
+        return f, sec.value
 
     def close(self) -> None:
         if self._h:

@@ -28,11 +28,14 @@ SIGNATURES = {
     "POSPOPCNT_cuda_u16_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
     "POSPOPCNT_cuda_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "FLAGSTAT_cuda_stream_open": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_int]),
+    "FLAGSTAT_cuda_stream_open_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_int,
+                                               C.c_int, C.c_int]),
     "FLAGSTAT_cuda_stream_acquire": (C.c_void_p, [C.c_void_p]),
     "FLAGSTAT_cuda_stream_submit": (C.c_int, [C.c_void_p, C.c_uint32]),
     "FLAGSTAT_cuda_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "FLAGSTAT_cuda_stream_finish": (C.c_int, [C.c_void_p, u64p]),
     "FLAGSTAT_cuda_stream_close": (C.c_int, [C.c_void_p]),
+    "FLAGSTAT_cuda_stream_selftime": (C.c_int, [C.c_void_p, C.c_uint32, u64p, C.POINTER(C.c_double)]),
     "FLAGSTAT_cuda_multi_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p, C.c_int]),
     "FLAGSTAT_cuda_xchg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
     "FLAGSTAT_cuda_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),

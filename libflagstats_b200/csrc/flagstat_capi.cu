@@ -6,6 +6,7 @@
 // There is deliberately NO CPU implementation behind these entry points: if no
 // device is usable they return FLAGSTAT_CUDA_ENODEV.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -328,17 +329,51 @@ uint32_t min_len_init()
 struct FLAGSTAT_cuda_stream {
     int dev = 0;
     uint32_t block_records = 0;
-    int n_slots = 0;
-    int next = 0;        // slot handed out by the next acquire
-    int acquired = -1;   // slot currently owned by the producer
-    std::vector<uint16_t*> h;  // pinned
-    std::vector<uint16_t*> d;
-    std::vector<cudaStream_t> st;
-    std::vector<cudaEvent_t> done;
-    std::vector<char> busy;
+    int n_groups = 0;     // ring depth, in groups
+    int coalesce = 1;     // blocks per group = per DMA + kernel launch
+    int mode = 0;         // FLAGSTAT_CUDA_STREAM_DMA / _ZEROCOPY
+    uint16_t* h_base = nullptr;  // pinned: n_groups * coalesce blocks, contiguous
+    uint16_t* d_base = nullptr;  // device twin (DMA mode only)
+    std::vector<cudaStream_t> st;    // per group
+    std::vector<cudaEvent_t> done;   // per group
+    std::vector<char> busy;          // per group
+    int cur_group = 0;
+    int cur_fill = 0;            // blocks submitted into the current group
+    uint64_t cur_records = 0;    // records submitted into the current group (contiguous)
+    bool acquired = false;
     uint64_t* d_flags = nullptr;
     uint64_t* h_flags = nullptr;
 };
+
+namespace {
+
+// Ship the current group: one DMA of its contiguous bytes (DMA mode) and one
+// kernel launch over all of them, on the group's own stream.
+int stream_flush_group(FLAGSTAT_cuda_stream* s)
+{
+    if (s->cur_fill == 0) return 0;
+    const int g = s->cur_group;
+    const size_t off = (size_t)g * s->coalesce * s->block_records;
+    if (s->cur_records) {
+        const uint16_t* src = s->h_base + off;
+        if (s->mode == FLAGSTAT_CUDA_STREAM_DMA) {
+            CK(cudaMemcpyAsync(s->d_base + off, src, s->cur_records * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, s->st[g]));
+            src = s->d_base + off;
+        }
+        // zero-copy: the kernel's cp.async loads pull the pinned block over PCIe themselves
+        const int rc = launch(kFlagstat, src, s->cur_records, s->d_flags, s->st[g]);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(s->done[g], s->st[g]));
+    s->busy[g] = 1;
+    s->cur_group = (g + 1) % s->n_groups;
+    s->cur_fill = 0;
+    s->cur_records = 0;
+    return 0;
+}
+
+}  // namespace
 
 // ---------------------------------------------------------------------------
 // fused counter exchange handle (one per rank)
@@ -418,29 +453,32 @@ int POSPOPCNT_cuda_device(const uint16_t* d_data, uint64_t len, uint64_t* d_out,
 
 // ---- streaming -------------------------------------------------------------
 
-int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** out, int device, uint32_t block_records,
-                              int n_slots)
+int FLAGSTAT_cuda_stream_open_ex(FLAGSTAT_cuda_stream** out, int device, uint32_t block_records,
+                                 int n_slots, int mode, int coalesce)
 {
     if (!out || block_records == 0) return FLAGSTAT_CUDA_EINVAL;
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     if (device < 0 || device >= g_ndev) return FLAGSTAT_CUDA_EINVAL;
     if (n_slots == 0) n_slots = 4;
-    if (n_slots < 2 || n_slots > 64) return FLAGSTAT_CUDA_EINVAL;
+    if (coalesce == 0) coalesce = 8;
+    if (n_slots < 2 || n_slots > 64 || coalesce < 1 || coalesce > 256) return FLAGSTAT_CUDA_EINVAL;
+    if (mode != FLAGSTAT_CUDA_STREAM_DMA && mode != FLAGSTAT_CUDA_STREAM_ZEROCOPY)
+        return FLAGSTAT_CUDA_EINVAL;
     CK(cudaSetDevice(device));
     FLAGSTAT_cuda_stream* s = new (std::nothrow) FLAGSTAT_cuda_stream();
     if (!s) return FLAGSTAT_CUDA_ENOMEM;
     s->dev = device;
     s->block_records = block_records;
-    s->n_slots = n_slots;
-    s->h.assign(n_slots, nullptr);
-    s->d.assign(n_slots, nullptr);
+    s->n_groups = n_slots;
+    s->coalesce = coalesce;
+    s->mode = mode;
     s->st.assign(n_slots, nullptr);
     s->done.assign(n_slots, nullptr);
     s->busy.assign(n_slots, 0);
-    const size_t bytes = (size_t)block_records * sizeof(uint16_t);
+    const size_t bytes = (size_t)n_slots * coalesce * block_records * sizeof(uint16_t);
+    CK(cudaHostAlloc(&s->h_base, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    if (mode == FLAGSTAT_CUDA_STREAM_DMA) CK(cudaMalloc(&s->d_base, bytes));
     for (int i = 0; i < n_slots; ++i) {
-        CK(cudaMallocHost(&s->h[i], bytes));
-        CK(cudaMalloc(&s->d[i], bytes));
         CK(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming));
     }
@@ -451,34 +489,41 @@ int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** out, int device, uint32_t b
     return 0;
 }
 
+int FLAGSTAT_cuda_stream_open(FLAGSTAT_cuda_stream** out, int device, uint32_t block_records,
+                              int n_slots)
+{
+    int mode = FLAGSTAT_CUDA_STREAM_DMA, coalesce = 0;
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_STREAM_MODE")) mode = std::atoi(e);
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_STREAM_COALESCE")) coalesce = std::atoi(e);
+    return FLAGSTAT_cuda_stream_open_ex(out, device, block_records, n_slots, mode, coalesce);
+}
+
 uint16_t* FLAGSTAT_cuda_stream_acquire(FLAGSTAT_cuda_stream* s)
 {
-    if (!s || s->acquired >= 0) return nullptr;
-    const int i = s->next;
-    if (s->busy[i]) {
-        if (cudaEventSynchronize(s->done[i]) != cudaSuccess) return nullptr;
-        s->busy[i] = 0;
+    if (!s || s->acquired) return nullptr;
+    const int g = s->cur_group;
+    if (s->cur_fill == 0 && s->busy[g]) {
+        if (cudaEventSynchronize(s->done[g]) != cudaSuccess) return nullptr;
+        s->busy[g] = 0;
     }
-    s->acquired = i;
-    return s->h[i];
+    s->acquired = true;
+    return s->h_base + ((size_t)g * s->coalesce + s->cur_fill) * s->block_records;
 }
 
 int FLAGSTAT_cuda_stream_submit(FLAGSTAT_cuda_stream* s, uint32_t n_records)
 {
-    if (!s || s->acquired < 0) return FLAGSTAT_CUDA_ESTATE;
+    if (!s || !s->acquired) return FLAGSTAT_CUDA_ESTATE;
     if (n_records > s->block_records) return FLAGSTAT_CUDA_EINVAL;
-    const int i = s->acquired;
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
-    if (cur != s->dev) CK(cudaSetDevice(s->dev));
-    CK(cudaMemcpyAsync(s->d[i], s->h[i], (size_t)n_records * sizeof(uint16_t),
-                       cudaMemcpyHostToDevice, s->st[i]));
-    const int rc = launch(kFlagstat, s->d[i], n_records, s->d_flags, s->st[i]);
-    if (rc) return rc;
-    CK(cudaEventRecord(s->done[i], s->st[i]));
-    s->busy[i] = 1;
-    s->acquired = -1;
-    s->next = (i + 1) % s->n_slots;
+    s->acquired = false;
+    s->cur_records += n_records;
+    s->cur_fill += 1;
+    // a short block ends the contiguous run: ship the group right away
+    if (s->cur_fill == s->coalesce || n_records < s->block_records) {
+        int cur = -1;
+        CK(cudaGetDevice(&cur));
+        if (cur != s->dev) CK(cudaSetDevice(s->dev));
+        return stream_flush_group(s);
+    }
     return 0;
 }
 
@@ -495,11 +540,13 @@ int FLAGSTAT_cuda_stream_push(FLAGSTAT_cuda_stream* s, const uint16_t* block, ui
 int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags)
 {
     if (!s || !flags) return FLAGSTAT_CUDA_EINVAL;
-    if (s->acquired >= 0) return FLAGSTAT_CUDA_ESTATE;
+    if (s->acquired) return FLAGSTAT_CUDA_ESTATE;
     int cur = -1;
     CK(cudaGetDevice(&cur));
     if (cur != s->dev) CK(cudaSetDevice(s->dev));
-    for (int i = 0; i < s->n_slots; ++i) {
+    const int rc = stream_flush_group(s);
+    if (rc) return rc;
+    for (int i = 0; i < s->n_groups; ++i) {
         CK(cudaStreamSynchronize(s->st[i]));
         s->busy[i] = 0;
     }
@@ -509,17 +556,32 @@ int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags)
     return 0;
 }
 
+int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, uint64_t* flags,
+                                  double* seconds)
+{
+    if (!s || !flags || !seconds) return FLAGSTAT_CUDA_EINVAL;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n_blocks; ++i) {
+        if (!FLAGSTAT_cuda_stream_acquire(s)) return FLAGSTAT_CUDA_ESTATE;
+        const int rc = FLAGSTAT_cuda_stream_submit(s, s->block_records);
+        if (rc) return rc;
+    }
+    const int rc = FLAGSTAT_cuda_stream_finish(s, flags);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
 int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s)
 {
     if (!s) return FLAGSTAT_CUDA_EINVAL;
     cudaSetDevice(s->dev);
-    for (int i = 0; i < s->n_slots; ++i) {
+    for (int i = 0; i < s->n_groups; ++i) {
         if (s->st[i]) cudaStreamSynchronize(s->st[i]);
         if (s->done[i]) cudaEventDestroy(s->done[i]);
         if (s->st[i]) cudaStreamDestroy(s->st[i]);
-        if (s->h[i]) cudaFreeHost(s->h[i]);
-        if (s->d[i]) cudaFree(s->d[i]);
     }
+    if (s->h_base) cudaFreeHost(s->h_base);
+    if (s->d_base) cudaFree(s->d_base);
     if (s->d_flags) cudaFree(s->d_flags);
     if (s->h_flags) cudaFreeHost(s->h_flags);
     delete s;
