@@ -19,6 +19,7 @@
 #include "../../include/flagstats_cuda.h"
 #include "flagstat_kernels.cuh"
 #include "flagstat_kernel_tma.cuh"
+#include "flagstat_kernel_group.cuh"
 #include "synth.cuh"
 
 namespace {
@@ -41,16 +42,18 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
     } while (0)
 
 // Kernel variants (FLAGSTAT_cuda_set_variant / env FLAGSTAT_CUDA_VARIANT).  All
-// compute the same thing; they differ in how bytes reach the registers and are
-// kept selectable for A/B measurement (profiles/, tools/perf_sweep.py):
-//   0  thread-private cp.async ring, depth 4 (64 KiB/CTA), fp16x2-compare mask  (default)
-//   1  same ring, integer-only mask select (cross-check of the fp16 compares)
-//   2  register-staged LDG.128 double buffer
+// compute the same thing; they differ in how bytes reach the registers and in
+// how the counters are organised, and are kept selectable for A/B measurement
+// (profiles/, tools/variant_ab.py, tools/perf_sweep.py):
+//   0  cp.async ring + compile-time groups of 4 batches, fp16x2-compare mask   (default)
+//   1  same, integer-only mask select (cross-check of the fp16 compares)
+//   2  register-staged LDG.128 double buffer, run-time hold levels
 //   3  TMA (cp.async.bulk + mbarrier) shared-memory ring, 4 stages, producer warp
 //   4  TMA ring, 6 stages
-//   5  cp.async ring, depth 2
-//   6  cp.async ring, depth 4, registers capped for 3 CTAs/SM
-constexpr int kNumVariants = 7;
+//   5  cp.async ring depth 4 with run-time hold levels (the round-1 "r1i" kernel)
+//   6  same, depth 2
+//   7  as 5 with the class tests as fp16x2 tent functions (half pipe instead of ALU pipe)
+constexpr int kNumVariants = 8;
 using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*, const XchgArgs);
 
 struct KernelCfg {
@@ -62,18 +65,20 @@ struct KernelCfg {
 constexpr size_t tma_smem(int stages) { return (size_t)stages * kStageBytes + 2u * stages * 8u; }
 
 const KernelCfg kKernels[kNumVariants] = {
-    {{flagstat_kernel_ring<kFlagstat, 0, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+    {{flagstat_kernel_group<kFlagstat, 0, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
-    {{flagstat_kernel_ring<kFlagstat, 1, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+    {{flagstat_kernel_group<kFlagstat, 1, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
     {{flagstat_kernel<kFlagstat, 0>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
     {{flagstat_kernel_tma<kFlagstat, 0, 4, 2>, flagstat_kernel_tma<kPospopcnt, 0, 4, 2>},
      kThreads + 32, tma_smem(4)},
     {{flagstat_kernel_tma<kFlagstat, 0, 6, 2>, flagstat_kernel_tma<kPospopcnt, 0, 6, 2>},
      kThreads + 32, tma_smem(6)},
+    {{flagstat_kernel_ring<kFlagstat, 0, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+     kThreads, (size_t)4 * kStageBytes},
     {{flagstat_kernel_ring<kFlagstat, 0, 2, 2>, flagstat_kernel_ring<kPospopcnt, 0, 2, 2>},
      kThreads, (size_t)2 * kStageBytes},
-    {{flagstat_kernel_ring<kFlagstat, 0, 4, 3>, flagstat_kernel_ring<kPospopcnt, 0, 4, 3>},
+    {{flagstat_kernel_ring<kFlagstat, 2, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
      kThreads, (size_t)4 * kStageBytes},
 };
 

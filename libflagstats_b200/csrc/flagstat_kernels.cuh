@@ -107,6 +107,44 @@ __device__ __forceinline__ uint32_t mask_select_h_nosec(uint32_t w)
     return lop3<0xE0>(w, e, 0x0F040F04u);
 }
 
+// Variant T: the two class tests as fp16x2 "tent" functions on the half/FMA pipe
+// instead of two HSET2 compares on the integer ALU pipe.  q = w & 0x0905 per
+// half is a small non-negative fp16 value (a subnormal when SUPPLEMENTARY is
+// clear); with ulp = 2^-24 (bit pattern 0x0001)
+//     u = sat(ulp - |q - 1 ulp|)  is 1 ulp iff q == 0x0001 (G),      else +0
+//     v = sat(ulp - |q - 5 ulp|)  is 1 ulp iff q == 0x0005 (K&UNMAP), else +0
+// (HADD2.SAT clamps below at +0; |.| and - are free operand modifiers), and
+//     e = 203 * u + 192 * v   has the bit pattern 0x00CB, 0x00C0 or 0x0000:
+// exactly the bits G / K&UNMAP records keep in their low byte.  All of this is
+// exact: the operands are integers < 1024 in units of ulp, or so large that the
+// tents are 0.  Six half-pipe instructions replace three ALU-pipe ones.
+__device__ __forceinline__ uint32_t class_bits_t(uint32_t w)
+{
+    const uint32_t q = w & 0x09050905u;
+    uint32_t t1, t5, u, v, m, e;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t1) : "r"(q), "r"(0x80018001u));
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t5) : "r"(q), "r"(0x80058005u));
+    asm("{ .reg .b32 a; abs.f16x2 a, %1; neg.f16x2 a, a; add.rn.sat.f16x2 %0, a, %2; }"
+        : "=r"(u) : "r"(t1), "r"(0x00010001u));
+    asm("{ .reg .b32 a; abs.f16x2 a, %1; neg.f16x2 a, a; add.rn.sat.f16x2 %0, a, %2; }"
+        : "=r"(v) : "r"(t5), "r"(0x00010001u));
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(m) : "r"(v), "r"(0x5A005A00u));             // 192.0
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(e) : "r"(u), "r"(0x5A585A58u), "r"(m));  // 203.0
+    return e;
+}
+
+__device__ __forceinline__ uint32_t mask_select_t(uint32_t w)
+{
+    const uint32_t e = class_bits_t(w);
+    const uint32_t wf = lop3<0x70>(w, w << 3, 0x08000800u);
+    return lop3<0xE0>(wf, e, 0x0F040F04u);
+}
+
+__device__ __forceinline__ uint32_t mask_select_t_nosec(uint32_t w)
+{
+    return lop3<0xE0>(w, class_bits_t(w), 0x0F040F04u);
+}
+
 __device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
 {
     // inline PTX: __byte_perm() documents selector bit 3 as ignored, prmt.b32 does not
@@ -197,10 +235,11 @@ struct Lanes {
             for (int i = 0; i < 16; ++i) y[i] = mask_select_i(w[i]);
         } else if ((wany & 0x01000100u) == 0u) {  // no SECONDARY record in this warp batch
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = mask_select_h_nosec(w[i]);
+            for (int i = 0; i < 16; ++i)
+                y[i] = VARIANT == 2 ? mask_select_t_nosec(w[i]) : mask_select_h_nosec(w[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = mask_select_h(w[i]);
+            for (int i = 0; i < 16; ++i) y[i] = VARIANT == 2 ? mask_select_t(w[i]) : mask_select_h(w[i]);
         }
         all.absorb16(y, b);
         // Any QCFAIL record in this warp batch?  In real data there is none and

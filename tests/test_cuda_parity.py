@@ -31,7 +31,7 @@ def _dev(a, off=0):
     return v
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
     fs = cuda_lib
     prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
@@ -43,6 +43,22 @@ def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
             assert got_h.tolist() == want, ("host", c["name"])
             got_d = fs.flagstat_u64(_dev(a))
             assert got_d.tolist() == want, ("device", c["name"])
+    finally:
+        fs.lib().FLAGSTAT_cuda_set_variant(prev)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 7])
+def test_every_record_value_in_both_register_halves(cuda_lib, variant):
+    """All 65536 FLAG words, once at even and once at odd record positions (low and
+    high half of the packed 32-bit register), and next to every neighbour class."""
+    fs = cuda_lib
+    ar = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    a = np.concatenate([ar, np.zeros(1, np.uint16), ar, ar[::-1], np.full(3, 0x0FFF, np.uint16), ar[::-1]])
+    want = O.flagstat_simd(a).tolist()
+    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    try:
+        assert fs.flagstat_u64(_dev(a)).tolist() == want
+        assert fs.flagstat_u64(_dev(a, 1)).tolist() == want
     finally:
         fs.lib().FLAGSTAT_cuda_set_variant(prev)
 
