@@ -5,7 +5,9 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input: every
 rank runs the sm_100a kernel over ITS shard of the FLAG column (already
-resident in HBM) and the 32 counters are all-reduced over NCCL.  Workload at
+resident in HBM); the same kernel launch exchanges the 32 counters with the
+other ranks through peer-mapped memory (--exchange nccl: a separate NCCL
+all-reduce instead).  Workload at
 any N: BASELINE.json configs[1] per GPU -- 824,541,892 HiSeqX-shaped records
 (1.65 GB, > L2) per rank, rank r holding global records [r*n, (r+1)*n) of the
 periodic generator, so the exact global answer is N x KAT-E (weak scaling).
