@@ -36,6 +36,8 @@ extern "C" {
 #define FLAGSTAT_CUDA_ENOMEM (-3) /* host allocation failed */
 #define FLAGSTAT_CUDA_ESTATE (-4) /* handle used out of order */
 #define FLAGSTAT_CUDA_ETIMEOUT (-5) /* a peer GPU never delivered its counters */
+#define FLAGSTAT_CUDA_EFORMAT (-6) /* malformed block container / LZ4 block */
+#define FLAGSTAT_CUDA_EIO (-7) /* cannot open or read the file */
 
 /* ---- the reference's plugin signature ---------------------------------- */
 
@@ -119,6 +121,31 @@ int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s);
  * whole loop including the final synchronisation. */
 int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, uint64_t* flags,
                                   double* seconds);
+
+/* ---- the reference's FLAG files (benchmark/flagstats.cpp) ------------------
+ *
+ * _RAW: a plain uint16 stream (".bin"), consumed in the reference's 1,024,000-byte
+ *       blocks through the pinned ring (flagstat_raw, flagstats.cpp:415-468).
+ * _LZ4: the container lz4f()/lz4hc() write (:110-186) and lz4_decompress() reads
+ *       (:288-358): repeated [int32 raw_size][int32 comp_size][LZ4 block].  The
+ *       blocks cross PCIe COMPRESSED and are decoded on the GPU (one warp per
+ *       block), then counted from HBM.  N = raw_size >> 1 records per block like
+ *       :323.  Zstd containers (:188-215) are not supported.
+ * flags[32] is accumulated into; *n_records (may be NULL) receives the number of
+ * records counted.  Runs on the current device; synchronous. */
+#define FLAGSTAT_CUDA_FILE_RAW 0
+#define FLAGSTAT_CUDA_FILE_LZ4 1
+int FLAGSTAT_cuda_file_u64(const char* path, int format, uint64_t* flags, uint64_t* n_records);
+/* the same for a container already in host memory */
+int FLAGSTAT_cuda_container_u64(const void* bytes, uint64_t n_bytes, int format, uint64_t* flags,
+                                uint64_t* n_records);
+/* Decode-only aid (tests / tools): n_blocks LZ4 blocks at comp_off[]/comp_size[] of
+ * `comp` are decoded to raw_off[] of `raw` (host memory, raw_total bytes);
+ * status[b] = bytes produced (must equal raw_size[b]) or < 0 for a malformed block. */
+int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+                             const uint32_t* comp_size, const uint64_t* raw_off,
+                             const uint32_t* raw_size, uint32_t n_blocks, void* raw,
+                             uint64_t raw_total, int* status);
 
 /* ---- several GPUs from one process (range shards, host-side sum) --------- */
 

@@ -21,6 +21,7 @@
 #include "flagstat_kernel_tma.cuh"
 #include "flagstat_kernel_group.cuh"
 #include "synth.cuh"
+#include "lz4_block.cuh"
 
 namespace {
 
@@ -774,6 +775,8 @@ const char* FLAGSTAT_cuda_strerror(int code)
         case FLAGSTAT_CUDA_ENOMEM: return "host allocation failed";
         case FLAGSTAT_CUDA_ESTATE: return "handle used out of order";
         case FLAGSTAT_CUDA_ETIMEOUT: return "timed out waiting for a peer GPU's counters";
+        case FLAGSTAT_CUDA_EFORMAT: return "malformed block container / LZ4 block";
+        case FLAGSTAT_CUDA_EIO: return "cannot open or read the file";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -889,3 +892,5 @@ int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d
 }
 
 }  // extern "C"
+
+#include "flagstat_blockfile.inl"

@@ -55,10 +55,10 @@ _oracle = None
 
 def build_oracle(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
-    src = os.path.join(HERE, "flagstat_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "flagstat_oracle.c"), os.path.join(HERE, "lz4_oracle.c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in srcs):
         subprocess.check_call(
-            ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", so, src]
+            ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", so] + srcs
         )
     return so
 
@@ -86,6 +86,10 @@ def oracle():
         lib.oracle_synth_hiseqx.restype = None
         lib.oracle_hiseqx_n.restype = C.c_uint64
         lib.oracle_hiseqx_m.restype = C.c_uint64
+        lib.oracle_lz4_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        lib.oracle_lz4_decompress.restype = C.c_int64
+        lib.oracle_lz4_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        lib.oracle_lz4_compress.restype = C.c_int64
         _oracle = lib
     return _oracle
 
@@ -313,3 +317,71 @@ def best_reference_kernel() -> Optional[str]:
     if reference() is None:
         return None
     return ref_dispatch_name(1 << 20)
+
+
+# --------------------------------------------------------------------------
+# LZ4 block containers (the caller either side of the path)
+# --------------------------------------------------------------------------
+REF_BLOCK_BYTES = 1_024_000
+"""benchmark/flagstats.cpp:119 -- 512,000 records per block."""
+
+
+def lz4_decompress(block: bytes, raw_size: int) -> bytes:
+    """oracle/lz4_oracle.c restatement of LZ4_decompress_safe; raises on malformed input."""
+    out = C.create_string_buffer(max(raw_size, 1))
+    got = oracle().oracle_lz4_decompress(block, len(block), out, raw_size)
+    if got != raw_size:
+        raise ValueError(f"malformed LZ4 block (decoder returned {got}, expected {raw_size})")
+    return out.raw[:raw_size]
+
+
+def lz4_compress(raw: bytes) -> bytes:
+    """Greedy encoder of oracle/lz4_oracle.c (valid LZ4 blocks, not liblz4's choices)."""
+    cap = len(raw) + len(raw) // 255 + 64
+    out = C.create_string_buffer(cap)
+    got = oracle().oracle_lz4_compress(raw, len(raw), out, cap)
+    if got < 0:
+        raise ValueError("compress bound exceeded")
+    return out.raw[:got]
+
+
+def liblz4_compress(raw: bytes) -> bytes:
+    """A real liblz4 (through pyarrow's lz4_raw codec): what the reference's lz4f() calls."""
+    import pyarrow as pa
+
+    return pa.compress(raw, codec="lz4_raw", asbytes=True)
+
+
+def liblz4_decompress(block: bytes, raw_size: int) -> bytes:
+    import pyarrow as pa
+
+    return pa.decompress(block, decompressed_size=raw_size, codec="lz4_raw", asbytes=True)
+
+
+def write_lz4_container(a, block_bytes: int = REF_BLOCK_BYTES, compressor=None) -> bytes:
+    """The file lz4f() writes (benchmark/flagstats.cpp:110-147) for the FLAG column `a`."""
+    import struct
+
+    compressor = compressor or liblz4_compress
+    raw = _as_u16(a).tobytes()
+    out = []
+    for lo in range(0, len(raw), block_bytes):
+        chunk = raw[lo:lo + block_bytes]
+        comp = compressor(chunk)
+        out.append(struct.pack("<ii", len(chunk), len(comp)))
+        out.append(comp)
+    return b"".join(out)
+
+
+def read_lz4_container(blob: bytes, decompressor=None):
+    """Block loop of benchmark/flagstats.cpp:288-358: yields uint16 arrays, one per block."""
+    import struct
+
+    decompressor = decompressor or lz4_decompress
+    pos = 0
+    while pos < len(blob):
+        raw_size, comp_size = struct.unpack_from("<ii", blob, pos)
+        pos += 8
+        chunk = decompressor(blob[pos:pos + comp_size], raw_size)
+        pos += comp_size
+        yield np.frombuffer(chunk[: (raw_size >> 1) * 2], dtype=np.uint16)

@@ -1,0 +1,124 @@
+"""The reference's FLAG files on the GPU: raw .bin streams and
+[int32 raw][int32 comp][LZ4 block] containers (benchmark/flagstats.cpp:110-186,
+288-358, 415-468).  The GPU LZ4 decoder is checked against blocks written by a
+real liblz4 (pyarrow lz4_raw) and by the oracle's own encoder."""
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _columns():
+    rng = np.random.default_rng(5)
+    return [
+        ("hiseqx", O.synth_hiseqx(0, 300_007, 2, 1000)),
+        ("uniform12", O.synth_uniform(0, 70_001, 3, 0x0FFF)),
+        ("runs", np.repeat(rng.integers(0, 4096, 500).astype(np.uint16), rng.integers(1, 3000, 500))),
+        ("constant", np.full(600_000, 99, np.uint16)),
+        ("period3", np.tile(np.array([99, 147, 83], np.uint16), 100_000)),
+        ("tiny", np.array([1, 2, 3], np.uint16)),
+    ]
+
+
+def test_gpu_lz4_decode_matches_original(cuda_lib):
+    from libflagstats_b200 import blockfile
+
+    blocks, sizes, raws = [], [], []
+    for _name, col in _columns():
+        raw = col.tobytes()
+        for comp in (O.liblz4_compress(raw), O.lz4_compress(raw)):
+            blocks.append(comp)
+            sizes.append(len(raw))
+            raws.append(raw)
+    out, status = blockfile.lz4_decode(blocks, sizes)
+    assert status == sizes
+    for got, want in zip(out, raws):
+        assert got == want
+
+
+def test_gpu_lz4_decode_rejects_malformed_blocks(cuda_lib):
+    from libflagstats_b200 import blockfile
+
+    raw = np.tile(np.array([99, 147, 83, 163], np.uint16), 5000).tobytes()
+    comp = O.liblz4_compress(raw)
+    bad_head = bytearray(comp)
+    bad_head[0] = 0x0F
+    out, status = blockfile.lz4_decode([comp, comp[:-3], bytes(bad_head), comp],
+                                       [len(raw), len(raw), len(raw), len(raw) - 10])
+    assert status[0] == len(raw) and out[0] == raw
+    assert status[1] != len(raw)
+    assert status[2] < 0
+    assert status[3] < 0
+
+
+@pytest.mark.parametrize("compressor", ["liblz4", "oracle"])
+def test_lz4_container_counts_match_the_column(cuda_lib, compressor):
+    from libflagstats_b200 import blockfile
+
+    comp = O.liblz4_compress if compressor == "liblz4" else O.lz4_compress
+    # 131 blocks: more than one decode batch (128), ragged last block
+    col = O.synth_hiseqx(0, 130 * 512_000 + 77_777, 3, 2000)
+    blob = O.write_lz4_container(col, compressor=comp)
+    f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
+    assert n == col.size
+    assert f.tolist() == O.numpy_flagstat(col).tolist()
+    # accumulate contract + small blocks of odd byte size (the reference drops the odd byte, :323)
+    small = O.synth_uniform(0, 10_001, 4, 0x0FFF)
+    raw = small.tobytes()[:-1]  # 20,001 bytes: 10,000 whole records + one stray byte
+    blob2 = struct.pack("<ii", len(raw), len(comp(raw))) + comp(raw)
+    blob2 += O.write_lz4_container(small[:777], compressor=comp)
+    f2, n2 = blockfile.flagstat_container(blob2, blockfile.LZ4, flags=f.copy())
+    assert n2 == 10_000 + 777
+    want = O.numpy_flagstat(col) + O.flagstat_simd(small[:10_000]) + O.flagstat_simd(small[:777])
+    assert f2.tolist() == want.tolist()
+
+
+def test_corrupt_container_is_an_error_and_leaves_flags_alone(cuda_lib):
+    from libflagstats_b200 import FlagstatCudaError, blockfile
+
+    col = O.synth_hiseqx(0, 600_000, 1, 0)
+    blob = bytearray(O.write_lz4_container(col))
+    blob[8 + 100] ^= 0xFF  # damage the first payload
+    blob[8 + 101] ^= 0xFF
+    flags = np.full(32, 5, np.uint64)
+    try:
+        blockfile.flagstat_container(bytes(blob), blockfile.LZ4, flags=flags)
+        damaged_but_decodable = True  # a flipped literal still decodes: then counts must differ or equal
+    except FlagstatCudaError as exc:
+        damaged_but_decodable = False
+        assert exc.code == -6
+        assert (flags == 5).all()
+    with pytest.raises(FlagstatCudaError) as ei:
+        blockfile.flagstat_container(bytes(blob[:-5]), blockfile.LZ4, flags=flags)  # truncated payload
+    assert ei.value.code == -6
+    with pytest.raises(FlagstatCudaError):
+        blockfile.flagstat_container(struct.pack("<ii", -4, 10) + b"x" * 10, blockfile.LZ4)
+    assert damaged_but_decodable in (True, False)
+
+
+def test_files_raw_and_lz4(cuda_lib, tmp_path):
+    from libflagstats_b200 import FlagstatCudaError, blockfile
+
+    col = O.synth_hiseqx(0, 9 * 512_000 + 4_321, 7, 3000)
+    want = O.numpy_flagstat(col).tolist()
+    p_raw = tmp_path / "flags.bin"
+    p_raw.write_bytes(col.tobytes() + b"\x07")  # odd trailing byte: dropped like flagstats.cpp:455
+    f, n = blockfile.flagstat_file(str(p_raw))
+    assert n == col.size and f.tolist() == want
+    p_lz4 = tmp_path / "flags_fast_a2.lz4"
+    p_lz4.write_bytes(O.write_lz4_container(col))
+    f, n = blockfile.flagstat_file(str(p_lz4))
+    assert n == col.size and f.tolist() == want
+    p_empty = tmp_path / "empty.bin"
+    p_empty.write_bytes(b"")
+    f, n = blockfile.flagstat_file(str(p_empty))
+    assert n == 0 and not f.any()
+    with pytest.raises(FlagstatCudaError) as ei:
+        blockfile.flagstat_file(str(tmp_path / "missing.lz4"))
+    assert ei.value.code == -7
+    with pytest.raises(ValueError):
+        blockfile.flagstat_file(str(tmp_path / "flags.zst"))
