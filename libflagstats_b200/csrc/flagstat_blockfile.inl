@@ -44,10 +44,51 @@ struct ByteSource {
 
 constexpr uint32_t kRefBlockBytes = 1024000u;          // benchmark/flagstats.cpp:119
 constexpr uint32_t kMaxRawBlock = 8u << 20;            // sanity bound on a header's raw_size
-constexpr int kBatchBlocks = 128;
-constexpr size_t kBatchRawCap = (size_t)kBatchBlocks * kRefBlockBytes;
-constexpr size_t kBatchCompCap = kBatchRawCap + (kBatchRawCap / 255) + 16u * kBatchBlocks + 4096u;
+// One decode launch needs thousands of blocks to fill the GPU (one warp per block, 12 warps
+// per SM): a batch is up to kBatchBlocks blocks / kBatchRawCap decoded bytes.
+constexpr int kBatchBlocks = 2048;
+constexpr size_t kBatchRawCap = (size_t)1 << 31;
 
+bool file_debug()
+{
+    static const bool on = std::getenv("FLAGSTAT_CUDA_DEBUG") != nullptr;
+    return on;
+}
+
+int io_threads()
+{
+    int t = 6;
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_IO_THREADS")) t = std::atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && t > hw) t = hw;
+    if (t < 1) t = 1;
+    if (t > 16) t = 16;
+    return t;
+}
+
+int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status,
+               uint32_t n_blocks, cudaStream_t st)
+{
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] {
+        attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem);
+    });
+    if (attr_rc != cudaSuccess) return (int)attr_rc;
+    const unsigned grid = (n_blocks + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
+    lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4Smem, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+struct BlockInfo {
+    uint64_t src_off;  // payload position in the file / memory image
+    uint32_t comp, raw;
+};
+
+// staging of one batch; capacities grow on demand and the buffers are pooled across calls
 struct Lz4Lane {
     unsigned char* h_comp = nullptr;   // pinned
     unsigned char* d_comp = nullptr;
@@ -56,6 +97,8 @@ struct Lz4Lane {
     Lz4BlockDesc* d_desc = nullptr;
     int* h_status = nullptr;           // pinned
     int* d_status = nullptr;
+    size_t comp_cap = 0, raw_cap = 0;
+    int blk_cap = 0;
     cudaStream_t st = nullptr;
     int n = 0;            // blocks in flight
     bool busy = false;
@@ -75,16 +118,42 @@ void lz4_lane_free(Lz4Lane& l)
     l = Lz4Lane();
 }
 
-int lz4_lane_alloc(Lz4Lane& l)
+int lz4_lane_reserve(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, int blocks)
 {
-    CK(cudaMallocHost(&l.h_comp, kBatchCompCap));
-    CK(cudaMalloc(&l.d_comp, kBatchCompCap));
-    CK(cudaMalloc(&l.d_raw, kBatchRawCap + 256));  // + one pad byte per odd-sized block
-    CK(cudaMallocHost(&l.h_desc, kBatchBlocks * sizeof(Lz4BlockDesc)));
-    CK(cudaMalloc(&l.d_desc, kBatchBlocks * sizeof(Lz4BlockDesc)));
-    CK(cudaMallocHost(&l.h_status, kBatchBlocks * sizeof(int)));
-    CK(cudaMalloc(&l.d_status, kBatchBlocks * sizeof(int)));
-    CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    if (comp_bytes > l.comp_cap) {
+        if (l.h_comp) cudaFreeHost(l.h_comp);
+        if (l.d_comp) cudaFree(l.d_comp);
+        l.h_comp = nullptr;
+        l.d_comp = nullptr;
+        l.comp_cap = 0;
+        const size_t cap = comp_bytes + comp_bytes / 8 + 4096;
+        CK(cudaMallocHost(&l.h_comp, cap));
+        CK(cudaMalloc(&l.d_comp, cap));
+        l.comp_cap = cap;
+    }
+    if (raw_bytes > l.raw_cap) {
+        if (l.d_raw) cudaFree(l.d_raw);
+        l.d_raw = nullptr;
+        l.raw_cap = 0;
+        const size_t cap = raw_bytes + raw_bytes / 8 + 4096;
+        CK(cudaMalloc(&l.d_raw, cap));
+        l.raw_cap = cap;
+    }
+    if (blocks > l.blk_cap) {
+        if (l.h_desc) cudaFreeHost(l.h_desc);
+        if (l.d_desc) cudaFree(l.d_desc);
+        if (l.h_status) cudaFreeHost(l.h_status);
+        if (l.d_status) cudaFree(l.d_status);
+        l.h_desc = nullptr; l.d_desc = nullptr; l.h_status = nullptr; l.d_status = nullptr;
+        l.blk_cap = 0;
+        const int cap = blocks + blocks / 4 + 16;
+        CK(cudaMallocHost(&l.h_desc, cap * sizeof(Lz4BlockDesc)));
+        CK(cudaMalloc(&l.d_desc, cap * sizeof(Lz4BlockDesc)));
+        CK(cudaMallocHost(&l.h_status, cap * sizeof(int)));
+        CK(cudaMalloc(&l.d_status, cap * sizeof(int)));
+        l.blk_cap = cap;
+    }
     return 0;
 }
 
@@ -105,18 +174,31 @@ int lz4_lane_ship(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even
     if (l.n == 0) return 0;
     CK(cudaMemcpyAsync(l.d_comp, l.h_comp, comp_bytes, cudaMemcpyHostToDevice, l.st));
     CK(cudaMemcpyAsync(l.d_desc, l.h_desc, l.n * sizeof(Lz4BlockDesc), cudaMemcpyHostToDevice, l.st));
-    const unsigned grid = (unsigned)((l.n + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta);
-    lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, 0, l.st>>>(l.d_comp, l.d_raw, l.d_desc, l.d_status,
-                                                              (uint32_t)l.n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CK(cudaGetLastError());
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (file_debug()) {
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, l.st));
+    }
+    int rc = lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st);
+    if (rc) return rc;
+    if (file_debug()) {
+        CK(cudaEventRecord(e1, l.st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::fprintf(stderr, "[flagstat_cuda] lz4 decode: %d blocks, %zu -> %zu bytes, %.3f ms (%.1f GB/s out)\n",
+                     l.n, comp_bytes, raw_bytes, ms, raw_bytes / (ms * 1e6));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     if (all_even) {  // the decoded blocks are one contiguous run of whole records
-        const int rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw), raw_bytes / 2, d_flags, l.st);
+        rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw), raw_bytes / 2, d_flags, l.st);
         if (rc) return rc;
     } else {         // a block with an odd byte count: the reference drops that byte (N = size >> 1)
         for (int b = 0; b < l.n; ++b) {
-            const int rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw + l.h_desc[b].raw_off),
-                                  l.h_desc[b].raw_size / 2, d_flags, l.st);
+            rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw + l.h_desc[b].raw_off),
+                        l.h_desc[b].raw_size / 2, d_flags, l.st);
             if (rc) return rc;
         }
     }
@@ -125,75 +207,162 @@ int lz4_lane_ship(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even
     return 0;
 }
 
-int consume_lz4(ByteSource& src, uint64_t* totals, uint64_t* n_records)
-{
+struct Lz4Ctx {
     Lz4Lane lanes[2];
     uint64_t* d_flags = nullptr;
-    struct Cleanup {
-        Lz4Lane* l;
-        uint64_t** f;
-        ~Cleanup()
-        {
-            lz4_lane_free(l[0]);
-            lz4_lane_free(l[1]);
-            if (*f) cudaFree(*f);
+    int dev = -1;
+};
+std::mutex g_file_mu;
+std::vector<Lz4Ctx*> g_lz4_pool[kMaxDevices];
+
+int lz4_ctx_acquire(Lz4Ctx** out)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_file_mu);
+        if (!g_lz4_pool[dev].empty()) {
+            *out = g_lz4_pool[dev].back();
+            g_lz4_pool[dev].pop_back();
+            return 0;
         }
-    } cleanup{lanes, &d_flags};
-    for (auto& l : lanes) {
-        const int rc = lz4_lane_alloc(l);
-        if (rc) return rc;
     }
-    CK(cudaMalloc(&d_flags, 32 * sizeof(uint64_t)));
-    CK(cudaMemset(d_flags, 0, 32 * sizeof(uint64_t)));
-    uint64_t records = 0;
-    int cur = 0;
-    bool done = false;
-    while (!done) {
-        Lz4Lane& l = lanes[cur];
-        int rc = lz4_lane_retire(l);  // its previous batch must be off the staging buffers
-        if (rc) return rc;
+    Lz4Ctx* c = new (std::nothrow) Lz4Ctx();
+    if (!c) return FLAGSTAT_CUDA_ENOMEM;
+    c->dev = dev;
+    CK(cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t)));
+    *out = c;
+    return 0;
+}
+
+void lz4_ctx_release(Lz4Ctx* c)
+{
+    for (auto& l : c->lanes) {
+        if (l.st) cudaStreamSynchronize(l.st);
+        l.busy = false;
         l.n = 0;
-        size_t comp_bytes = 0, raw_bytes = 0;
+    }
+    std::lock_guard<std::mutex> lk(g_file_mu);
+    g_lz4_pool[c->dev].push_back(c);
+}
+
+// Walk the container's headers: [int32 raw][int32 comp][comp bytes] ... (flagstats.cpp:312-314)
+int lz4_index(ByteSource& src, int fd, uint64_t total, std::vector<BlockInfo>& idx)
+{
+    uint64_t pos = 0;
+    while (pos < total) {
+        int32_t hdr[2];
+        if (total - pos < sizeof(hdr)) return FLAGSTAT_CUDA_EFORMAT;
+        if (src.mem) std::memcpy(hdr, src.mem + pos, sizeof(hdr));
+        else if (::pread(fd, hdr, sizeof(hdr), (off_t)pos) != (ssize_t)sizeof(hdr)) return FLAGSTAT_CUDA_EIO;
+        pos += sizeof(hdr);
+        if (hdr[0] < 0 || hdr[1] <= 0 || (uint32_t)hdr[0] > kMaxRawBlock || (uint64_t)hdr[1] > total - pos)
+            return FLAGSTAT_CUDA_EFORMAT;
+        idx.push_back(BlockInfo{pos, (uint32_t)hdr[1], (uint32_t)hdr[0]});
+        pos += (uint64_t)hdr[1];
+    }
+    return 0;
+}
+
+int consume_lz4(ByteSource& src, uint64_t* totals, uint64_t* n_records)
+{
+    int fd = -1;
+    uint64_t total = src.size;
+    if (src.fp) {
+        struct stat sb;
+        fd = ::fileno(src.fp);
+        if (fd < 0 || ::fstat(fd, &sb) != 0) return FLAGSTAT_CUDA_EIO;
+        total = (uint64_t)sb.st_size;
+    }
+    std::vector<BlockInfo> idx;
+    int rc = lz4_index(src, fd, total, idx);
+    if (rc) return rc;
+
+    Lz4Ctx* ctx = nullptr;
+    rc = lz4_ctx_acquire(&ctx);
+    if (rc) return rc;
+    struct Cleanup {
+        Lz4Ctx* c;
+        ~Cleanup() { lz4_ctx_release(c); }
+    } cleanup{ctx};
+    Lz4Lane* lanes = ctx->lanes;
+    uint64_t* d_flags = ctx->d_flags;
+    CK(cudaMemset(d_flags, 0, 32 * sizeof(uint64_t)));
+
+    const int T = io_threads();
+    int batch_blocks = kBatchBlocks;
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_LZ4_BATCH")) {  // tests: force several batches
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= kBatchBlocks) batch_blocks = v;
+    }
+    uint64_t records = 0;
+    size_t first = 0;
+    int cur = 0;
+    while (first < idx.size()) {
+        // batch [first, last): layout of the payloads (16-byte aligned) and of the decoded blocks
+        size_t last = first, comp_bytes = 0, raw_bytes = 0;
         bool all_even = true;
-        while (l.n < kBatchBlocks) {
-            if (src.at_end()) {
-                done = true;
-                break;
-            }
-            int32_t hdr[2];
-            if (src.read(hdr, sizeof(hdr)) != sizeof(hdr)) return FLAGSTAT_CUDA_EFORMAT;
-            if (hdr[0] < 0 || hdr[1] <= 0 || (uint32_t)hdr[0] > kMaxRawBlock ||
-                (uint32_t)hdr[1] > kMaxRawBlock + kMaxRawBlock / 255 + 16)
-                return FLAGSTAT_CUDA_EFORMAT;
-            const size_t comp_at = (comp_bytes + 15u) & ~(size_t)15u;
-            if (comp_at + (size_t)hdr[1] > kBatchCompCap || raw_bytes + (size_t)hdr[0] > kBatchRawCap) {
-                if (l.n == 0) return FLAGSTAT_CUDA_EFORMAT;  // one block larger than a whole batch
-                // does not fit: rewind the header and close the batch
-                if (src.fp) std::fseek(src.fp, -(long)sizeof(hdr), SEEK_CUR);
-                src.pos -= sizeof(hdr);
-                break;
-            }
-            if (src.read(l.h_comp + comp_at, (size_t)hdr[1]) != (size_t)hdr[1]) return FLAGSTAT_CUDA_EFORMAT;
-            Lz4BlockDesc& d = l.h_desc[l.n];
-            d.comp_off = comp_at;
-            d.comp_size = (uint32_t)hdr[1];
-            d.raw_off = raw_bytes;
-            d.raw_size = (uint32_t)hdr[0];
-            comp_bytes = comp_at + (size_t)hdr[1];
-            raw_bytes += (size_t)hdr[0];
-            if (hdr[0] & 1) {
-                all_even = false;
-                raw_bytes += 1;  // keep every block's first record 2-byte aligned
-            }
-            records += (uint64_t)hdr[0] >> 1;
-            ++l.n;
+        while (last < idx.size() && (int)(last - first) < batch_blocks) {
+            const size_t r = idx[last].raw + (idx[last].raw & 1u);  // keep every block 2-byte aligned
+            if (last > first && raw_bytes + r > kBatchRawCap) break;
+            comp_bytes = ((comp_bytes + 15u) & ~(size_t)15u) + idx[last].comp;
+            raw_bytes += r;
+            all_even = all_even && (idx[last].raw & 1u) == 0u;
+            ++last;
         }
-        rc = lz4_lane_ship(l, comp_bytes, raw_bytes, all_even, d_flags);
+        Lz4Lane& l = lanes[cur];
+        rc = lz4_lane_retire(l);  // its previous batch must be off the staging buffers
+        if (rc) return rc;
+        rc = lz4_lane_reserve(l, comp_bytes, raw_bytes, (int)(last - first));
+        if (rc) return rc;
+        l.n = (int)(last - first);
+        size_t c = 0, r = 0;
+        for (size_t b = first; b < last; ++b) {
+            c = (c + 15u) & ~(size_t)15u;
+            l.h_desc[b - first] = Lz4BlockDesc{c, r, idx[b].comp, idx[b].raw};
+            c += idx[b].comp;
+            r += idx[b].raw + (idx[b].raw & 1u);
+            records += idx[b].raw >> 1;
+        }
+        // gather the payloads into the pinned staging buffer with T threads
+        std::atomic<int> err{0};
+        auto gather = [&](int t) {
+            for (size_t b = first + (size_t)t; b < last; b += (size_t)T) {
+                unsigned char* dst = l.h_comp + l.h_desc[b - first].comp_off;
+                if (src.mem) {
+                    std::memcpy(dst, src.mem + idx[b].src_off, idx[b].comp);
+                } else {
+                    size_t got = 0;
+                    while (got < idx[b].comp) {
+                        const ssize_t k = ::pread(fd, dst + got, idx[b].comp - got, (off_t)(idx[b].src_off + got));
+                        if (k <= 0) {
+                            err.store(FLAGSTAT_CUDA_EIO);
+                            return;
+                        }
+                        got += (size_t)k;
+                    }
+                }
+            }
+        };
+        {
+            std::vector<std::thread> th;
+            const int use = (l.n < 4 * T) ? 1 : T;  // not worth threads for a handful of blocks
+            if (use == 1) {
+                for (int t = 0; t < T; ++t) gather(t);
+            } else {
+                for (int t = 1; t < T; ++t) th.emplace_back(gather, t);
+                gather(0);
+                for (auto& x : th) x.join();
+            }
+        }
+        if (err.load()) return err.load();
+        rc = lz4_lane_ship(l, c, r, all_even, d_flags);
         if (rc) return rc;
         cur ^= 1;
+        first = last;
     }
-    for (auto& l : lanes) {
-        const int rc = lz4_lane_retire(l);
+    for (int i = 0; i < 2; ++i) {
+        rc = lz4_lane_retire(lanes[i]);
         if (rc) return rc;
     }
     CK(cudaMemcpy(totals, d_flags, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -201,33 +370,131 @@ int consume_lz4(ByteSource& src, uint64_t* totals, uint64_t* n_records)
     return 0;
 }
 
-int consume_raw(ByteSource& src, uint64_t* totals, uint64_t* n_records)
+// Raw ".bin" files: T reader threads, each with two private ring slots (8 blocks = 8,192,000
+// bytes each: the coalesced-DMA size of the block stream).  A thread pread()s its next
+// group straight into a pinned slot, enqueues one DMA + one kernel on the slot's stream and
+// moves to its other slot, so the page-cache copy of group k+1 overlaps DMA + count of group
+// k, and T such pipelines run side by side (one reader thread tops out at ~5 GB/s).
+constexpr size_t kRawSlotBytes = 8u * (size_t)kRefBlockBytes;
+constexpr int kRawMaxThreads = 16;
+
+struct RawCtx {
+    int dev = -1;
+    int threads = 0;
+    unsigned char* h = nullptr;  // pinned, threads * 2 slots
+    unsigned char* d = nullptr;
+    cudaStream_t st[2 * kRawMaxThreads] = {};
+    uint64_t* d_flags = nullptr;
+};
+std::vector<RawCtx*> g_raw_pool[kMaxDevices];
+
+int raw_ctx_acquire(RawCtx** out)
 {
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    FLAGSTAT_cuda_stream* s = nullptr;
-    int rc = FLAGSTAT_cuda_stream_open_ex(&s, dev, kRefBlockBytes / 2, 4, FLAGSTAT_CUDA_STREAM_DMA, 8);
-    if (rc) return rc;
-    uint64_t records = 0;
-    for (;;) {
-        uint16_t* slot = FLAGSTAT_cuda_stream_acquire(s);
-        if (!slot) {
-            rc = FLAGSTAT_CUDA_ESTATE;
-            break;
+    const int want = io_threads();
+    {
+        std::lock_guard<std::mutex> lk(g_file_mu);
+        auto& pool = g_raw_pool[dev];
+        for (size_t i = 0; i < pool.size(); ++i)
+            if (pool[i]->threads == want) {
+                *out = pool[i];
+                pool.erase(pool.begin() + (long)i);
+                return 0;
+            }
+    }
+    RawCtx* c = new (std::nothrow) RawCtx();
+    if (!c) return FLAGSTAT_CUDA_ENOMEM;
+    c->dev = dev;
+    c->threads = want;
+    CK(cudaHostAlloc(&c->h, (size_t)want * 2 * kRawSlotBytes, cudaHostAllocPortable));
+    CK(cudaMalloc(&c->d, (size_t)want * 2 * kRawSlotBytes));
+    for (int i = 0; i < 2 * want; ++i) CK(cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t)));
+    *out = c;
+    return 0;
+}
+
+void raw_ctx_release(RawCtx* c)
+{
+    std::lock_guard<std::mutex> lk(g_file_mu);
+    g_raw_pool[c->dev].push_back(c);
+}
+
+int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
+{
+    RawCtx* c = nullptr;
+    {
+        const int rc = raw_ctx_acquire(&c);
+        if (rc) return rc;
+    }
+    struct Cleanup {
+        RawCtx* c;
+        ~Cleanup() { raw_ctx_release(c); }
+    } cleanup{c};
+    CK(cudaMemset(c->d_flags, 0, 32 * sizeof(uint64_t)));
+    const uint64_t n_groups = (size + kRawSlotBytes - 1) / kRawSlotBytes;
+    std::atomic<int> err{0};
+    auto worker = [&](int t) {
+        if (cudaSetDevice(c->dev) != cudaSuccess) {
+            err.store(FLAGSTAT_CUDA_ENODEV);
+            return;
         }
-        const size_t got = src.read(slot, kRefBlockBytes);
-        rc = FLAGSTAT_cuda_stream_submit(s, (uint32_t)(got >> 1));  // an odd trailing byte is dropped, like :455
-        if (rc) break;
-        records += got >> 1;
-        if (got < kRefBlockBytes) break;
+        int k = 0;
+        for (uint64_t g = (uint64_t)t; g < n_groups && err.load() == 0; g += (uint64_t)c->threads, ++k) {
+            const int slot = 2 * t + (k & 1);
+            unsigned char* h = c->h + (size_t)slot * kRawSlotBytes;
+            unsigned char* d = c->d + (size_t)slot * kRawSlotBytes;
+            const uint64_t off = g * kRawSlotBytes;
+            const size_t len = (size_t)((size - off < kRawSlotBytes) ? (size - off) : kRawSlotBytes);
+            if (cudaStreamSynchronize(c->st[slot]) != cudaSuccess) {  // slot's previous DMA is done
+                err.store(FLAGSTAT_CUDA_EIO);
+                return;
+            }
+            size_t got = 0;
+            while (got < len) {
+                const ssize_t r = ::pread(fd, h + got, len - got, (off_t)(off + got));
+                if (r <= 0) {
+                    err.store(FLAGSTAT_CUDA_EIO);
+                    return;
+                }
+                got += (size_t)r;
+            }
+            const uint64_t recs = len >> 1;  // only the last group can carry an odd byte; dropped like :455
+            if (recs == 0) continue;
+            if (cudaMemcpyAsync(d, h, recs * 2, cudaMemcpyHostToDevice, c->st[slot]) != cudaSuccess) {
+                err.store(FLAGSTAT_CUDA_EIO);
+                return;
+            }
+            const int rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(d), recs, c->d_flags, c->st[slot]);
+            if (rc) {
+                err.store(rc);
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < c->threads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
+    for (int i = 0; i < 2 * c->threads; ++i) CK(cudaStreamSynchronize(c->st[i]));
+    if (err.load()) return err.load();
+    CK(cudaMemcpy(totals, c->d_flags, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *n_records = size >> 1;
+    return 0;
+}
+
+int consume_raw(ByteSource& src, uint64_t* totals, uint64_t* n_records)
+{
+    if (src.fp) {
+        struct stat sb;
+        const int fd = ::fileno(src.fp);
+        if (fd < 0 || ::fstat(fd, &sb) != 0) return FLAGSTAT_CUDA_EIO;
+        return consume_raw_fd(fd, (uint64_t)sb.st_size, totals, n_records);
     }
-    if (!rc) {
-        for (int i = 0; i < 32; ++i) totals[i] = 0;
-        rc = FLAGSTAT_cuda_stream_finish(s, totals);
-    }
-    FLAGSTAT_cuda_stream_close(s);
-    *n_records = records;
-    return rc;
+    // already in host memory: the host-pointer path of FLAGSTAT_cuda_u64 (chunked, overlapped staging)
+    *n_records = src.size >> 1;
+    return run_sync(kFlagstat, reinterpret_cast<const uint16_t*>(src.mem), src.size >> 1, totals);
 }
 
 int consume(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
@@ -300,10 +567,7 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
         if ((rc = (int)cudaMemcpy(d_comp, comp, comp_bytes, cudaMemcpyHostToDevice))) break;
         if ((rc = (int)cudaMemset(d_raw, 0, raw_total ? raw_total : 1))) break;
         if ((rc = (int)cudaMemcpy(d_desc, desc.data(), n_blocks * sizeof(Lz4BlockDesc), cudaMemcpyHostToDevice))) break;
-        const unsigned grid = (n_blocks + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
-        lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if ((rc = (int)cudaGetLastError())) break;
+        if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr))) break;
         if ((rc = (int)cudaMemcpy(raw, d_raw, raw_total, cudaMemcpyDeviceToHost))) break;
         if ((rc = (int)cudaMemcpy(status, d_status, n_blocks * sizeof(int), cudaMemcpyDeviceToHost))) break;
     } while (0);

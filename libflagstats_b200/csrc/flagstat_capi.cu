@@ -14,6 +14,9 @@
 #include <thread>
 #include <vector>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cuda_runtime.h>
 
 #include "../../include/flagstats_cuda.h"

@@ -35,14 +35,97 @@ struct Lz4BlockDesc {
 };
 
 constexpr int kLz4WarpsPerCta = 4;
+constexpr uint32_t kLz4Win = 16384;  // bytes of a block's most recent output mirrored in shared memory
+constexpr uint32_t kLz4Unroll = 8;   // independent byte loads in flight per lane and copy step
+constexpr size_t kLz4Smem = (size_t)kLz4WarpsPerCta * kLz4Win;
+
+// One warp's view of the block it is decoding: global output + a shared-memory ring that
+// mirrors the last kLz4Win bytes.  Short matches -- the latency-critical ones: a block of
+// FLAG words is ~10^5 sequences of a few bytes each -- read their source from the ring
+// (~30 cycles) instead of from L2 (~300 cycles: global stores are not kept in L1).
+struct Lz4Out {
+    uint8_t* g;      // global output of this block
+    uint8_t* ring;   // this warp's kLz4Win bytes of shared memory
+    __device__ __forceinline__ void put(uint32_t pos, uint8_t v) const
+    {
+        g[pos] = v;
+        ring[pos & (kLz4Win - 1u)] = v;
+    }
+};
+
+// out[op + i] = src[i], i < n: literals from the compressed stream (never aliases the output)
+__device__ __forceinline__ void warp_literals(const Lz4Out& o, uint32_t op, const uint8_t* __restrict__ src,
+                                              uint32_t n, uint32_t lane)
+{
+    uint32_t i = lane;
+    for (; i + 32u * (kLz4Unroll - 1u) < n; i += 32u * kLz4Unroll) {
+        uint8_t v[kLz4Unroll];
+#pragma unroll
+        for (uint32_t u = 0; u < kLz4Unroll; ++u) v[u] = src[i + 32u * u];
+#pragma unroll
+        for (uint32_t u = 0; u < kLz4Unroll; ++u) o.put(op + i + 32u * u, v[u]);
+    }
+    for (; i < n; i += 32u) o.put(op + i, src[i]);
+}
+
+// out[op + i] = out[op - offset + (i % offset)], i < n.  For offset >= n that is a plain copy,
+// for offset < n the LZ4 overlapping match (periodic extension of the last `offset` bytes).
+// All source bytes were produced by earlier sequences (the caller has synchronised the warp).
+// FROM_RING requires offset + n <= kLz4Win: then no byte written here reuses a ring slot
+// that still holds a source byte.
+template <bool FROM_RING>
+__device__ __forceinline__ void warp_match(const Lz4Out& o, uint32_t op, uint32_t offset, uint32_t n,
+                                           uint32_t lane)
+{
+    const uint32_t base = op - offset;
+    if (offset >= n) {  // plain copy: no index arithmetic modulo the period
+        uint32_t i = lane;
+        for (; i + 32u * (kLz4Unroll - 1u) < n; i += 32u * kLz4Unroll) {
+            uint8_t v[kLz4Unroll];
+#pragma unroll
+            for (uint32_t u = 0; u < kLz4Unroll; ++u) {
+                const uint32_t p = base + i + 32u * u;
+                v[u] = FROM_RING ? o.ring[p & (kLz4Win - 1u)] : o.g[p];
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < kLz4Unroll; ++u) o.put(op + i + 32u * u, v[u]);
+        }
+        for (; i < n; i += 32u) {
+            const uint32_t p = base + i;
+            o.put(op + i, FROM_RING ? o.ring[p & (kLz4Win - 1u)] : o.g[p]);
+        }
+        return;
+    }
+    const uint32_t step = 32u % offset;  // a lane's phase advances by this (mod offset) per 32 bytes
+    uint32_t r = lane % offset;
+    uint32_t i = lane;
+    for (; i + 32u * (kLz4Unroll - 1u) < n; i += 32u * kLz4Unroll) {
+        uint8_t v[kLz4Unroll];
+#pragma unroll
+        for (uint32_t u = 0; u < kLz4Unroll; ++u) {
+            v[u] = FROM_RING ? o.ring[(base + r) & (kLz4Win - 1u)] : o.g[base + r];
+            r += step;
+            if (r >= offset) r -= offset;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < kLz4Unroll; ++u) o.put(op + i + 32u * u, v[u]);
+    }
+    for (; i < n; i += 32u) {
+        const uint8_t v = FROM_RING ? o.ring[(base + r) & (kLz4Win - 1u)] : o.g[base + r];
+        o.put(op + i, v);
+        r += step;
+        if (r >= offset) r -= offset;
+    }
+}
 
 // Returns the number of bytes produced, or a negative code for a malformed block.
 __device__ __forceinline__ int lz4_decode_block_warp(const uint8_t* __restrict__ in, uint32_t in_size,
-                                                      uint8_t* out, uint32_t out_cap, uint32_t lane)
+                                                      const Lz4Out& o, uint32_t out_cap, uint32_t lane)
 {
     uint32_t ip = 0, op = 0;
-    while (ip < in_size) {
-        const uint32_t token = in[ip++];
+    if (in_size == 0u) return 0;
+    uint32_t token = in[ip++];
+    for (;;) {
         uint32_t lit = token >> 4;
         if (lit == 15u) {
             uint32_t b;
@@ -53,49 +136,81 @@ __device__ __forceinline__ int lz4_decode_block_warp(const uint8_t* __restrict__
             } while (b == 255u);
         }
         if (lit > in_size - ip || lit > out_cap - op) return -2;
-        for (uint32_t i = lane; i < lit; i += 32u) out[op + i] = in[ip + i];
+        const uint32_t lit_at = ip;
         ip += lit;
-        op += lit;
-        if (ip >= in_size) break;  // the last sequence has no match part
-        if (in_size - ip < 2u) return -3;
-        const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);
-        ip += 2;
-        uint32_t ml = token & 15u;
-        if (ml == 15u) {
-            uint32_t b;
-            do {
-                if (ip >= in_size) return -1;
-                b = in[ip++];
-                ml += b;
-            } while (b == 255u);
+        const bool last = ip >= in_size;  // the last sequence has no match part
+        uint32_t offset = 0u, ml = 0u;
+        if (!last) {
+            if (in_size - ip < 2u) return -3;
+            offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);
+            ip += 2;
+            ml = token & 15u;
+            if (ml == 15u) {
+                uint32_t b;
+                do {
+                    if (ip >= in_size) return -1;
+                    b = in[ip++];
+                    ml += b;
+                } while (b == 255u);
+            }
+            ml += 4u;
+            if (offset == 0u || offset > op + lit || ml > out_cap - op - lit) return -4;
         }
-        ml += 4u;
-        if (offset == 0u || offset > op || ml > out_cap - op) return -4;
-        __syncwarp();  // the literals (and everything before them) are visible to every lane
-        const uint8_t* src = out + (op - offset);
-        if (offset >= ml) {
-            for (uint32_t i = lane; i < ml; i += 32u) out[op + i] = src[i];
-        } else {  // overlapping match: periodic extension of the last `offset` bytes
-            for (uint32_t i = lane; i < ml; i += 32u) out[op + i] = src[i % offset];
+        // the next token's address is known before any byte is copied: have it in flight
+        const bool more = !last && ip < in_size;
+        const uint32_t next_token = more ? in[ip] : 0u;
+
+        if (!last && lit <= 32u && ml <= 32u) {
+            // Fast path -- a block of FLAG words is ~10^5 sequences of a few bytes each, so the
+            // serial chain is instruction-latency bound: one byte per lane, no loops, and the
+            // match source comes from the shared-memory ring whenever it is near enough.
+            if (lane < lit) o.put(op + lane, in[lit_at + lane]);
+            op += lit;
+            __syncwarp();  // the literals (and everything before them) are visible to every lane
+            if (lane < ml) {
+                uint32_t rel = lane;
+                if (offset < ml) rel = lane % offset;  // warp-uniform branch: overlapping match
+                const uint32_t sidx = op - offset + rel;
+                const uint8_t v = (offset <= kLz4Win - 32u) ? o.ring[sidx & (kLz4Win - 1u)] : o.g[sidx];
+                o.put(op + lane, v);
+            }
+            op += ml;
+            __syncwarp();
+        } else {
+            warp_literals(o, op, in + lit_at, lit, lane);
+            op += lit;
+            if (last) break;
+            __syncwarp();
+            if (offset + ml <= kLz4Win) warp_match<true>(o, op, offset, ml, lane);
+            else warp_match<false>(o, op, offset, ml, lane);
+            op += ml;
+            __syncwarp();
         }
-        op += ml;
-        __syncwarp();
+        if (!more) break;
+        token = next_token;
+        ++ip;
     }
     return (int)op;
 }
 
 // status[b] = decoded size (must equal raw_size) or a negative error code
 __global__ void __launch_bounds__(kLz4WarpsPerCta * 32)
-lz4_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* __restrict__ raw,
-                  const Lz4BlockDesc* __restrict__ desc, int* __restrict__ status, uint32_t n_blocks)
+lz4_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4BlockDesc* __restrict__ desc,
+                  int* __restrict__ status, uint32_t n_blocks)
 {
+    extern __shared__ __align__(16) unsigned char lz4_smem[];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = blockIdx.x * kLz4WarpsPerCta + (threadIdx.x >> 5);
+    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * kLz4WarpsPerCta + wic;
     const uint32_t n_warps = gridDim.x * kLz4WarpsPerCta;
     for (uint32_t b = warp; b < n_blocks; b += n_warps) {
         const Lz4BlockDesc d = desc[b];
-        const int r = lz4_decode_block_warp(comp + d.comp_off, d.comp_size, raw + d.raw_off, d.raw_size, lane);
+        Lz4Out o;
+        o.g = raw + d.raw_off;
+        o.ring = lz4_smem + wic * kLz4Win;
+        const int r = lz4_decode_block_warp(comp + d.comp_off, d.comp_size, o, d.raw_size, lane);
         if (lane == 0) status[b] = r;
+        __syncwarp();
     }
 }
 

@@ -55,13 +55,15 @@ def test_gpu_lz4_decode_rejects_malformed_blocks(cuda_lib):
     assert status[3] < 0
 
 
-@pytest.mark.parametrize("compressor", ["liblz4", "oracle"])
-def test_lz4_container_counts_match_the_column(cuda_lib, compressor):
+@pytest.mark.parametrize("compressor,batch", [("liblz4", None), ("oracle", None), ("liblz4", "7"), ("liblz4", "1")])
+def test_lz4_container_counts_match_the_column(cuda_lib, compressor, batch, monkeypatch):
     from libflagstats_b200 import blockfile
 
+    if batch:
+        monkeypatch.setenv("FLAGSTAT_CUDA_LZ4_BATCH", batch)  # several decode batches, two lanes alternating
     comp = O.liblz4_compress if compressor == "liblz4" else O.lz4_compress
-    # 131 blocks: more than one decode batch (128), ragged last block
-    col = O.synth_hiseqx(0, 130 * 512_000 + 77_777, 3, 2000)
+    # 41 blocks, ragged last block
+    col = O.synth_hiseqx(0, 40 * 512_000 + 77_777, 3, 2000)
     blob = O.write_lz4_container(col, compressor=comp)
     f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
     assert n == col.size
