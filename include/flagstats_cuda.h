@@ -147,6 +147,16 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
                              const uint32_t* raw_size, uint32_t n_blocks, void* raw,
                              uint64_t raw_total, int* status);
 
+/* ---- FLAG ingest (benchmark/utility.cpp:29-32) -------------------------------
+ * `samtools view FILE | cut -f 2` text -- one decimal FLAG per line -- to the
+ * uint16 column, on the GPU: one record per line (std::getline: a last line
+ * without '\n' counts), value = (uint16_t)atoi(line).  `out` (host, may be NULL)
+ * receives the column if out_capacity records fit (else EINVAL with *n_records =
+ * the room needed); `flags` (may be NULL) is accumulated with the counters of
+ * the column straight from device memory. */
+int FLAGSTAT_cuda_ingest_text(const char* text, uint64_t n_bytes, uint16_t* out, uint64_t out_capacity,
+                              uint64_t* n_records, uint64_t* flags);
+
 /* ---- several GPUs from one process (range shards, host-side sum) --------- */
 
 /* Splits [0,len) into n_devices contiguous ranges (boundaries on 8-record

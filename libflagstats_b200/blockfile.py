@@ -90,3 +90,20 @@ def lz4_decode(blocks: Sequence[bytes], raw_sizes: Sequence[int]):
         status.ctypes.data_as(C.POINTER(C.c_int))), "FLAGSTAT_cuda_lz4_decode")
     out = [raw[int(raw_off[i]):int(raw_off[i]) + int(raw_size[i])].tobytes() for i in range(nb)]
     return out, status[:nb].tolist()
+
+
+def ingest_text(text, with_flags: bool = False):
+    """FLAG text column (one decimal FLAG per line, benchmark/utility.cpp:29-32) -> uint16
+    column, parsed on the GPU.  Returns the column, or (column, flags) with the counters of
+    that column (counted from device memory) when ``with_flags``."""
+    buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = int(np.count_nonzero(buf == 10)) + 1
+    out = np.empty(cap, np.uint16)
+    n = C.c_uint64(0)
+    f = np.zeros(32, np.uint64)
+    check(lib().FLAGSTAT_cuda_ingest_text(buf.ctypes.data, buf.size, out.ctypes.data, cap, C.byref(n),
+                                          f.ctypes.data_as(_capi.u64p) if with_flags else None),
+          "FLAGSTAT_cuda_ingest_text")
+    col = out[: int(n.value)].copy()
+    return (col, f) if with_flags else col

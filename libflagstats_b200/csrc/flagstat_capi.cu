@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -25,6 +26,8 @@
 #include "flagstat_kernel_group.cuh"
 #include "synth.cuh"
 #include "lz4_block.cuh"
+#include "ingest_text.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -897,3 +900,79 @@ int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d
 }  // extern "C"
 
 #include "flagstat_blockfile.inl"
+
+// ---- FLAG ingest (benchmark/utility.cpp:29-32) ---------------------------------------------
+extern "C" int FLAGSTAT_cuda_ingest_text(const char* text, uint64_t n_bytes, uint16_t* out,
+                                         uint64_t out_capacity, uint64_t* n_records, uint64_t* flags)
+{
+    using namespace fsb200;
+    if ((!text && n_bytes) || !n_records) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    *n_records = 0;
+    if (n_bytes == 0) return 0;
+    const uint64_t tiles = (n_bytes + kIngestTile - 1) / kIngestTile;
+    if (tiles > 0x7FFFFFFFull) return FLAGSTAT_CUDA_EINVAL;
+    // a last line without '\n' is still a line (std::getline); parse it on the host
+    uint64_t tail_lo = n_bytes;
+    bool has_tail = text[n_bytes - 1] != '\n';
+    if (has_tail)
+        while (tail_lo > 0 && text[tail_lo - 1] != '\n') --tail_lo;
+    unsigned char* d_text = nullptr;
+    unsigned long long *d_tiles = nullptr, *d_first = nullptr;
+    uint16_t* d_out = nullptr;
+    void* d_tmp = nullptr;
+    uint64_t* d_flags = nullptr;
+    int rc = 0;
+    uint64_t lines = 0;
+    do {
+        if ((rc = (int)cudaMalloc(&d_text, n_bytes))) break;
+        if ((rc = (int)cudaMalloc(&d_tiles, (tiles + 1) * sizeof(unsigned long long)))) break;
+        if ((rc = (int)cudaMalloc(&d_first, (tiles + 1) * sizeof(unsigned long long)))) break;
+        if ((rc = (int)cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice))) break;
+        if ((rc = (int)cudaMemset(d_tiles + tiles, 0, sizeof(unsigned long long)))) break;
+        ingest_count_kernel<<<(unsigned)tiles, kIngestThreads>>>(d_text, n_bytes, d_tiles);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        size_t tmp_bytes = 0;
+        if ((rc = (int)cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_tiles, d_first, (int)(tiles + 1)))) break;
+        if ((rc = (int)cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1))) break;
+        if ((rc = (int)cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_tiles, d_first, (int)(tiles + 1)))) break;
+        unsigned long long total = 0;
+        if ((rc = (int)cudaMemcpy(&total, d_first + tiles, sizeof(total), cudaMemcpyDeviceToHost))) break;
+        lines = total + (has_tail ? 1 : 0);
+        if (out && lines > out_capacity) {
+            rc = FLAGSTAT_CUDA_EINVAL;
+            *n_records = lines;  // tell the caller how much room is needed
+            break;
+        }
+        if ((rc = (int)cudaMalloc(&d_out, (lines ? lines : 1) * sizeof(uint16_t)))) break;
+        if (total) {
+            ingest_parse_kernel<<<(unsigned)tiles, kIngestThreads>>>(d_text, n_bytes, d_first, d_out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if ((rc = (int)cudaGetLastError())) break;
+        }
+        if (has_tail) {
+            const std::string last(text + tail_lo, text + n_bytes);
+            const uint16_t v = (uint16_t)std::atoi(last.c_str());
+            if ((rc = (int)cudaMemcpy(d_out + total, &v, sizeof(v), cudaMemcpyHostToDevice))) break;
+        }
+        if (flags) {  // count straight from the device column: the text never becomes a host uint16 array
+            if ((rc = (int)cudaMalloc(&d_flags, 32 * sizeof(uint64_t)))) break;
+            if ((rc = (int)cudaMemset(d_flags, 0, 32 * sizeof(uint64_t)))) break;
+            if ((rc = launch(kFlagstat, d_out, lines, d_flags, nullptr))) break;
+            uint64_t t[32];
+            if ((rc = (int)cudaMemcpy(t, d_flags, sizeof(t), cudaMemcpyDeviceToHost))) break;
+            for (int i = 0; i < 32; ++i) flags[i] += t[i];
+        }
+        if (out && lines)
+            if ((rc = (int)cudaMemcpy(out, d_out, lines * sizeof(uint16_t), cudaMemcpyDeviceToHost))) break;
+        if ((rc = (int)cudaDeviceSynchronize())) break;
+        *n_records = lines;
+    } while (0);
+    cudaFree(d_text);
+    cudaFree(d_tiles);
+    cudaFree(d_first);
+    cudaFree(d_out);
+    cudaFree(d_tmp);
+    cudaFree(d_flags);
+    return rc;
+}

@@ -385,3 +385,18 @@ def read_lz4_container(blob: bytes, decompressor=None):
         chunk = decompressor(blob[pos:pos + comp_size], raw_size)
         pos += comp_size
         yield np.frombuffer(chunk[: (raw_size >> 1) * 2], dtype=np.uint16)
+
+
+# --------------------------------------------------------------------------
+# FLAG ingest (benchmark/utility.cpp:29-32)
+# --------------------------------------------------------------------------
+def ingest_text(text: bytes) -> np.ndarray:
+    """while (getline(cin, str)) write((uint16_t) atoi(str.c_str())) -- with the C library's
+    own atoi, one call per line."""
+    libc = C.CDLL(None)
+    libc.atoi.argtypes = [C.c_char_p]
+    libc.atoi.restype = C.c_int
+    lines = text.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()  # getline: nothing after the final newline is not a line
+    return np.array([libc.atoi(ln) & 0xFFFF for ln in lines], dtype=np.uint16)
