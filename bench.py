@@ -370,6 +370,31 @@ def ours(args) -> int:
     pcie_gbs = 2 * n / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del tmp
 
+    # ---- the same call on PAGEABLE memory (what numpy / malloc give the reference's callers):
+    # T threads copy slices into pinned slots (run_pageable); N=1 only, rank 0
+    pageable_info = None
+    if world == 1:
+        try:
+            page_np = np.empty(n, np.uint16)
+            page_np[:] = host_np
+            fs.flagstat_u64(page_np)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                f_pg = fs.flagstat_u64(page_np)
+            t1 = time.perf_counter()
+            pg_s = (t1 - t0) / 3
+            pageable_info = {
+                "value": n / pg_s, "unit": UNIT, "gbs": 2 * n / pg_s / 1e9,
+                "frac_of_pcie_probe": 2 * n / pg_s / 1e9 / pcie_gbs,
+                "api": "FLAGSTAT_cuda_u64(pageable numpy array): threaded copy into pinned slots, "
+                       "one DMA + launch per slice",
+                "threads": int(os.environ.get("FLAGSTAT_CUDA_IO_THREADS", "6")),
+                "same_counters": f_pg.tolist() == f_e2e.tolist(),
+            }
+            del page_np
+        except Exception as exc:
+            pageable_info = {"error": repr(exc)}
+
     # ---- streamed end to end (BASELINE configs[4]): 1,024,000-byte blocks from a pinned ring,
     # DMA of group k+1 overlapping the kernel of group k on separate streams; the submit loop
     # runs in C (FLAGSTAT_cuda_stream_selftime), data already in the pinned slots
@@ -463,6 +488,7 @@ def ours(args) -> int:
             "achieved_gbs_per_gpu": 2 * n / e2e_s / 1e9, "pcie_h2d_probe_gbs": pcie_gbs,
             "frac_of_pcie_probe": (2 * n / e2e_s / 1e9) / pcie_gbs,
         },
+        "e2e_pageable": pageable_info,
         "stream_e2e": stream_info,
         "gpu_launches": int(launches),
         "exchange": ("fused: counters exchanged by the counting kernel itself through peer-mapped "

@@ -211,6 +211,10 @@ const char* FLAGSTAT_cuda_version(void);
 uint64_t FLAGSTAT_cuda_launch_count(void);
 /* Select a kernel variant for A/B tests (0 = default).  Returns the previous. */
 int FLAGSTAT_cuda_set_variant(int variant);
+/* LZ4 block decoder for A/B tests: 1 = 32 sequences per warp step (default), 0 = one
+ * sequence per warp step.  Returns the previous.  Env FLAGSTAT_CUDA_LZ4_VARIANT sets the
+ * initial value. */
+int FLAGSTAT_cuda_set_lz4_variant(int variant);
 /* Persistent-grid size override: CTAs per SM (0 = default). */
 int FLAGSTAT_cuda_set_ctas_per_sm(int n);
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "FLAGSTAT_cuda_version": (C.c_char_p, []),
     "FLAGSTAT_cuda_launch_count": (C.c_uint64, []),
     "FLAGSTAT_cuda_set_variant": (C.c_int, [C.c_int]),
+    "FLAGSTAT_cuda_set_lz4_variant": (C.c_int, [C.c_int]),
     "FLAGSTAT_cuda_set_ctas_per_sm": (C.c_int, [C.c_int]),
     "FLAGSTAT_cuda_synth_uniform": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.c_uint16, C.c_void_p]),

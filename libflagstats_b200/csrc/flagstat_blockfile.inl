@@ -66,6 +66,20 @@ int io_threads()
     return t;
 }
 
+// FLAGSTAT_CUDA_LZ4_VARIANT: 1 = 32 sequences per warp step (lz4_block_group.cuh, default),
+// 0 = one sequence per warp step (lz4_block.cuh; kept for A/B, profiles/)
+std::atomic<int> g_lz4_variant{-1};
+int lz4_variant()
+{
+    int v = g_lz4_variant.load();
+    if (v < 0) {
+        const char* e = std::getenv("FLAGSTAT_CUDA_LZ4_VARIANT");
+        v = (e && std::atoi(e) == 0) ? 0 : 1;
+        g_lz4_variant.store(v);
+    }
+    return v;
+}
+
 int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status,
                uint32_t n_blocks, cudaStream_t st)
 {
@@ -74,10 +88,17 @@ int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4Block
     std::call_once(once, [] {
         attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem);
+        if (attr_rc == cudaSuccess)
+            attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem);
     });
     if (attr_rc != cudaSuccess) return (int)attr_rc;
     const unsigned grid = (n_blocks + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
-    lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4Smem, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
+    if (lz4_variant() == 0)
+        lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4Smem, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
+    else
+        lz4_decode_group_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4GroupSmem, st>>>(d_comp, d_raw, d_desc,
+                                                                                  d_status, n_blocks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
     return 0;
@@ -421,7 +442,11 @@ void raw_ctx_release(RawCtx* c)
     g_raw_pool[c->dev].push_back(c);
 }
 
-int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
+// The staged pipeline shared by raw files and pageable host arrays: `fill(dst, off, len)` puts
+// bytes [off, off + len) of the column into a pinned slot (pread for files, memcpy for memory).
+// slot_bytes <= kRawSlotBytes, even.  totals: 32 (flagstat) / 16 (pospopcnt) u64, overwritten.
+template <class Fill>
+int consume_staged(int mode, uint64_t size, size_t slot_bytes, Fill fill, uint64_t* totals)
 {
     RawCtx* c = nullptr;
     {
@@ -433,7 +458,7 @@ int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
         ~Cleanup() { raw_ctx_release(c); }
     } cleanup{c};
     CK(cudaMemset(c->d_flags, 0, 32 * sizeof(uint64_t)));
-    const uint64_t n_groups = (size + kRawSlotBytes - 1) / kRawSlotBytes;
+    const uint64_t n_groups = (size + slot_bytes - 1) / slot_bytes;
     std::atomic<int> err{0};
     auto worker = [&](int t) {
         if (cudaSetDevice(c->dev) != cudaSuccess) {
@@ -445,20 +470,15 @@ int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
             const int slot = 2 * t + (k & 1);
             unsigned char* h = c->h + (size_t)slot * kRawSlotBytes;
             unsigned char* d = c->d + (size_t)slot * kRawSlotBytes;
-            const uint64_t off = g * kRawSlotBytes;
-            const size_t len = (size_t)((size - off < kRawSlotBytes) ? (size - off) : kRawSlotBytes);
+            const uint64_t off = g * slot_bytes;
+            const size_t len = (size_t)((size - off < slot_bytes) ? (size - off) : slot_bytes);
             if (cudaStreamSynchronize(c->st[slot]) != cudaSuccess) {  // slot's previous DMA is done
                 err.store(FLAGSTAT_CUDA_EIO);
                 return;
             }
-            size_t got = 0;
-            while (got < len) {
-                const ssize_t r = ::pread(fd, h + got, len - got, (off_t)(off + got));
-                if (r <= 0) {
-                    err.store(FLAGSTAT_CUDA_EIO);
-                    return;
-                }
-                got += (size_t)r;
+            if (!fill(h, off, len)) {
+                err.store(FLAGSTAT_CUDA_EIO);
+                return;
             }
             const uint64_t recs = len >> 1;  // only the last group can carry an odd byte; dropped like :455
             if (recs == 0) continue;
@@ -466,22 +486,64 @@ int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
                 err.store(FLAGSTAT_CUDA_EIO);
                 return;
             }
-            const int rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(d), recs, c->d_flags, c->st[slot]);
+            const int rc = launch(mode, reinterpret_cast<const uint16_t*>(d), recs, c->d_flags, c->st[slot]);
             if (rc) {
                 err.store(rc);
                 return;
             }
         }
     };
+    const int use = (int)((n_groups < (uint64_t)c->threads) ? n_groups : (uint64_t)c->threads);
     std::vector<std::thread> th;
-    for (int t = 1; t < c->threads; ++t) th.emplace_back(worker, t);
+    for (int t = 1; t < use; ++t) th.emplace_back(worker, t);
     worker(0);
     for (auto& x : th) x.join();
     for (int i = 0; i < 2 * c->threads; ++i) CK(cudaStreamSynchronize(c->st[i]));
     if (err.load()) return err.load();
-    CK(cudaMemcpy(totals, c->d_flags, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(totals, c->d_flags, (mode == kPospopcnt ? 16 : 32) * sizeof(uint64_t),
+                  cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
+{
+    const int rc = consume_staged(
+        kFlagstat, size, kRawSlotBytes,
+        [fd](unsigned char* h, uint64_t off, size_t len) {
+            size_t got = 0;
+            while (got < len) {
+                const ssize_t r = ::pread(fd, h + got, len - got, (off_t)(off + got));
+                if (r <= 0) return false;
+                got += (size_t)r;
+            }
+            return true;
+        },
+        totals);
+    if (rc) return rc;
     *n_records = size >> 1;
     return 0;
+}
+
+// Pageable (unregistered) host arrays -- what numpy / malloc hand the reference's entry points.
+// cudaMemcpyAsync from such memory is staged by the driver through its own bounce buffer on
+// the calling thread; here T threads memcpy their slices into pinned slots and every slice is
+// its own DMA + launch, so the page-in copy of one slice overlaps the DMA of the others.
+int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
+{
+    const uint64_t size = len * sizeof(uint16_t);
+    const int T = io_threads();
+    // at least two slices per thread, 64 KiB granules, at most one ring slot
+    uint64_t slot = (size / (uint64_t)(2 * T) + 65535u) & ~(uint64_t)65535u;
+    if (slot < (1u << 20)) slot = 1u << 20;
+    if (slot > kRawSlotBytes) slot = kRawSlotBytes & ~(size_t)65535u;
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(array);
+    return consume_staged(
+        mode, size, (size_t)slot,
+        [base](unsigned char* h, uint64_t off, size_t n) {
+            std::memcpy(h, base + off, n);
+            return true;
+        },
+        totals);
 }
 
 int consume_raw(ByteSource& src, uint64_t* totals, uint64_t* n_records)
@@ -515,6 +577,13 @@ int consume(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
 }  // namespace
 
 extern "C" {
+
+int FLAGSTAT_cuda_set_lz4_variant(int v)
+{
+    const int prev = lz4_variant();
+    g_lz4_variant.store(v == 0 ? 0 : 1);
+    return prev;
+}
 
 int FLAGSTAT_cuda_file_u64(const char* path, int format, uint64_t* flags, uint64_t* n_records)
 {

@@ -26,6 +26,7 @@
 #include "flagstat_kernel_group.cuh"
 #include "synth.cuh"
 #include "lz4_block.cuh"
+#include "lz4_block_group.cuh"
 #include "ingest_text.cuh"
 #include <cub/device/device_scan.cuh>
 
@@ -245,6 +246,19 @@ void lane_release(Lane* l)
     g_pool[l->dev].push_back(l);
 }
 
+// flagstat_blockfile.inl: T threads copy slices of a PAGEABLE host array into pinned slots
+int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals);
+
+// host arrays of at least this many bytes that are not page-locked take run_pageable()
+uint64_t pageable_min_bytes()
+{
+    static const uint64_t v = [] {
+        if (const char* e = std::getenv("FLAGSTAT_CUDA_PAGEABLE_MIN")) return (uint64_t)std::strtoull(e, nullptr, 10);
+        return (uint64_t)(8u << 20);
+    }();
+    return v;
+}
+
 // Synchronous run on the CURRENT device; array may be host or device memory.
 // totals: 32 (flagstat) or 16 (pospopcnt) u64, overwritten.
 int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
@@ -256,7 +270,7 @@ int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
     int dev = 0;
     CK(cudaGetDevice(&dev));
 
-    bool on_device = false;
+    bool on_device = false, pageable = false;
     struct Restore {  // device-resident input runs on the device that owns it
         int dev = -1;
         ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
@@ -271,10 +285,14 @@ int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
                 restore.dev = dev;
                 dev = attr.device;
             }
+            pageable = attr.type == cudaMemoryTypeUnregistered;
         } else {
             cudaGetLastError();  // plain malloc memory on old drivers
+            pageable = true;
         }
     }
+    if (pageable && len * sizeof(uint16_t) >= pageable_min_bytes())
+        return run_pageable(mode, array, len, totals);
 
     Lane* l = nullptr;
     int rc = lane_acquire(dev, &l);

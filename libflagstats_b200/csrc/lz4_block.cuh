@@ -45,11 +45,14 @@ constexpr size_t kLz4Smem = (size_t)kLz4WarpsPerCta * kLz4Win;
 // (~30 cycles) instead of from L2 (~300 cycles: global stores are not kept in L1).
 struct Lz4Out {
     uint8_t* g;      // global output of this block
-    uint8_t* ring;   // this warp's kLz4Win bytes of shared memory
+    uint8_t* ring;   // this warp's kLz4Win bytes of shared memory (16-byte aligned)
+    uint32_t ga;     // (address of g) & 15: the ring is indexed so that 16-byte chunks of the
+                     // ring and of global memory line up (lz4_block_group.cuh flushes in uint4)
+    __device__ __forceinline__ uint32_t ridx(uint32_t pos) const { return (pos + ga) & (kLz4Win - 1u); }
     __device__ __forceinline__ void put(uint32_t pos, uint8_t v) const
     {
         g[pos] = v;
-        ring[pos & (kLz4Win - 1u)] = v;
+        ring[ridx(pos)] = v;
     }
 };
 
@@ -85,14 +88,14 @@ __device__ __forceinline__ void warp_match(const Lz4Out& o, uint32_t op, uint32_
 #pragma unroll
             for (uint32_t u = 0; u < kLz4Unroll; ++u) {
                 const uint32_t p = base + i + 32u * u;
-                v[u] = FROM_RING ? o.ring[p & (kLz4Win - 1u)] : o.g[p];
+                v[u] = FROM_RING ? o.ring[o.ridx(p)] : o.g[p];
             }
 #pragma unroll
             for (uint32_t u = 0; u < kLz4Unroll; ++u) o.put(op + i + 32u * u, v[u]);
         }
         for (; i < n; i += 32u) {
             const uint32_t p = base + i;
-            o.put(op + i, FROM_RING ? o.ring[p & (kLz4Win - 1u)] : o.g[p]);
+            o.put(op + i, FROM_RING ? o.ring[o.ridx(p)] : o.g[p]);
         }
         return;
     }
@@ -103,7 +106,7 @@ __device__ __forceinline__ void warp_match(const Lz4Out& o, uint32_t op, uint32_
         uint8_t v[kLz4Unroll];
 #pragma unroll
         for (uint32_t u = 0; u < kLz4Unroll; ++u) {
-            v[u] = FROM_RING ? o.ring[(base + r) & (kLz4Win - 1u)] : o.g[base + r];
+            v[u] = FROM_RING ? o.ring[o.ridx(base + r)] : o.g[base + r];
             r += step;
             if (r >= offset) r -= offset;
         }
@@ -111,7 +114,7 @@ __device__ __forceinline__ void warp_match(const Lz4Out& o, uint32_t op, uint32_
         for (uint32_t u = 0; u < kLz4Unroll; ++u) o.put(op + i + 32u * u, v[u]);
     }
     for (; i < n; i += 32u) {
-        const uint8_t v = FROM_RING ? o.ring[(base + r) & (kLz4Win - 1u)] : o.g[base + r];
+        const uint8_t v = FROM_RING ? o.ring[o.ridx(base + r)] : o.g[base + r];
         o.put(op + i, v);
         r += step;
         if (r >= offset) r -= offset;
@@ -171,7 +174,7 @@ __device__ __forceinline__ int lz4_decode_block_warp(const uint8_t* __restrict__
                 uint32_t rel = lane;
                 if (offset < ml) rel = lane % offset;  // warp-uniform branch: overlapping match
                 const uint32_t sidx = op - offset + rel;
-                const uint8_t v = (offset <= kLz4Win - 32u) ? o.ring[sidx & (kLz4Win - 1u)] : o.g[sidx];
+                const uint8_t v = (offset <= kLz4Win - 32u) ? o.ring[o.ridx(sidx)] : o.g[sidx];
                 o.put(op + lane, v);
             }
             op += ml;
@@ -208,6 +211,7 @@ lz4_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4Block
         Lz4Out o;
         o.g = raw + d.raw_off;
         o.ring = lz4_smem + wic * kLz4Win;
+        o.ga = 0u;
         const int r = lz4_decode_block_warp(comp + d.comp_off, d.comp_size, o, d.raw_size, lane);
         if (lane == 0) status[b] = r;
         __syncwarp();

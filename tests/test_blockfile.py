@@ -24,23 +24,109 @@ def _columns():
     ]
 
 
-def test_gpu_lz4_decode_matches_original(cuda_lib):
+@pytest.fixture(params=[1, 0], ids=["group_decoder", "sequence_decoder"])
+def lz4_variant(request, cuda_lib):
+    """Both LZ4 decoders: 32 sequences per warp step (default) and one per step."""
+    prev = cuda_lib.lib().FLAGSTAT_cuda_set_lz4_variant(request.param)
+    yield request.param
+    cuda_lib.lib().FLAGSTAT_cuda_set_lz4_variant(prev)
+
+
+def _more_columns():
+    rng = np.random.default_rng(11)
+    cats = np.array([99, 147, 83, 163, 97, 145, 73, 137, 2113, 77], np.uint16)
+    return [
+        ("runs_mean8", np.repeat(cats[rng.integers(0, 10, 60000)], rng.geometric(1 / 8, 60000))),
+        ("runs_mean2", np.repeat(cats[rng.integers(0, 10, 100000)], rng.geometric(1 / 2, 100000))),
+        ("iid_categories", cats[rng.integers(0, 10, 400_000)]),
+        ("far_matches", np.concatenate([O.synth_uniform(0, 12_000, 9, 0x0FFF)] * 5)),  # offsets > 16 KiB
+    ]
+
+
+def _handmade_chain_block():
+    """Every match reads the previous sequence's match (32 dependency rounds in one group),
+    overlapping copies, offset-1 runs, one-byte length extensions (tests/test_lz4_group_model.py)."""
+    seqs, want = bytearray(), bytearray()
+
+    def seq(lit, off, ml):
+        seqs.append((len(lit) << 4) | min(ml - 4, 15))
+        seqs.extend(lit)
+        seqs.extend(bytes([off & 255, off >> 8]))
+        if ml >= 19:
+            seqs.append(ml - 19)
+        want.extend(lit)
+        for _ in range(ml):
+            want.append(want[-off])
+
+    seq(b"ab", 2, 6)
+    for i in range(70):
+        seq(bytes([65 + i % 26]), 3 + (i % 4), 4 + (i * 5) % 15)
+    seq(b"", 1, 18)
+    seq(b"q", 5, 19)
+    seq(b"", 3, 200)
+    seq(b"", 150, 273)
+    seq(b"xyz", 1, 4)
+    seq(b"", 7, 18)
+    seqs.append(0x50)
+    seqs.extend(b"tail!")
+    want.extend(b"tail!")
+    return bytes(seqs), bytes(want)
+
+
+def test_gpu_lz4_decode_matches_original(cuda_lib, lz4_variant):
     from libflagstats_b200 import blockfile
 
     blocks, sizes, raws = [], [], []
-    for _name, col in _columns():
+    for _name, col in _columns() + _more_columns():
         raw = col.tobytes()
         for comp in (O.liblz4_compress(raw), O.lz4_compress(raw)):
             blocks.append(comp)
             sizes.append(len(raw))
             raws.append(raw)
+    comp, raw = _handmade_chain_block()
+    assert O.lz4_decompress(comp, len(raw)) == raw
+    blocks.append(comp)
+    sizes.append(len(raw))
+    raws.append(raw)
     out, status = blockfile.lz4_decode(blocks, sizes)
     assert status == sizes
     for got, want in zip(out, raws):
         assert got == want
 
 
-def test_gpu_lz4_decode_rejects_malformed_blocks(cuda_lib):
+def test_gpu_lz4_decode_unaligned_output_bases(cuda_lib, lz4_variant):
+    """Blocks whose decoded bytes start at odd global addresses (a container may hold blocks of
+    any raw size): the group decoder's ring is shifted so its uint4 flushes stay aligned."""
+    import ctypes as C
+
+    from libflagstats_b200 import _capi
+
+    fs = cuda_lib
+    rng = np.random.default_rng(3)
+    cats = np.array([99, 147, 83, 163, 97, 145], np.uint16)
+    raws = [np.repeat(cats[rng.integers(0, 6, 3000)], rng.geometric(1 / 5, 3000)).tobytes()[: 20_001 + 7 * i]
+            for i in range(9)]
+    comps = [O.liblz4_compress(r) for r in raws]
+    nb = len(raws)
+    comp_off = np.zeros(nb, np.uint64); raw_off = np.zeros(nb, np.uint64)
+    c = r = 0
+    for i in range(nb):  # packed back to back: no alignment of either side
+        comp_off[i] = c; c += len(comps[i])
+        raw_off[i] = r; r += len(raws[i])
+    comp = np.frombuffer(b"".join(comps), np.uint8).copy()
+    raw = np.zeros(r, np.uint8)
+    status = np.zeros(nb, np.int32)
+    comp_size = np.array([len(x) for x in comps], np.uint32)
+    raw_size = np.array([len(x) for x in raws], np.uint32)
+    fs.check(fs.lib().FLAGSTAT_cuda_lz4_decode(
+        comp.ctypes.data, c, comp_off.ctypes.data_as(_capi.u64p), comp_size.ctypes.data_as(_capi.u32p),
+        raw_off.ctypes.data_as(_capi.u64p), raw_size.ctypes.data_as(_capi.u32p), nb, raw.ctypes.data, r,
+        status.ctypes.data_as(C.POINTER(C.c_int))), "lz4_decode")
+    assert status.tolist() == [len(x) for x in raws]
+    assert raw.tobytes() == b"".join(raws)
+
+
+def test_gpu_lz4_decode_rejects_malformed_blocks(cuda_lib, lz4_variant):
     from libflagstats_b200 import blockfile
 
     raw = np.tile(np.array([99, 147, 83, 163], np.uint16), 5000).tobytes()
@@ -53,10 +139,16 @@ def test_gpu_lz4_decode_rejects_malformed_blocks(cuda_lib):
     assert status[1] != len(raw)
     assert status[2] < 0
     assert status[3] < 0
+    # short sequences (the group path): offset before the block start, zero offset, output overrun
+    tiny = [bytes([0x10, 65, 5, 0, 0x10, 66, 1, 0, 0x50, 1, 2, 3, 4, 5]),
+            bytes([0x10, 65, 0, 0, 0x50, 1, 2, 3, 4, 5]),
+            bytes([0x1E, 65, 1, 0, 0x50, 1, 2, 3, 4, 5])]
+    _out, st = blockfile.lz4_decode(tiny, [64, 64, 10])
+    assert all(x < 0 for x in st)
 
 
 @pytest.mark.parametrize("compressor,batch", [("liblz4", None), ("oracle", None), ("liblz4", "7"), ("liblz4", "1")])
-def test_lz4_container_counts_match_the_column(cuda_lib, compressor, batch, monkeypatch):
+def test_lz4_container_counts_match_the_column(cuda_lib, compressor, batch, monkeypatch, lz4_variant):
     from libflagstats_b200 import blockfile
 
     if batch:

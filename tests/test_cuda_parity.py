@@ -248,3 +248,19 @@ def test_multi_device_entry_and_errors(cuda_lib):
     rc = fs.lib().FLAGSTAT_cuda_u64(a.ctypes.data + 1, 10, g.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == -2 and (g == 7).all()
     assert fs.lib().FLAGSTAT_cuda_launch_count() > 0
+
+
+@pytest.mark.parametrize("n,off", [(4_194_304, 0), (20_000_003, 1), (37_123_457, 3)])
+def test_pageable_host_arrays_take_the_threaded_staging_path(cuda_lib, n, off):
+    """numpy memory is pageable: arrays >= 8 MiB go through run_pageable() (T threads copy
+    slices into pinned slots; one DMA + launch per slice).  Same counters as the oracle for
+    flagstat, the reference's uint32 signature and pospopcnt; ragged lengths, odd bases."""
+    fs = cuda_lib
+    a = offset_copy(O.synth_hiseqx(off, n, 5, 20000), off)
+    launches = fs.lib().FLAGSTAT_cuda_launch_count()
+    want = O.flagstat_simd(a)
+    assert fs.flagstat_u64(a).tolist() == want.tolist()
+    assert fs.lib().FLAGSTAT_cuda_launch_count() - launches >= 2  # sliced, not one chunk
+    f = fs.flagstat_u32(a)
+    assert f.astype(np.uint64)[CORE20].tolist() == (want[CORE20] & 0xFFFFFFFF).tolist()
+    assert fs.pospopcnt_u16(a).tolist() == O.pospopcnt(a).tolist()

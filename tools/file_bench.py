@@ -54,7 +54,11 @@ def main():
         p_lz4 = os.path.join(tmp, name + ".lz4")
         with open(p_lz4, "wb") as fh:
             fh.write(blob)
-        for label, path in (("raw .bin", p_raw), ("lz4 container", p_lz4)):
+        for label, path, variant in (("raw .bin", p_raw, None),
+                                     ("lz4 container, group decoder (32 sequences per warp step)", p_lz4, 1),
+                                     ("lz4 container, sequence decoder (1 sequence per warp step)", p_lz4, 0)):
+            if variant is not None:
+                fs.lib().FLAGSTAT_cuda_set_lz4_variant(variant)
             best = None
             for _ in range(4):
                 t0 = time.perf_counter()

@@ -34,4 +34,32 @@ for mode in (0, 1):
         for lo in range(0, a.size, 40_000):
             bs.push(a[lo:lo + 40_000])
         assert bs.finish().tolist() == O.flagstat_simd(a).tolist()
+# LZ4 block decoders (both), aligned and packed (unaligned) outputs, every copy path
+from libflagstats_b200 import blockfile  # noqa: E402
+from tests.test_blockfile import _handmade_chain_block  # noqa: E402
+
+rng = np.random.default_rng(11)
+cats = np.array([99, 147, 83, 163, 97, 145, 73, 137, 2113, 77], np.uint16)
+cols = [np.repeat(cats[rng.integers(0, 10, 3000)], rng.geometric(1 / 8, 3000)),
+        cats[rng.integers(0, 10, 20_000)],
+        np.concatenate([O.synth_uniform(0, 12_000, 9, 0x0FFF)] * 2),
+        np.repeat(rng.integers(0, 4096, 40).astype(np.uint16), rng.integers(1, 3000, 40)),
+        O.synth_hiseqx(0, 50_001, 2, 1000)]
+blocks = [O.liblz4_compress(c.tobytes()) for c in cols] + [O.lz4_compress(c.tobytes()) for c in cols]
+raws = [c.tobytes() for c in cols] * 2
+hb, hr = _handmade_chain_block()
+blocks.append(hb)
+raws.append(hr)
+for v in (1, 0):
+    lib.FLAGSTAT_cuda_set_lz4_variant(v)
+    out, status = blockfile.lz4_decode(blocks, [len(r) for r in raws])
+    assert status == [len(r) for r in raws], (v, status)
+    assert all(o == r for o, r in zip(out, raws)), v
+    blob = O.write_lz4_container(cols[0], block_bytes=20_002)
+    f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
+    assert n == cols[0].size and f.tolist() == O.numpy_flagstat(cols[0]).tolist(), v
+lib.FLAGSTAT_cuda_set_lz4_variant(1)
+# pageable host arrays: threaded staging
+a = O.synth_hiseqx(0, 6_000_001, 4, 5000)
+assert fs.flagstat_u64(a).tolist() == O.flagstat_simd(a).tolist()
 print("sanitize driver ok")
