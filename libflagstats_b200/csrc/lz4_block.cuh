@@ -48,7 +48,8 @@ struct Lz4Out {
     uint8_t* ring;   // this warp's kLz4Win bytes of shared memory (16-byte aligned)
     uint32_t ga;     // (address of g) & 15: the ring is indexed so that 16-byte chunks of the
                      // ring and of global memory line up (lz4_block_group.cuh flushes in uint4)
-    __device__ __forceinline__ uint32_t ridx(uint32_t pos) const { return (pos + ga) & (kLz4Win - 1u); }
+    uint32_t mask;   // ring bytes - 1 (kLz4Win here, kGrpRing in lz4_block_group.cuh)
+    __device__ __forceinline__ uint32_t ridx(uint32_t pos) const { return (pos + ga) & mask; }
     __device__ __forceinline__ void put(uint32_t pos, uint8_t v) const
     {
         g[pos] = v;
@@ -212,6 +213,7 @@ lz4_decode_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4Block
         o.g = raw + d.raw_off;
         o.ring = lz4_smem + wic * kLz4Win;
         o.ga = 0u;
+        o.mask = kLz4Win - 1u;
         const int r = lz4_decode_block_warp(comp + d.comp_off, d.comp_size, o, d.raw_size, lane);
         if (lane == 0) status[b] = r;
         __syncwarp();

@@ -11,18 +11,21 @@
 // byte, so a sequence is 3 or 4 + lit bytes of input):
 //
 //   1. stage   256 bytes of input into shared memory; every lane also writes, for
-//              its 8 byte positions p, len[p] = size of a simple sequence whose
-//              token would sit at p (0 = not simple / does not fit / last sequence)
-//   2. chase   lane 0 follows p += len[p] from the cursor: the starts of the next
-//              K <= 32 sequences (the only serial step: one LDS per sequence)
+//              its 8 byte positions p, nx[0][p] = p + size of a simple sequence
+//              whose token would sit at p (p itself = not simple / does not fit /
+//              last sequence of the block)
+//   2. chase   by doubling: nx[L][p] = nx[L-1][nx[L-1][p]] for all 256 positions
+//              (4 levels), then lane k walks k steps from the cursor with at most 5
+//              dependent loads: the starts of the next K <= 32 sequences
 //   3. parse   lane k decodes sequence k; a warp scan of lit + match lengths
 //              gives every sequence its output position
-//   4. copy    literals lane-parallel; matches in dependency rounds: a match is
-//              copied once no still-pending earlier match of the group overlaps
-//              its source (for FLAG runs the source is the sequence's own
-//              literals: one round).  Within a round the short matches (< 19
-//              bytes) are copied lane-parallel, the extended ones one after the
-//              other by the whole warp.
+//   4. copy    literals lane-parallel.  Matches of FLAG data mostly copy bytes that
+//              another match of the SAME group produces (offsets of a few hundred
+//              bytes), so every match byte first gets a parent pointer P[b] = the
+//              output byte it copies (bytes produced before the group are copied at
+//              once and become roots); pointer jumping P[b] = P[P[b]] over all bytes
+//              of the group in parallel resolves the chains in log(depth) steps,
+//              and a last pass copies root -> byte
 //   5. flush   output goes to the shared-memory window only; whole 16-byte
 //              chunks are written to HBM with coalesced uint4 stores
 //
@@ -38,8 +41,11 @@
 
 namespace fsb200 {
 
-constexpr uint32_t kGrpWin = 256;  // input bytes examined per group (8 per lane)
-constexpr uint32_t kGrpSmemPerWarp = kLz4Win + 2u * kGrpWin + 64u;  // ring | win | len | pos[32] u16
+constexpr uint32_t kGrpWin = 256;      // input bytes examined per group (8 per lane)
+constexpr uint32_t kGrpRing = 8192;    // bytes of a block's most recent output mirrored in shared memory
+constexpr uint32_t kGrpOutCap = 2048;  // output bytes of one group = entries of the parent table P[]
+// ring | win | nx[5][kGrpWin] | P[kGrpOutCap] u16
+constexpr uint32_t kGrpSmemPerWarp = kGrpRing + 6u * kGrpWin + 2u * kGrpOutCap;
 constexpr size_t kLz4GroupSmem = (size_t)kLz4WarpsPerCta * kGrpSmemPerWarp;
 
 // ring -> global for output bytes [flushed, upto); without `exact` only up to the last
@@ -113,57 +119,28 @@ __device__ __forceinline__ int lz4g_slow_sequence(const uint8_t* __restrict__ in
     op += lit;
     if (last) return 1;
     __syncwarp();
-    if (offset + ml <= kLz4Win) warp_match<true>(o, op, offset, ml, lane);
+    if (offset + ml <= o.mask + 1u) warp_match<true>(o, op, offset, ml, lane);
     else warp_match<false>(o, op, offset, ml, lane);
     op += ml;
     __syncwarp();
     return ip < in_size ? 0 : 1;
 }
 
-// ring[dst + i] = source[src + (i % offset)], i < n, by the whole warp; the source is the ring
-// or (further back than the window) global memory.  Only the first min(n, offset) source
-// bytes are read, all of them produced before this call.
-__device__ __forceinline__ void lz4g_warp_match(const Lz4Out& o, uint32_t dst, uint32_t src, uint32_t offset,
-                                                uint32_t n, bool from_ring, uint32_t lane)
-{
-    if (offset >= n) {
-        for (uint32_t i = lane; i < n; i += 32u)
-            o.ring[o.ridx(dst + i)] = from_ring ? o.ring[o.ridx(src + i)] : o.g[src + i];
-        return;
-    }
-    const uint32_t step = 32u % offset;
-    uint32_t r = lane % offset;
-    for (uint32_t i = lane; i < n; i += 32u) {
-        o.ring[o.ridx(dst + i)] = from_ring ? o.ring[o.ridx(src + r)] : o.g[src + r];
-        r += step;
-        if (r >= offset) r -= offset;
-    }
-}
-
-// number of lanes j whose (ascending) value v_j is <= x  [STRICT: < x]; the answer must be < 32
-template <bool STRICT>
-__device__ __forceinline__ uint32_t lz4g_count_below(uint32_t v, uint32_t x)
-{
-    uint32_t cnt = 0u;
-#pragma unroll
-    for (uint32_t s = 16u; s >= 1u; s >>= 1) {
-        const uint32_t t = __shfl_sync(0xffffffffu, v, (int)(cnt + s - 1u));
-        if (STRICT ? (t < x) : (t <= x)) cnt += s;
-    }
-    return cnt;
-}
-
 // Returns the number of bytes produced, or a negative code for a malformed block.
 __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict__ in, uint32_t in_size,
-                                                       const Lz4Out& o, uint8_t* win, uint8_t* lent,
-                                                       uint16_t* posv, uint32_t out_cap, uint32_t lane)
+                                                       const Lz4Out& o, uint8_t* win, uint8_t* nx,
+                                                       uint16_t* P, uint32_t out_cap, uint32_t lane)
 {
     constexpr uint32_t kFull = 0xffffffffu;
     uint32_t ip = 0u, op = 0u, flushed = 0u;
     if (in_size == 0u) return 0;
     for (;;) {
         const uint32_t avail = in_size - ip;  // > 0
-        uint32_t K = 0u, consumed = 0u;
+        uint32_t K = 0u, pos = 0u, endp = 0u;
+        if (lane < 8u) {  // the next windows: have their lines on the way
+            const uint32_t pf = ip + kGrpWin + lane * 128u;
+            if (pf < in_size) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + pf));
+        }
         const uint32_t t0 = in[ip];
         bool simple = (t0 >> 4) != 15u;  // cheap look at the first token before staging a window
         if (simple && (t0 & 15u) == 15u) {
@@ -188,27 +165,35 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
                 uint32_t len = lit != 15u ? 3u + lit : 0u;
                 if (mln == 15u && len != 0u) {  // one extension byte, and it must end the length
                     len += 1u;
-                    if (p + len > kGrpWin || win[p + len - 1u] == 255u) len = 0u;
+                    if (p + len >= kGrpWin || win[p + len - 1u] == 255u) len = 0u;
                 }
-                // whole sequence inside the window, and another token after it (a sequence
-                // that ends the input is the block's last one: literals only, slow path)
-                if (p + len > kGrpWin || p + len >= avail) len = 0u;
-                lent[p] = (uint8_t)len;
+                // whole sequence inside the window (next position < 256: one byte), and another
+                // token after it (a sequence that ends the input is the block's last one:
+                // literals only, slow path)
+                if (p + len >= kGrpWin || p + len >= avail) len = 0u;
+                nx[p] = (uint8_t)(p + len);  // successor; a position that cannot start a sequence loops
             }
             __syncwarp();
-            // 2. the serial step: starts of the next K sequences
-            uint32_t p = 0u, k = 0u;
-            if (lane == 0u) {
-                while (k < 32u && p < kGrpWin) {
-                    const uint32_t l = lent[p];
-                    if (l == 0u) break;
-                    posv[k++] = (uint16_t)p;
-                    p += l;
+            // 2. successor tables by doubling: nx[L][p] = 2^L-th successor of p
+#pragma unroll
+            for (uint32_t L = 1; L < 5u; ++L) {
+                const uint8_t* a = nx + (L - 1u) * kGrpWin;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    const uint32_t p = lane + 32u * j;
+                    nx[L * kGrpWin + p] = a[a[p]];
                 }
+                __syncwarp();
             }
-            K = __shfl_sync(kFull, k, 0);
-            consumed = __shfl_sync(kFull, p, 0);
-            __syncwarp();
+            // lane k walks k steps from the cursor: binary decomposition, 5 dependent loads
+            uint32_t p = 0u;
+#pragma unroll
+            for (uint32_t L = 0; L < 5u; ++L)
+                if (lane & (1u << L)) p = nx[L * kGrpWin + p];
+            pos = p;
+            endp = nx[p];
+            // a lane that landed on a looping position, or walked through one, is past the end
+            K = __popc(__ballot_sync(kFull, endp != p));
         }
         if (K == 0u) {
             lz4g_flush(o, flushed, op, true, lane);
@@ -220,72 +205,112 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
         }
 
         // 3. parse: lane k owns sequence k
-        const bool mine = lane < K;
-        const uint32_t pk = mine ? (uint32_t)posv[lane] : 0u;
+        bool mine = lane < K;
+        const uint32_t pk = mine ? pos : 0u;
         const uint32_t tok = win[pk];
-        const uint32_t lit = mine ? (tok >> 4) : 0u;
-        const bool ext = mine && (tok & 15u) == 15u;  // one match-length extension byte
-        const uint32_t ml = mine ? (tok & 15u) + 4u + (ext ? (uint32_t)win[pk + 3u + (tok >> 4)] : 0u) : 0u;
-        const uint32_t off = (uint32_t)win[pk + 1u + (tok >> 4)] | ((uint32_t)win[pk + 2u + (tok >> 4)] << 8);
-        const uint32_t tot = lit + ml;
+        const uint32_t litn = tok >> 4;
+        const bool ext = (tok & 15u) == 15u;  // one match-length extension byte
+        uint32_t lit = mine ? litn : 0u;
+        uint32_t ml = mine ? (tok & 15u) + 4u + (ext ? (uint32_t)win[pk + 3u + litn] : 0u) : 0u;
+        const uint32_t off = (uint32_t)win[pk + 1u + litn] | ((uint32_t)win[pk + 2u + litn] << 8);
+        uint32_t tot = lit + ml;
         uint32_t incl = tot;
 #pragma unroll
         for (uint32_t s = 1u; s < 32u; s <<= 1) {
             const uint32_t t = __shfl_up_sync(kFull, incl, s);
             if (lane >= s) incl += t;
         }
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        // P[] holds kGrpOutCap bytes: cut the group there (one sequence is at most 287 bytes)
+        const uint32_t fit = __popc(__ballot_sync(kFull, mine && incl <= kGrpOutCap));
+        if (fit < K) {
+            K = fit;
+            mine = lane < K;
+            if (!mine) lit = ml = tot = 0u;
+        }
+        const uint32_t total = __shfl_sync(kFull, incl, (int)(K - 1u));
+        const uint32_t consumed = __shfl_sync(kFull, endp, (int)(K - 1u));
         if (total > out_cap - op) return -4;
-        const uint32_t o_k = op + incl - tot;  // first output byte of the sequence
+        const uint32_t o_k = op + incl - tot;  // first output byte of the sequence (mine only)
         const uint32_t m_k = o_k + lit;        // first byte of its match
         if (__any_sync(kFull, mine && (off == 0u || off > m_k))) return -4;
 
-        // 4a. literals (input never aliases output)
+        // 4a. literals (input never aliases output); a literal byte is its own root
         const uint32_t maxlit = __reduce_max_sync(kFull, lit);
         for (uint32_t i = 0; i < maxlit; ++i)
-            if (i < lit) o.ring[o.ridx(o_k + i)] = win[pk + 1u + i];
-
-        // 4b. matches.  Sequence k reads [src, src + min(ml, off)) from other sequences (the
-        // rest of an overlapping match is its own output).  It depends on exactly the
-        // earlier sequences j whose match region [m_j, end_j) meets that range.
-        const uint32_t src = m_k - off;
-        const uint32_t src_hi = src + (ml < off ? ml : off);
-        const uint32_t endv = mine ? op + incl : 0xffffffffu;
-        const uint32_t mv = mine ? m_k : 0xffffffffu;
-        const uint32_t jlo = lz4g_count_below<false>(endv, src);    // end_j <= src: entirely before
-        const uint32_t jhi = lz4g_count_below<true>(mv, src_hi);    // m_j < src_hi
-        const uint32_t dep = (mine && jhi > jlo) ? (((1u << jhi) - 1u) & ~((1u << jlo) - 1u)) : 0u;
-        // The source is still in the ring unless it lies more than a window behind the end
-        // of this group; then it is in global memory (flushed long ago) and cannot overlap.
-        const bool from_ring = (op + total) - src <= kLz4Win;
-        __syncwarp();  // literals visible
-        bool pending = mine;
-        for (;;) {
-            const uint32_t pm = __ballot_sync(kFull, pending);
-            if (pm == 0u) break;
-            const bool go = pending && (pm & dep) == 0u;
-            // short matches: every lane copies its own, byte by byte (an overlapping match
-            // reads what the same lane wrote a few iterations earlier)
-            const uint32_t n = __reduce_max_sync(kFull, (go && !ext) ? ml : 0u);
-            if (from_ring) {
-                for (uint32_t i = 0; i < n; ++i)
-                    if (go && !ext && i < ml) o.ring[o.ridx(m_k + i)] = o.ring[o.ridx(src + i)];
-            } else {
-                for (uint32_t i = 0; i < n; ++i)
-                    if (go && !ext && i < ml) o.ring[o.ridx(m_k + i)] = o.g[src + i];
+            if (i < lit) {
+                o.ring[o.ridx(o_k + i)] = win[pk + 1u + i];
+                P[o_k - op + i] = (uint16_t)(o_k - op + i);
             }
-            // extended matches (19..273 bytes): one after the other, 32 bytes per step
-            uint32_t lm = __ballot_sync(kFull, go && ext);
+
+        // 4b. matches.  Every match byte gets a parent: the output byte it copies
+        // (src + i, or src + i % off for an overlapping match, so that a run costs one
+        // hop).  A parent produced before this group is copied right away and the byte
+        // becomes a root; the others are resolved by pointer jumping over P[].
+        const uint32_t src = m_k - off;
+        const uint32_t gend = op + total;
+        {
+            // short matches lane-parallel (the lane walks its own bytes) ...
+            const uint32_t n = __reduce_max_sync(kFull, (mine && !ext) ? ml : 0u);
+            uint32_t r = 0u;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (mine && !ext && i < ml) {
+                    const uint32_t sp = src + r;  // absolute position of the parent
+                    const uint32_t rel = m_k - op + i;
+                    if (sp < op) {
+                        o.ring[o.ridx(m_k + i)] = (gend - sp <= kGrpRing) ? o.ring[o.ridx(sp)] : o.g[sp];
+                        P[rel] = (uint16_t)rel;
+                    } else {
+                        P[rel] = (uint16_t)(sp - op);
+                    }
+                    if (++r == off) r = 0u;
+                }
+            }
+            // ... extended ones (19..273 bytes) 32 bytes per step by the whole warp
+            uint32_t lm = __ballot_sync(kFull, mine && ext);
             while (lm) {
                 const int j = __ffs((int)lm) - 1;
                 lm &= lm - 1u;
-                lz4g_warp_match(o, __shfl_sync(kFull, m_k, j), __shfl_sync(kFull, src, j),
-                                __shfl_sync(kFull, off, j), __shfl_sync(kFull, ml, j),
-                                __shfl_sync(kFull, (int)from_ring, j) != 0, lane);
+                const uint32_t jm = __shfl_sync(kFull, m_k, j), js = __shfl_sync(kFull, src, j);
+                const uint32_t jo = __shfl_sync(kFull, off, j), jn = __shfl_sync(kFull, ml, j);
+                const uint32_t step = 32u % jo;
+                uint32_t rr = lane % jo;
+                for (uint32_t i = lane; i < jn; i += 32u) {
+                    const uint32_t sp = js + rr;
+                    const uint32_t rel = jm - op + i;
+                    if (sp < op) {
+                        o.ring[o.ridx(jm + i)] = (gend - sp <= kGrpRing) ? o.ring[o.ridx(sp)] : o.g[sp];
+                        P[rel] = (uint16_t)rel;
+                    } else {
+                        P[rel] = (uint16_t)(sp - op);
+                    }
+                    rr += step;
+                    if (rr >= jo) rr -= jo;
+                }
             }
-            if (go) pending = false;
-            __syncwarp();
         }
+        __syncwarp();
+        // pointer jumping, in place: whatever a lane reads from P[] is an ancestor
+        for (;;) {
+            bool changed = false;
+            for (uint32_t b = lane; b < total; b += 32u) {
+                const uint32_t p = P[b];
+                if (p != b) {
+                    const uint32_t q = P[p];
+                    if (q != p) {
+                        P[b] = (uint16_t)q;
+                        changed = true;
+                    }
+                }
+            }
+            __syncwarp();
+            if (!__any_sync(kFull, changed)) break;
+        }
+        // every match byte that is not a root copies its root (roots are never written here)
+        for (uint32_t b = lane; b < total; b += 32u) {
+            const uint32_t r = P[b];
+            if (r != b) o.ring[o.ridx(op + b)] = o.ring[o.ridx(op + r)];
+        }
+        __syncwarp();
         ip += consumed;
         op += total;
         // 5. whole 16-byte chunks to HBM
@@ -312,10 +337,10 @@ lz4_decode_group_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz
         o.g = raw + d.raw_off;
         o.ring = mine;
         o.ga = (uint32_t)(reinterpret_cast<uintptr_t>(o.g) & 15u);
-        const int r = lz4_decode_block_group(comp + d.comp_off, d.comp_size, o, mine + kLz4Win,
-                                             mine + kLz4Win + kGrpWin,
-                                             reinterpret_cast<uint16_t*>(mine + kLz4Win + 2u * kGrpWin),
-                                             d.raw_size, lane);
+        o.mask = kGrpRing - 1u;
+        const int r = lz4_decode_block_group(
+            comp + d.comp_off, d.comp_size, o, mine + kGrpRing, mine + kGrpRing + kGrpWin,
+            reinterpret_cast<uint16_t*>(mine + kGrpRing + 6u * kGrpWin), d.raw_size, lane);
         if (lane == 0) status[b] = r;
         __syncwarp();
     }

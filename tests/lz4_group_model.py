@@ -10,8 +10,10 @@ __syncwarp() in the design shows up as a wrong byte.
 """
 import random
 
-WIN = 16384   # kLz4Win
+WIN = 8192    # kGrpRing: bytes of recent output mirrored in shared memory
+RING = WIN
 GW = 256      # kGrpWin
+OUTCAP = 2048  # kGrpOutCap: output bytes of one group (entries of P[])
 
 
 class Out:
@@ -137,9 +139,9 @@ def decode(inp, out_cap, ga=0, seed=0, stats=None):
                 ln = 3 + lit if lit != 15 else 0
                 if mln == 15 and ln:
                     ln += 1
-                    if p + ln > GW or win[p + ln - 1] == 255:
+                    if p + ln >= GW or win[p + ln - 1] == 255:
                         ln = 0
-                if p + ln > GW or p + ln >= avail:
+                if p + ln >= GW or p + ln >= avail:   # successor positions are one byte (nx[] tables)
                     ln = 0
                 lent[p] = ln
             p = 0
@@ -149,7 +151,8 @@ def decode(inp, out_cap, ga=0, seed=0, stats=None):
                     break
                 posv.append(p)
                 p += ln
-            K, consumed = len(posv), p
+            K = len(posv)
+            posv.append(p)              # posv[K] = end of the last sequence
         if K == 0:
             o.flush(op, True)
             assert o.flushed == op
@@ -176,6 +179,12 @@ def decode(inp, out_cap, ga=0, seed=0, stats=None):
         for k in range(32):
             acc += lit[k] + ml[k]
             incl[k] = acc
+        if incl[K - 1] > OUTCAP:        # P[] holds OUTCAP bytes: cut the group (one sequence is <= 287)
+            K = max(k + 1 for k in range(K) if incl[k] <= OUTCAP)
+            for k in range(K, 32):
+                lit[k] = ml[k] = 0
+            incl = [incl[min(k, K - 1)] for k in range(32)]
+        consumed = posv[K]
         total = incl[31]
         if total > out_cap - op:
             return -4, b""
@@ -187,82 +196,50 @@ def decode(inp, out_cap, ga=0, seed=0, stats=None):
         for k in lanes:
             for i in range(lit[k]):
                 o.ring[o.ridx(o_k[k] + i)] = win[pk[k] + 1 + i]
-        endv = [op + incl[k] if k < K else 0xFFFFFFFF for k in range(32)]
-        mv = [m_k[k] if k < K else 0xFFFFFFFF for k in range(32)]
-
-        def count_below(v, x, strict):
-            cnt, s = 0, 16
-            while s >= 1:
-                t = v[cnt + s - 1]
-                if (t < x) if strict else (t <= x):
-                    cnt += s
-                s >>= 1
-            return cnt
-
-        dep = [0] * 32
-        from_ring = [True] * 32
-        src = [0] * 32
-        for k in range(K):
-            src[k] = m_k[k] - off[k]
-            src_hi = src[k] + min(ml[k], off[k])
-            jlo = count_below(endv, src[k], False)
-            jhi = count_below(mv, src_hi, True)
-            assert jhi <= k
-            dep[k] = (((1 << jhi) - 1) & ~((1 << jlo) - 1)) if jhi > jlo else 0
-            from_ring[k] = (op + total) - src[k] <= WIN
-        pending = [k < K for k in range(32)]
-        rounds = 0
-        while True:
-            pm = sum(1 << k for k in range(32) if pending[k])
-            if pm == 0:
-                break
-            rounds += 1
-            go = [pending[k] and (pm & dep[k]) == 0 for k in range(32)]
-            assert any(go)
-            nmax = max([ml[k] for k in range(32) if go[k] and not ext[k]] + [0])
-            go_ext = [k for k in range(32) if go[k] and ext[k]]
-            go = [go[k] and not ext[k] for k in range(32)]
-            if rnd.random() < 0.5:
-                # lock-step over i, lanes scrambled inside each step (reads of step i precede its writes)
-                for i in range(nmax):
-                    act = [k for k in lanes if go[k] and i < ml[k]]
-                    vals = {}
-                    for k in act:
-                        s = src[k] + i
-                        if from_ring[k]:
-                            vals[k] = o.ring[o.ridx(s)]
-                        else:
-                            assert s < o.flushed
-                            vals[k] = o.g[s]
-                    for k in act:
-                        o.ring[o.ridx(m_k[k] + i)] = vals[k]
-            else:
-                # independent thread scheduling: one lane runs its whole copy before the next
-                for k in lanes:
-                    if not go[k]:
-                        continue
-                    for i in range(ml[k]):
-                        s = src[k] + i
-                        if from_ring[k]:
-                            v = o.ring[o.ridx(s)]
-                        else:
-                            assert s < o.flushed
-                            v = o.g[s]
-                        o.ring[o.ridx(m_k[k] + i)] = v
-            for j in go_ext:  # lz4g_warp_match: lanes of one copy in scrambled order
-                order = list(range(ml[j]))
-                rnd.shuffle(order)
-                for i in order:
-                    s_ = src[j] + (i % off[j] if off[j] < ml[j] else i)
-                    if from_ring[j]:
+        # 4b. matches: per-byte parent pointers P[] (relative to op), then pointer jumping
+        P = list(range(total))          # literal bytes are their own root
+        order = list(range(32))
+        rnd.shuffle(order)
+        for k in order:
+            if k >= K:
+                continue
+            src = m_k[k] - off[k]
+            for i in range(ml[k]):
+                s_ = src + (i % off[k] if off[k] < ml[k] else i)
+                rel = m_k[k] + i - op
+                if s_ < op:             # produced before this group: copy now, byte becomes a root
+                    if (op + total) - s_ <= RING:
                         v = o.ring[o.ridx(s_)]
                     else:
                         assert s_ < o.flushed
                         v = o.g[s_]
-                    o.ring[o.ridx(m_k[j] + i)] = v
-            for k in range(32):
-                if go[k] or k in go_ext:
-                    pending[k] = False
+                    o.ring[o.ridx(op + rel)] = v
+                    P[rel] = rel
+                else:
+                    assert s_ - op < rel
+                    P[rel] = s_ - op
+        rounds = 0
+        while True:
+            rounds += 1
+            changed = False
+            bs = list(range(total))
+            rnd.shuffle(bs)             # in-place, any order: every value read is an ancestor
+            for b in bs:
+                p_ = P[b]
+                if p_ != b:
+                    q = P[p_]
+                    if q != p_:
+                        P[b] = q
+                        changed = True
+            if not changed:
+                break
+        bs = list(range(total))
+        rnd.shuffle(bs)
+        for b in bs:
+            r = P[b]
+            if r != b:
+                assert P[r] == r
+                o.ring[o.ridx(op + b)] = o.ring[o.ridx(op + r)]
         if stats is not None:
             stats["groups"] = stats.get("groups", 0) + 1
             stats["seqs"] = stats.get("seqs", 0) + K

@@ -36,7 +36,7 @@ def test_group_algorithm_decodes_real_blocks(name, col, ga):
     if name in ("runs_mean8", "iid_categories", "runs_mean2"):
         # the point of the design: many sequences per group, few dependency rounds
         assert stats["seqs"] / stats["groups"] > 24
-        assert stats["rounds"] / stats["groups"] < 8
+        assert stats["rounds"] / stats["groups"] < 6  # pointer-jumping steps, incl. the last (no change)
 
 
 def test_group_algorithm_rejects_what_the_oracle_rejects():
@@ -89,4 +89,4 @@ def test_chained_dependencies_inside_one_group():
         stats = {}
         status, out = M.decode(bytes(seqs), len(want), ga=ga, seed=ga, stats=stats)
         assert status == len(want) and out == bytes(want)
-    assert stats["rounds"] > stats["groups"]  # dependencies really were serialised
+    assert stats["rounds"] > stats["groups"]  # chains needed more than one jumping step
