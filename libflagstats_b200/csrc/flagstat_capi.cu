@@ -53,15 +53,20 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
 // compute the same thing; they differ in how bytes reach the registers and in
 // how the counters are organised, and are kept selectable for A/B measurement
 // (profiles/, tools/variant_ab.py, tools/perf_sweep.py):
-//   0  cp.async ring + compile-time groups of 4 batches, fp16x2-compare mask   (default)
-//   1  same, integer-only mask select (cross-check of the fp16 compares)
+//   0  cp.async ring + compile-time groups of 4 batches; QC-clean batches without SECONDARY
+//      records use the fp16x2-compare mask of variant 8, all others build the keep-mask and the
+//      SECONDARY fix-up with HFMA2 and gate the QC-fail counter with HMUL2 on the FMA pipe;
+//      detect-free dense mode while every batch needs the second counter          (default)
+//   1  the group kernel with the integer-only mask select (cross-check of the fp16 forms)
 //   2  register-staged LDG.128 double buffer, run-time hold levels
 //   3  TMA (cp.async.bulk + mbarrier) shared-memory ring, 4 stages, producer warp
 //   4  TMA ring, 6 stages
 //   5  cp.async ring depth 4 with run-time hold levels (the round-1 "r1i" kernel)
 //   6  same, depth 2
 //   7  as 5 with the class tests as fp16x2 tent functions (half pipe instead of ALU pipe)
-constexpr int kNumVariants = 8;
+//   8  the group kernel with the fp16x2-compare mask + PRMT fail mask on every path (the
+//      default until profiles/r2f: 0.71-0.76 of the measured peak on U(0,4095), 0.92 now)
+constexpr int kNumVariants = 9;
 using KernelFn = void (*)(const uint16_t*, uint64_t, unsigned long long*, const XchgArgs);
 
 struct KernelCfg {
@@ -73,7 +78,7 @@ struct KernelCfg {
 constexpr size_t tma_smem(int stages) { return (size_t)stages * kStageBytes + 2u * stages * 8u; }
 
 const KernelCfg kKernels[kNumVariants] = {
-    {{flagstat_kernel_group<kFlagstat, 0, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
+    {{flagstat_kernel_group<kFlagstat, 3, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
     {{flagstat_kernel_group<kFlagstat, 1, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
@@ -87,6 +92,8 @@ const KernelCfg kKernels[kNumVariants] = {
     {{flagstat_kernel_ring<kFlagstat, 0, 2, 2>, flagstat_kernel_ring<kPospopcnt, 0, 2, 2>},
      kThreads, (size_t)2 * kStageBytes},
     {{flagstat_kernel_ring<kFlagstat, 2, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+     kThreads, (size_t)4 * kStageBytes},
+    {{flagstat_kernel_group<kFlagstat, 0, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
 };
 

@@ -160,6 +160,7 @@ struct GroupCounter {
 };
 
 using GCounter = GroupCounter<6>;  // 12 planes: 63 groups = 4032 words per epoch
+constexpr uint32_t kDenseGroups = 7u;  // detect-free groups after a group that was all general-path
 
 template <int MODE, int VARIANT>
 struct GroupLanes {
@@ -176,24 +177,39 @@ struct GroupLanes {
         fail_dirty = false;
     }
 
+    // One batch.  `dense` (warp-uniform, VARIANT 3 only): skip the OR-detect and feed
+    // the second counter unconditionally; that is correct for any data, the detect
+    // only buys the cheaper path.  Returns whether the batch needed the second
+    // counter (feeds the caller's dense-mode decision).
     template <int POS>
-    __device__ __forceinline__ void step(const uint32_t (&w)[16])
+    __device__ __forceinline__ bool step(const uint32_t (&w)[16], bool dense = false)
     {
         if (MODE == kPospopcnt) {
             all.template absorb<POS>(w);
-            return;
+            return false;
         }
         // warp-uniform view of the batch: OR of all 512 packed words (REDUX.OR)
-        uint32_t any = w[0];
+        uint32_t wany = 0xffffffffu;
+        if (VARIANT != 3 || !dense) {
+            uint32_t any = w[0];
 #pragma unroll
-        for (int i = 1; i < 16; ++i) any |= w[i];
-        const uint32_t wany = __reduce_or_sync(0xffffffffu, any);
+            for (int i = 1; i < 16; ++i) any |= w[i];
+            wany = __reduce_or_sync(0xffffffffu, any);
+        }
+        const bool has_sec = (wany & 0x01000100u) != 0u;   // a SECONDARY record in this warp batch
+        const bool has_fail = (wany & 0x02000200u) != 0u;  // a QC-fail record
 
         uint32_t y[16];
         if (VARIANT == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = mask_select_i(w[i]);
-        } else if ((wany & 0x01000100u) == 0u) {  // no SECONDARY record in this warp batch
+        } else if (VARIANT == 3 && (has_sec || has_fail)) {
+            // ALU-bound batches: keep-mask and SECONDARY fix-up built on the FMA pipe (4 ALU +
+            // 4 HFMA2 per word).  QC-clean batches without SECONDARY records -- real data, where
+            // DRAM is the limit -- keep the form with the fewest instructions overall (below).
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = mask_select_f(w[i]);
+        } else if (!has_sec) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = mask_select_h_nosec(w[i]);
         } else {
@@ -201,9 +217,9 @@ struct GroupLanes {
             for (int i = 0; i < 16; ++i) y[i] = mask_select_h(w[i]);
         }
         all.template absorb<POS>(y);
-        if ((wany & 0x02000200u) != 0u) {  // QC-fail records present: second counter
+        if (has_fail) {  // second counter
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] &= fail_mask<VARIANT>(w[i]);
+            for (int i = 0; i < 16; ++i) y[i] = VARIANT == 3 ? fail_gate_f(w[i], y[i]) : (y[i] & fail_mask<VARIANT>(w[i]));
             fail.template absorb<POS>(y);
             fail_dirty = true;
             fail_open = POS != 3;
@@ -211,6 +227,7 @@ struct GroupLanes {
             fail.template absorb_zero<POS>();
             fail_open = POS != 3;
         }
+        return VARIANT == 3 ? has_fail : (has_sec && has_fail);
     }
 
     __device__ __forceinline__ void close()
@@ -308,7 +325,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
         }
         cp_async_commit();  // empty groups keep the group count uniform
     };
-    auto batch = [&](auto pos_tag) {
+    auto batch = [&](auto pos_tag, bool dense) -> bool {
         constexpr int POS = decltype(pos_tag)::value;
         cp_async_wait<DEPTH - 1>();
         uint32_t w[16];
@@ -316,8 +333,9 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
         lds128_imm<(POS * kU + 1) * kThreads * 16>(my_smem, w[4], w[5], w[6], w[7]);
         lds128_imm<(POS * kU + 2) * kThreads * 16>(my_smem, w[8], w[9], w[10], w[11]);
         lds128_imm<(POS * kU + 3) * kThreads * 16>(my_smem, w[12], w[13], w[14], w[15]);
-        st.template step<POS>(w);
+        const bool general = st.template step<POS>(w, dense);
         fetch(pos_tag);  // the registers have been consumed: refill this stage
+        return general;
     };
     using P0 = std::integral_constant<int, 0>;
     using P1 = std::integral_constant<int, 1>;
@@ -333,22 +351,30 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
     // groups); the ragged last group (my % 4 batches) rides in the last epoch with room.
     const uint32_t ngroups = my >> 2, rem = my & 3u;
     uint32_t g = 0;
+    uint32_t dense_left = 0u;  // groups left to run without the OR-detect (warp-uniform)
     bool rem_done = rem == 0u;
     do {
         uint32_t lim = GCounter::kMaxGroups - groups;
         if (lim > ngroups - g) lim = ngroups - g;
         for (uint32_t i = 0; i < lim; ++i) {
-            batch(P0{});
-            batch(P1{});
-            batch(P2{});
-            batch(P3{});
+            // Dense mode (VARIANT 3): a group whose four batches all needed the general
+            // path switches the detect off for the next kDenseGroups groups.
+            const bool dense = VARIANT == 3 && dense_left != 0u;
+            const bool g0 = batch(P0{}, dense);
+            const bool g1 = batch(P1{}, dense);
+            const bool g2 = batch(P2{}, dense);
+            const bool g3 = batch(P3{}, dense);
+            if (VARIANT == 3) {
+                if (dense) --dense_left;
+                else if (g0 && g1 && g2 && g3) dense_left = kDenseGroups;
+            }
         }
         g += lim;
         groups += lim;
         if (g == ngroups && !rem_done && groups < GCounter::kMaxGroups) {
-            batch(P0{});
-            if (rem > 1) batch(P1{});
-            if (rem > 2) batch(P2{});
+            batch(P0{}, false);
+            if (rem > 1) batch(P1{}, false);
+            if (rem > 2) batch(P2{}, false);
             st.close();
             rem_done = true;
         }

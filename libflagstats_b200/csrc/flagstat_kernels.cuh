@@ -153,6 +153,52 @@ __device__ __forceinline__ uint32_t fail_mask_h(uint32_t w)
     return d;
 }
 
+// Variant F (default since round 2): the keep-mask is BUILT on the FMA pipe.
+// The two class tests come out of HSET2 as fp16 1.0 / 0.0 (.BF form) and HFMA2
+// add the bits each class keeps to the always-kept base, in units of the base's
+// own ulp (2^-22; 0x0F04 = 1796 ulp, exponent field 3):
+//     k = 0x0F04 + [K & UNMAP] * 0xC0 + [G] * 0xCB   ->  0x0FC4 / 0x0FCF / 0x0F04
+// (0xC0 ulp = fp16 subnormal 0x0300, 0xCB ulp = 0x032C; every sum is < 2048 ulp,
+// so the additions are exact and the bit patterns are the masks themselves).
+// SUPPLEMENTARY must not count for SECONDARY records (the reference's else-if):
+// q = w & 0x0905 read as fp16 is >= 0x0900 exactly when both bits are set, the
+// next smaller possible value is 0x0805, and
+//     z = sat(q * 49152 - 6.03125)   is 1.0 for the former and 0 for everything else
+// (0x0900 -> 7.5 - 6.03, 0x0805 -> 6.0293 - 6.03125 < 0).  Such a record is never
+// in class G or K, so its k is the base, and k - z * 1347 ulp = 449 ulp = 0x0704:
+// the base with bit 11 cleared.  One AND then applies everything:  y = w & k.
+// ALU pipe: AND, HSET2, HSET2, AND = 4 (was 5, or 6 with a SECONDARY record in the
+// batch); FMA pipe: 4 HFMA2.  y has bits 4, 5, 12..15 CLEAR (the HSET2-mask form
+// let input bits through for G records).  The pipe microbenchmark shows HFMA2 /
+// HMUL2 issue for free beside LOP3 up to 1 per 2 ALU instructions
+// (profiles/r2b_pipe_microbench.txt).
+__device__ __forceinline__ uint32_t mask_select_f(uint32_t w)
+{
+    const uint32_t q = w & 0x09050905u;
+    uint32_t g1, x1, z, k;
+    asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(g1) : "r"(q), "r"(0x00010001u));
+    asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(x1) : "r"(q), "r"(0x00050005u));
+    asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(z) : "r"(q), "r"(0x7A007A00u), "r"(0xC608C608u));
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(x1), "r"(0x03000300u), "r"(0x0F040F04u));
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(g1), "r"(0x032C032Cu), "r"(k));
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(z), "r"(0x8D438D43u), "r"(k));
+    return w & k;
+}
+
+// QC-fail gating of a variant-F word without an integer mask: bit 9 of the record,
+// read as fp16, is the subnormal 2^-15; times 2^15 it is 1.0 or 0.0, and y * 1.0
+// is y exactly (y <= 0x0FCF is a finite non-negative fp16 -- this needs the CLEAN
+// bits 12..15 of mask_select_f), y * 0.0 = +0.  One ALU instruction (the AND)
+// and two HMUL2 instead of shift + PRMT + AND.
+__device__ __forceinline__ uint32_t fail_gate_f(uint32_t w, uint32_t y)
+{
+    const uint32_t f = w & 0x02000200u;
+    uint32_t f1, yf;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(f1) : "r"(f), "r"(0x78007800u));
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(yf) : "r"(y), "r"(f1));
+    return yf;
+}
+
 // Variant I: integer-only formulation (A/B reference for the one above and a
 // safety net should a future toolchain change fp16 subnormal semantics).
 __device__ __forceinline__ uint32_t mask_select_i(uint32_t w)

@@ -31,7 +31,7 @@ def _dev(a, off=0):
     return v
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
     fs = cuda_lib
     prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
@@ -47,7 +47,7 @@ def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
         fs.lib().FLAGSTAT_cuda_set_variant(prev)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 7, 8])
 def test_every_record_value_in_both_register_halves(cuda_lib, variant):
     """All 65536 FLAG words, once at even and once at odd record positions (low and
     high half of the packed 32-bit register), and next to every neighbour class."""
@@ -163,6 +163,33 @@ def test_inmemory_config_100m_uniform(cuda_lib):
     assert parts.tolist() == got.tolist()
     assert fs.flagstat_u64(torch.flip(d, dims=[0]).contiguous()).tolist() == got.tolist()
     assert fs.flagstat_u64(host).tolist() == got.tolist()  # pageable host pointer, chunked staging
+
+
+@pytest.mark.parametrize("variant", [0, 8])
+def test_dense_mode_transitions(cuda_lib, variant):
+    """The default kernel (variant 0) switches its per-batch OR-detect off after a group of
+    batches that all fed the QC-fail counter and probes again 7 groups later (variant 8, the
+    round-1 default, has no such mode and runs as the cross-check).  A column whose phases are long enough for every CTA to enter the mode, run it
+    over QC-clean data, leave it and enter it again must still count exactly; with 50 000
+    records of bits 12..15 garbage sprinkled in (the fp16 gating needs clean high bits)."""
+    fs = cuda_lib
+    from libflagstats_b200 import synth
+    torch = _torch()
+    phase = 120_000_000
+    d = torch.empty(3 * phase + 5, dtype=torch.int16, device="cuda")
+    synth.uniform_device(phase, 0, 7, 0x0FFF, out=d[:phase])
+    synth.hiseqx_device(phase, 0, 3, 0, out=d[phase:2 * phase])
+    synth.uniform_device(phase + 5, 1 << 33, 9, 0xFFFF, out=d[2 * phase:])
+    torch.cuda.synchronize()
+    host = d.cpu().numpy().view(np.uint16)
+    want = O.flagstat_simd(host)
+    head = O.flagstat_simd(host[:3])
+    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    try:
+        assert fs.flagstat_u64(d).tolist() == want.tolist()
+        assert fs.flagstat_u64(d[3:]).tolist() == (want - head).tolist()  # unaligned base
+    finally:
+        fs.lib().FLAGSTAT_cuda_set_variant(prev)
 
 
 def test_kat_e_full_hiseqx_on_device(cuda_lib, golden):

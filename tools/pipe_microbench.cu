@@ -23,7 +23,10 @@ constexpr int kInner = 16;  // ops per chain per loop iteration
 enum Op {
     LOP3, IMAD, SHL, SHR, PRMT, IADD, POPC, HSET2, HFMA2, HADD2, IMADWIDE, FFMA,
     MIX_LOP3_IMAD, MIX_LOP3_HSET2, MIX_KERNEL, MIX_LOP3_SHR, MIX_LOP3_HFMA2, VOTE, SHFL,
-    LDS, MIX_LOP3_LDS, MIX_LOP3_POPC, HMNMX2, MIX_LOP3_HSET2_IMAD, NOPS
+    LDS, MIX_LOP3_LDS, MIX_LOP3_POPC, HMNMX2, MIX_LOP3_HSET2_IMAD,
+    MINU16X2, ADDU16X2, IMNMX, FMNMX, SEL, MIX_LOP3_HMNMX2, MIX_LOP3_MINU16X2, MIX_LOP3_IADD, MIX_LOP3_FFMA,
+    MIX_LOP3_HMNMX2_4, MIX_LOP3_HFMA2_8, MIX_LOP3_IADD_IMAD, HSET2F, MIX_LOP3_HFMA2_2, MIX_LOP3_HFMA2_3, MIX_LOP3_HFMA2_4, MIX_LOP3_HMUL2_3,
+    MIX_LOP3_HFMA2_IMAD_6, NOPS
 };
 
 const char* kNames[] = {
@@ -31,7 +34,11 @@ const char* kNames[] = {
     "HFMA2", "HADD2", "IMAD.WIDE", "FFMA",
     "mix LOP3:IMAD 1:1", "mix LOP3:HSET2 1:1", "mix kernel 8 LOP3 : 2 HSET2 : 2 IMAD", "mix LOP3:SHR 1:1",
     "mix LOP3:HFMA2 1:1", "VOTE.ANY", "SHFL.BFLY", "LDS.32 (conflict-free)", "mix LOP3:LDS 4:1",
-    "mix LOP3:POPC 4:1", "HMNMX2 (min.f16x2)", "mix LOP3:HSET2:IMAD 2:1:1"};
+    "mix LOP3:POPC 4:1", "HMNMX2 (min.f16x2)", "mix LOP3:HSET2:IMAD 2:1:1",
+    "min.u16x2", "add.u16x2", "min.u32", "min.f32", "selp", "mix LOP3:HMNMX2 1:1", "mix LOP3:min.u16x2 1:1",
+    "mix LOP3:IADD 1:1", "mix LOP3:FFMA 1:1", "mix LOP3:HMNMX2 4:1", "mix LOP3:HFMA2 8:1", "mix LOP3:IADD:IMAD 2:1:1",
+    "HSET2 (set.eq.f16x2.f16x2)", "mix LOP3:HFMA2 2:1", "mix LOP3:HFMA2 3:1", "mix LOP3:HFMA2 4:1", "mix LOP3:HMUL2 3:1",
+    "mix LOP3:HFMA2:IMAD 6:2:1"};
 
 template <int OP>
 __device__ __forceinline__ void body(uint32_t (&a)[kChains], uint32_t b, uint32_t c, const uint32_t* sm)
@@ -52,7 +59,7 @@ __device__ __forceinline__ void body(uint32_t (&a)[kChains], uint32_t b, uint32_
             if (OP == HSET2) asm volatile("set.eq.u32.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
             if (OP == HFMA2) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
             if (OP == HADD2) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
-            if (OP == HMNMX2) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+            if (OP == HMNMX2) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
             if (OP == IMADWIDE) {
                 uint64_t w;
                 asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(a[i]), "r"(b), "l"((uint64_t)c));
@@ -89,6 +96,67 @@ __device__ __forceinline__ void body(uint32_t (&a)[kChains], uint32_t b, uint32_
                 const int m = k % 4;
                 if (m == 2) asm volatile("set.eq.u32.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
                 else if (m == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+
+            if (OP == MINU16X2) asm volatile("min.u16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            if (OP == ADDU16X2) asm volatile("add.u16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            if (OP == IMNMX) asm volatile("min.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            if (OP == FMNMX) {
+                float f = __uint_as_float(a[i]);
+                asm volatile("min.f32 %0, %0, %1;" : "+f"(f) : "f"(__uint_as_float(y)));
+                a[i] = __float_as_uint(f);
+            }
+            if (OP == SEL) asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; selp.u32 %0, %0, %1, q; }" : "+r"(a[i]) : "r"(y), "r"(c));
+            if (OP == HSET2F) asm volatile("set.eq.f16x2.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            if (OP == MIX_LOP3_HMNMX2) {
+                if (k & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            }
+            if (OP == MIX_LOP3_MINU16X2) {
+                if (k & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else asm volatile("min.u16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            }
+            if (OP == MIX_LOP3_IADD) {
+                if (k & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+            }
+            if (OP == MIX_LOP3_FFMA) {
+                if (k & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else {
+                    float f = __uint_as_float(a[i]);
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(b)), "f"(__uint_as_float(c)));
+                    a[i] = __float_as_uint(f);
+                }
+            }
+            if (OP == MIX_LOP3_HMNMX2_4) {
+                if (k % 5 == 4) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+            if (OP == MIX_LOP3_HFMA2_8) {
+                if ((k * kChains + i) % 9 == 8) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+            if (OP == MIX_LOP3_IADD_IMAD) {
+                const int m = k % 4;
+                if (m == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(y));
+                else if (m == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(y), "r"(c));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+
+            if (OP == MIX_LOP3_HFMA2_2 || OP == MIX_LOP3_HFMA2_3 || OP == MIX_LOP3_HFMA2_4) {
+                const int per = OP == MIX_LOP3_HFMA2_2 ? 3 : OP == MIX_LOP3_HFMA2_3 ? 4 : 5;
+                if ((k * kChains + i) % per == per - 1) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+            if (OP == MIX_LOP3_HMUL2_3) {
+                if ((k * kChains + i) % 4 == 3) asm volatile("mul.rn.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
+            }
+            if (OP == MIX_LOP3_HFMA2_IMAD_6) {
+                const int m = (k * kChains + i) % 9;
+                if (m == 2 || m == 6) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                else if (m == 8) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(y), "r"(c));
                 else asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[i]) : "r"(y), "r"(c));
             }
             if (OP == VOTE) {
@@ -190,5 +258,23 @@ int main()
     rc |= run<LDS>(d_out, d_cyc, nsm);
     rc |= run<MIX_LOP3_LDS>(d_out, d_cyc, nsm);
     rc |= run<MIX_LOP3_POPC>(d_out, d_cyc, nsm);
+    rc |= run<MINU16X2>(d_out, d_cyc, nsm);
+    rc |= run<ADDU16X2>(d_out, d_cyc, nsm);
+    rc |= run<IMNMX>(d_out, d_cyc, nsm);
+    rc |= run<FMNMX>(d_out, d_cyc, nsm);
+    rc |= run<SEL>(d_out, d_cyc, nsm);
+    rc |= run<HSET2F>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HMNMX2>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_MINU16X2>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_IADD>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_FFMA>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HMNMX2_4>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HFMA2_8>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_IADD_IMAD>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HFMA2_2>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HFMA2_3>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HFMA2_4>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HMUL2_3>(d_out, d_cyc, nsm);
+    rc |= run<MIX_LOP3_HFMA2_IMAD_6>(d_out, d_cyc, nsm);
     return rc;
 }

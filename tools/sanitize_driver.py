@@ -13,7 +13,7 @@ from libflagstats_b200 import sharded, synth
 from oracle import oracle as O
 
 lib = fs.lib()
-for variant in range(8):
+for variant in range(9):
     lib.FLAGSTAT_cuda_set_variant(variant)
     for n, off in ((0, 0), (5, 1), (16384 * 8 * 3 + 77, 3), (1_300_003, 0)):
         d = synth.uniform_device(n + off, 0, 7, 0x0FFF)[off:]
