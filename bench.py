@@ -340,6 +340,21 @@ def ours(args) -> int:
     if clocks is not None:
         clocks["window"] = f"{kiters} back-to-back kernel launches ({(tk1 - tk0) * 1e3:.0f} ms) right after the timed steps"
 
+    # ---- read-only HBM probe on the same bytes (LDG.128 + one XOR per 16 B, nothing else):
+    # what a stream that only READS reaches on this device in this run; MEASURED_PEAKS.json
+    # is a copy (read + write), which a read-only kernel can exceed
+    read_probe_gbs = None
+    try:
+        import ctypes as C
+        pm = C.c_float(0)
+        nbytes16 = (2 * n) & ~15
+        fs.check(fs.lib().FLAGSTAT_cuda_read_probe(data.data_ptr(), nbytes16, 3, C.byref(pm)), "read_probe")
+        fs.check(fs.lib().FLAGSTAT_cuda_read_probe(data.data_ptr(), nbytes16, 200, C.byref(pm)), "read_probe")
+        read_probe_gbs = nbytes16 / (pm.value * 1e-3) / 1e9
+    except Exception as exc:
+        read_probe_gbs = None
+        print(f"bench.py: read probe failed: {exc!r}", file=sys.stderr)
+
     # ---- end to end through the public host-pointer API ---------------------
     host = torch.empty(n, dtype=torch.int16, pin_memory=True)
     host.copy_(data)
@@ -465,6 +480,9 @@ def ours(args) -> int:
     value = world * n / (step_ms * 1e-3)
     achieved = 2.0 * n / (kernel_ms * 1e-3) / 1e9
     traffic = load_traffic()
+    kernel_name = fs.lib().FLAGSTAT_cuda_kernel_name(0).decode()
+    if traffic and "fsb200::" + traffic.get("kernel", "") != kernel_name:
+        traffic = None  # the committed ncu capture is of another kernel: no traffic claim
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
@@ -474,8 +492,10 @@ def ours(args) -> int:
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src,
-            "kernel": "fsb200::" + (traffic or {}).get("kernel", "flagstat_kernel_ring<0, 0, 4, 2>"),
+            "kernel": kernel_name,
             "kernel_ms": kernel_ms, "kernel_ms_slowest_rank": kernel_ms_max,
+            "read_only_probe_gbs": read_probe_gbs,
+            "frac_of_read_only_probe": (achieved / read_probe_gbs) if read_probe_gbs else None,
             "algorithmic_bytes_per_launch": 2 * n,
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),

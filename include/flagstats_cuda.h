@@ -215,6 +215,9 @@ int FLAGSTAT_cuda_set_variant(int variant);
  * sequence per warp step.  Returns the previous.  Env FLAGSTAT_CUDA_LZ4_VARIANT sets the
  * initial value. */
 int FLAGSTAT_cuda_set_lz4_variant(int variant);
+/* Name of the kernel instantiation the selected variant launches (as ncu prints it);
+ * mode 0 = flagstat, 1 = pospopcnt. */
+const char* FLAGSTAT_cuda_kernel_name(int mode);
 /* Persistent-grid size override: CTAs per SM (0 = default). */
 int FLAGSTAT_cuda_set_ctas_per_sm(int n);
 
@@ -239,6 +242,10 @@ int FLAGSTAT_cuda_sync(void);
  * internal stream; returns 0 and the mean milliseconds per launch. */
 int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
                               int pospopcnt_mode, float* ms_per_launch);
+/* Read-only HBM probe over device memory (16-byte aligned): LDG.128 + one XOR per 16
+ * bytes, nothing else; mean milliseconds per pass.  The roofline a stream that only
+ * reads can reach on this device (a copy pays bus turn-arounds a read does not). */
+int FLAGSTAT_cuda_read_probe(const void* d_bytes, uint64_t n_bytes, int iters, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ SIGNATURES = {
     "FLAGSTAT_cuda_version": (C.c_char_p, []),
     "FLAGSTAT_cuda_launch_count": (C.c_uint64, []),
     "FLAGSTAT_cuda_set_variant": (C.c_int, [C.c_int]),
+    "FLAGSTAT_cuda_kernel_name": (C.c_char_p, [C.c_int]),
     "FLAGSTAT_cuda_set_lz4_variant": (C.c_int, [C.c_int]),
     "FLAGSTAT_cuda_set_ctas_per_sm": (C.c_int, [C.c_int]),
     "FLAGSTAT_cuda_synth_uniform": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
@@ -72,6 +73,7 @@ SIGNATURES = {
     "FLAGSTAT_cuda_sync": (C.c_int, []),
     "FLAGSTAT_cuda_time_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
                                             C.POINTER(C.c_float)]),
+    "FLAGSTAT_cuda_read_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

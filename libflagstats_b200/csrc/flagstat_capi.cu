@@ -825,6 +825,30 @@ int FLAGSTAT_cuda_set_variant(int v)
 }
 int FLAGSTAT_cuda_set_ctas_per_sm(int n) { return g_ctas_per_sm.exchange(n); }
 
+const char* FLAGSTAT_cuda_kernel_name(int mode)
+{
+    // the instantiation launch() picks for the selected variant, spelled as ncu prints it
+    static const char* const kNames[kNumVariants][2] = {
+        {"fsb200::flagstat_kernel_group<0, 3, 2>", "fsb200::flagstat_kernel_group<1, 0, 2>"},
+        {"fsb200::flagstat_kernel_group<0, 1, 2>", "fsb200::flagstat_kernel_group<1, 0, 2>"},
+        {"fsb200::flagstat_kernel<0, 0>", "fsb200::flagstat_kernel<1, 0>"},
+        {"fsb200::flagstat_kernel_tma<0, 0, 4, 2>", "fsb200::flagstat_kernel_tma<1, 0, 4, 2>"},
+        {"fsb200::flagstat_kernel_tma<0, 0, 6, 2>", "fsb200::flagstat_kernel_tma<1, 0, 6, 2>"},
+        {"fsb200::flagstat_kernel_ring<0, 0, 4, 2>", "fsb200::flagstat_kernel_ring<1, 0, 4, 2>"},
+        {"fsb200::flagstat_kernel_ring<0, 0, 2, 2>", "fsb200::flagstat_kernel_ring<1, 0, 2, 2>"},
+        {"fsb200::flagstat_kernel_ring<0, 2, 4, 2>", "fsb200::flagstat_kernel_ring<1, 0, 4, 2>"},
+        {"fsb200::flagstat_kernel_group<0, 0, 2>", "fsb200::flagstat_kernel_group<1, 0, 2>"},
+    };
+    static_assert(kFlagstat == 0 && kPospopcnt == 1, "names above spell the MODE template argument");
+    int v = g_variant.load();
+    if (v == -1) {
+        v = 0;
+        if (const char* e = std::getenv("FLAGSTAT_CUDA_VARIANT")) v = std::atoi(e);
+    }
+    if (v < 0 || v >= kNumVariants) v = 0;
+    return kNames[v][mode == kPospopcnt ? 1 : 0];
+}
+
 int FLAGSTAT_cuda_synth_uniform(uint16_t* d_out, uint64_t start, uint64_t n, uint64_t seed,
                                 uint16_t mask, void* stream)
 {
@@ -920,6 +944,47 @@ int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d
     cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return rc;
+}
+
+// Read-only HBM probe: the same bytes through LDG.128 with one XOR per 16 bytes and no
+// other work (tools/hbm_read_probe.cu holds the sweep this configuration won: 8 loads in
+// flight per thread, 4 CTAs per SM).  bench.py reports the flagstat kernel against it
+// next to the copy-kernel peak of MEASURED_PEAKS.json.
+int FLAGSTAT_cuda_read_probe(const void* d_bytes, uint64_t n_bytes, int iters, float* ms_per_launch)
+{
+    if (!d_bytes || !ms_per_launch || iters <= 0) return FLAGSTAT_CUDA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(d_bytes) & 15u) != 0) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    DeviceInfo* di = nullptr;
+    int rc = device_info(dev, &di);
+    if (rc) return rc;
+    Lane* l = nullptr;
+    rc = lane_acquire(dev, &l);
+    if (rc) return rc;
+    struct Release {
+        Lane* l;
+        ~Release() { lane_release(l); }
+    } rel{l};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0, l->comp));
+    for (int i = 0; i < iters; ++i)
+        hbm_read_probe_kernel<<<di->sms * 4, kThreads, 0, l->comp>>>(
+            static_cast<const uint4*>(d_bytes), n_bytes / 16u,
+            reinterpret_cast<unsigned long long*>(l->d_flags));
+    CK(cudaEventRecord(e1, l->comp));
+    CK(cudaStreamSynchronize(l->comp));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / (float)iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
 }
 
 }  // extern "C"
