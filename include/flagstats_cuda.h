@@ -77,6 +77,43 @@ int FLAGSTAT_cuda_available(void);
 uint32_t FLAGSTAT_cuda_min_len(void);
 void FLAGSTAT_cuda_set_min_len(uint32_t n);
 
+/* ---- samtools mode: the reference benchmark's flagstat_loop caller -----------
+ *
+ * benchmark/flagstats.cpp:43-71 keeps a bam_flagstat_t next to the 32 counters and
+ * prints samtools' report from it (:577-588).  Ten of its eleven FLAG-derived
+ * fields follow from the 32 counters; the eleventh, n_pair_all ("paired in
+ * sequencing", :58-59), does not -- FLAGSTAT_scalar_update has it commented out
+ * (libflagstats.h:132) and the Python wrapper approximates it as READ1 + READ2
+ * (python/libflagstats.pyx:35).  The *_samtools entries count it exactly, in the
+ * same single pass: flags[0] / flags[16] += n_pair_all of QC-pass / QC-fail
+ * records (slots the FLAGSTAT_* contract leaves free), every other slot as
+ * FLAGSTAT_cuda_u64.  Same pointer kinds, accumulate and error contract. */
+int FLAGSTAT_cuda_samtools_u64(const uint16_t* array, uint64_t len, uint64_t* flags /*[32]*/);
+/* async, device pointers (cf. FLAGSTAT_cuda_device) */
+int FLAGSTAT_cuda_samtools_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags,
+                                  void* stream);
+
+/* bam_flagstat_t, benchmark/flagstats.cpp:43-49 (same fields, same order; each
+ * [QC-pass, QC-fail]).  n_diffchr / n_diffhigh need RNAME / MAPQ, not the FLAG
+ * word, and are never written. */
+typedef struct {
+    long long n_reads[2], n_mapped[2], n_pair_all[2], n_pair_map[2], n_pair_good[2];
+    long long n_sgltn[2], n_read1[2], n_read2[2];
+    long long n_dup[2];
+    long long n_diffchr[2], n_diffhigh[2];
+    long long n_secondary[2], n_supp[2];
+} FLAGSTAT_cuda_bam_flagstat;
+
+/* flagstat_loop (benchmark/flagstats.cpp:51-71) over a whole column: ADDS to *s. */
+int FLAGSTAT_cuda_samtools(const uint16_t* array, uint64_t len, FLAGSTAT_cuda_bam_flagstat* s);
+/* The same struct from 32 counters produced by a *_samtools entry (host memory); ADDS. */
+int FLAGSTAT_cuda_samtools_from_counters(const uint64_t* flags /*[32]*/,
+                                         FLAGSTAT_cuda_bam_flagstat* s);
+/* The report of benchmark/flagstats.cpp:577-588, byte for byte (percent() of :73-78).
+ * Writes at most capacity - 1 characters + NUL; returns the length of the full
+ * report (snprintf convention) or a negative FLAGSTAT_CUDA_E* code.  Host only. */
+int FLAGSTAT_cuda_samtools_report(const FLAGSTAT_cuda_bam_flagstat* s, char* buf, size_t capacity);
+
 /* ---- raw positional popcount (STORM_pospopcnt_u16, libalgebra.h:3496) ---- */
 
 int POSPOPCNT_cuda_u16(const uint16_t* data, size_t len, uint32_t* out /*[16]*/);
@@ -135,6 +172,10 @@ int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, ui
  * records counted.  Runs on the current device; synchronous. */
 #define FLAGSTAT_CUDA_FILE_RAW 0
 #define FLAGSTAT_CUDA_FILE_LZ4 1
+/* OR into `format`: count like FLAGSTAT_cuda_samtools_u64 (flags[0] / flags[16] =
+ * n_pair_all) -- the reference's "samtools" readers of the same files
+ * (flagstat_loop per block, flagstats.cpp:496-519 raw, :547-590 LZ4). */
+#define FLAGSTAT_CUDA_FILE_SAMTOOLS 0x100
 int FLAGSTAT_cuda_file_u64(const char* path, int format, uint64_t* flags, uint64_t* n_records);
 /* the same for a container already in host memory */
 int FLAGSTAT_cuda_container_u64(const void* bytes, uint64_t n_bytes, int format, uint64_t* flags,
@@ -194,6 +235,9 @@ int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs /* [world], by rank
  * handle's. */
 int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
                                    uint64_t* d_flags, int accumulate, void* stream);
+int FLAGSTAT_cuda_samtools_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array,
+                                            uint64_t len, uint64_t* d_flags, int accumulate,
+                                            void* stream);
 int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
                                     uint64_t* d_out /*[16]*/, int accumulate, void* stream);
 /* Peers that never show up: the kernel gives up after the timeout (default 20 s),
@@ -216,7 +260,7 @@ int FLAGSTAT_cuda_set_variant(int variant);
  * initial value. */
 int FLAGSTAT_cuda_set_lz4_variant(int variant);
 /* Name of the kernel instantiation the selected variant launches (as ncu prints it);
- * mode 0 = flagstat, 1 = pospopcnt. */
+ * mode 0 = flagstat, 1 = pospopcnt, 2 = samtools. */
 const char* FLAGSTAT_cuda_kernel_name(int mode);
 /* Persistent-grid size override: CTAs per SM (0 = default). */
 int FLAGSTAT_cuda_set_ctas_per_sm(int n);
@@ -239,7 +283,8 @@ int FLAGSTAT_cuda_memcpy_d2h(void* h, const void* d, size_t bytes);
 int FLAGSTAT_cuda_memset(void* d, int value, size_t bytes);
 int FLAGSTAT_cuda_sync(void);
 /* Times `iters` back-to-back device-resident launches with CUDA events on an
- * internal stream; returns 0 and the mean milliseconds per launch. */
+ * internal stream; returns 0 and the mean milliseconds per launch. pospopcnt_mode: 0 = flagstat,
+ * 1 = pospopcnt, 2 = samtools mode. */
 int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
                               int pospopcnt_mode, float* ms_per_launch);
 /* Read-only HBM probe over device memory (16-byte aligned): LDG.128 + one XOR per 16

@@ -10,6 +10,9 @@ missing or no GPU is present, calls raise.
 Beyond the reference surface:
   flagstat_u64 / flagstat_u32   counters as arrays (the FLAGSTAT_* contract)
   pospopcnt_u16                 raw 16-counter mode (STORM_pospopcnt_u16)
+  flagstat_samtools_u64 / samtools_stats / samtools_text
+                                the reference benchmark's flagstat_loop caller:
+                                bam_flagstat_t with the exact n_pair_all and its report
   flagstat_device               async, device-resident (torch CUDA tensors or
                                 anything with __cuda_array_interface__)
   BlockStream                   pinned ring for 1,024,000-byte block streaming
@@ -142,11 +145,12 @@ def pospopcnt_u16(values) -> np.ndarray:
     return out
 
 
-def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False):
+def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False, samtools: bool = False):
     """Asynchronous, device-resident form (FLAGSTAT_cuda_device /
-    POSPOPCNT_cuda_device).  ``values``: torch CUDA tensor of 16-bit integers.
-    ``out``: torch.int64[32] (or [16]) CUDA tensor that is ACCUMULATED into;
-    allocated zeroed if omitted.  Returns ``out`` without synchronising."""
+    POSPOPCNT_cuda_device / FLAGSTAT_cuda_samtools_device).  ``values``: torch CUDA
+    tensor of 16-bit integers.  ``out``: torch.int64[32] (or [16]) CUDA tensor that is
+    ACCUMULATED into; allocated zeroed if omitted.  Returns ``out`` without
+    synchronising.  ``samtools``: also the exact n_pair_all in slots 0 / 16."""
     import torch
 
     ptr, n, _keep = _device_view(values)
@@ -157,7 +161,10 @@ def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False):
         raise ValueError(f"out must be a CUDA int64[{nout}] tensor")
     if stream is None:
         stream = torch.cuda.current_stream(values.device)
-    fn = lib().POSPOPCNT_cuda_device if pospopcnt else lib().FLAGSTAT_cuda_device
+    if pospopcnt and samtools:
+        raise ValueError("pospopcnt and samtools are different modes")
+    fn = (lib().POSPOPCNT_cuda_device if pospopcnt
+          else lib().FLAGSTAT_cuda_samtools_device if samtools else lib().FLAGSTAT_cuda_device)
     with torch.cuda.device(values.device):
         check(fn(ptr, n, out.data_ptr(), _stream_ptr(stream)), "FLAGSTAT_cuda_device")
     return out
@@ -191,10 +198,73 @@ def flagstats(values) -> dict:
     return counters_to_dict(flags, n)
 
 
+SAMTOOLS_FIELDS = ("n_reads", "n_mapped", "n_pair_all", "n_pair_map", "n_pair_good", "n_sgltn",
+                   "n_read1", "n_read2", "n_dup", "n_diffchr", "n_diffhigh", "n_secondary", "n_supp")
+"""bam_flagstat_t in declaration order (benchmark/flagstats.cpp:43-49); each [QC-pass, QC-fail]."""
+
+
+def flagstat_samtools_u64(values, flags: Optional[np.ndarray] = None) -> np.ndarray:
+    """FLAGSTAT_cuda_samtools_u64: flagstat_u64 plus the exact 'paired in sequencing' count
+    (n_pair_all, benchmark/flagstats.cpp:58-59) in slots 0 / 16.  Accumulates."""
+    f = np.zeros(32, np.uint64) if flags is None else flags
+    if f.dtype != np.uint64 or f.size != 32 or not f.flags["C_CONTIGUOUS"]:
+        raise ValueError("flags must be a contiguous uint64[32]")
+    if _is_device_array(values):
+        ptr, n, _keep = _device_view(values)
+    else:
+        values = _host_u16(values)
+        ptr, n = values.ctypes.data, values.size
+    check(lib().FLAGSTAT_cuda_samtools_u64(ptr, n, f.ctypes.data_as(_capi.u64p)),
+          "FLAGSTAT_cuda_samtools_u64")
+    return f
+
+
+def samtools_stats(values, stats: Optional[np.ndarray] = None) -> np.ndarray:
+    """FLAGSTAT_cuda_samtools: the reference benchmark's flagstat_loop
+    (benchmark/flagstats.cpp:51-71) over a host or device column.  Returns (and adds to)
+    a bam_flagstat_t as int64[13, 2], rows in SAMTOOLS_FIELDS order."""
+    s = np.zeros((13, 2), np.int64) if stats is None else stats
+    if s.dtype != np.int64 or s.shape != (13, 2) or not s.flags["C_CONTIGUOUS"]:
+        raise ValueError("stats must be a contiguous int64[13, 2]")
+    if _is_device_array(values):
+        ptr, n, _keep = _device_view(values)
+    else:
+        values = _host_u16(values)
+        ptr, n = values.ctypes.data, values.size
+    check(lib().FLAGSTAT_cuda_samtools(ptr, n, s.ctypes.data), "FLAGSTAT_cuda_samtools")
+    return s
+
+
+def samtools_stats_from_counters(flags) -> np.ndarray:
+    """bam_flagstat_t (int64[13, 2]) from 32 counters of a *_samtools entry."""
+    f = np.ascontiguousarray(np.asarray(flags), dtype=np.uint64)
+    if f.size != 32:
+        raise ValueError("flags must hold 32 counters")
+    s = np.zeros((13, 2), np.int64)
+    check(lib().FLAGSTAT_cuda_samtools_from_counters(f.ctypes.data_as(_capi.u64p), s.ctypes.data),
+          "FLAGSTAT_cuda_samtools_from_counters")
+    return s
+
+
+def samtools_text(stats) -> str:
+    """FLAGSTAT_cuda_samtools_report: the report of benchmark/flagstats.cpp:577-588, byte
+    for byte, from a bam_flagstat_t (int64[13, 2])."""
+    s = np.ascontiguousarray(np.asarray(stats), dtype=np.int64)
+    if s.size != 26:
+        raise ValueError("stats must be an int64[13, 2] bam_flagstat_t")
+    buf = C.create_string_buffer(2048)
+    n = lib().FLAGSTAT_cuda_samtools_report(s.ctypes.data, buf, len(buf))
+    if n < 0:
+        raise FlagstatCudaError(n, "FLAGSTAT_cuda_samtools_report")
+    return buf.value.decode()
+
+
 def samtools_report(flags) -> str:
-    """Text report in samtools-flagstat order from the 32 counters
-    (cf. benchmark/flagstats.cpp:577-588).  'paired in sequencing' uses the
-    wrapper's READ1+READ2 approximation (python/libflagstats.pyx:35)."""
+    """Text report in samtools-flagstat order from the 32 counters of the plain
+    FLAGSTAT_* contract (cf. benchmark/flagstats.cpp:577-588).  'paired in sequencing'
+    uses the wrapper's READ1+READ2 approximation (python/libflagstats.pyx:35); use
+    samtools_stats + samtools_text for the exact count and the reference's own
+    formatting."""
     f = [int(x) for x in np.asarray(flags)]
     p, q = f[:16], f[16:]
 

@@ -24,6 +24,13 @@ SIGNATURES = {
     "FLAGSTAT_cuda_available": (C.c_int, []),
     "FLAGSTAT_cuda_min_len": (C.c_uint32, []),
     "FLAGSTAT_cuda_set_min_len": (None, [C.c_uint32]),
+    "FLAGSTAT_cuda_samtools_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
+    "FLAGSTAT_cuda_samtools_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "FLAGSTAT_cuda_samtools": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "FLAGSTAT_cuda_samtools_from_counters": (C.c_int, [u64p, C.c_void_p]),
+    "FLAGSTAT_cuda_samtools_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "FLAGSTAT_cuda_samtools_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                          C.c_int, C.c_void_p]),
     "POSPOPCNT_cuda_u16": (C.c_int, [C.c_void_p, C.c_size_t, u32p]),
     "POSPOPCNT_cuda_u16_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
     "POSPOPCNT_cuda_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

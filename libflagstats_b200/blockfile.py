@@ -22,6 +22,9 @@ from . import _capi
 from ._capi import check, lib
 
 RAW, LZ4 = 0, 1
+SAMTOOLS = 0x100
+"""OR into the format: count like FLAGSTAT_cuda_samtools_u64 (flags[0] / flags[16] = the exact
+n_pair_all) -- the reference's 'samtools' readers of the same files (flagstats.cpp:496-519, 547-590)."""
 _EXT = {".bin": RAW, ".raw": RAW, ".lz4": LZ4}
 
 
@@ -41,24 +44,25 @@ def _flags(flags: Optional[np.ndarray]) -> np.ndarray:
     return f
 
 
-def flagstat_file(path: str, fmt: Optional[int] = None,
-                  flags: Optional[np.ndarray] = None) -> Tuple[np.ndarray, int]:
+def flagstat_file(path: str, fmt: Optional[int] = None, flags: Optional[np.ndarray] = None,
+                  samtools: bool = False) -> Tuple[np.ndarray, int]:
     """Accumulate the counters of a FLAG file into ``flags``; returns (flags, n_records)."""
     f = _flags(flags)
     n = C.c_uint64(0)
-    check(lib().FLAGSTAT_cuda_file_u64(os.fsencode(path), _format_of(path, fmt),
+    check(lib().FLAGSTAT_cuda_file_u64(os.fsencode(path), _format_of(path, fmt) | (SAMTOOLS if samtools else 0),
                                        f.ctypes.data_as(_capi.u64p), C.byref(n)),
           "FLAGSTAT_cuda_file_u64")
     return f, int(n.value)
 
 
-def flagstat_container(blob, fmt: int, flags: Optional[np.ndarray] = None) -> Tuple[np.ndarray, int]:
+def flagstat_container(blob, fmt: int, flags: Optional[np.ndarray] = None,
+                       samtools: bool = False) -> Tuple[np.ndarray, int]:
     """Same for a container held in host memory (bytes-like or uint8 array)."""
     f = _flags(flags)
     buf = np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
     n = C.c_uint64(0)
-    check(lib().FLAGSTAT_cuda_container_u64(buf.ctypes.data, buf.size, int(fmt),
+    check(lib().FLAGSTAT_cuda_container_u64(buf.ctypes.data, buf.size, int(fmt) | (SAMTOOLS if samtools else 0),
                                             f.ctypes.data_as(_capi.u64p), C.byref(n)),
           "FLAGSTAT_cuda_container_u64")
     return f, int(n.value)

@@ -190,7 +190,7 @@ int lz4_lane_retire(Lz4Lane& l)
     return 0;
 }
 
-int lz4_lane_ship(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even, uint64_t* d_flags)
+int lz4_lane_ship(int mode, Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even, uint64_t* d_flags)
 {
     if (l.n == 0) return 0;
     CK(cudaMemcpyAsync(l.d_comp, l.h_comp, comp_bytes, cudaMemcpyHostToDevice, l.st));
@@ -214,11 +214,11 @@ int lz4_lane_ship(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even
         cudaEventDestroy(e1);
     }
     if (all_even) {  // the decoded blocks are one contiguous run of whole records
-        rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw), raw_bytes / 2, d_flags, l.st);
+        rc = launch(mode, reinterpret_cast<const uint16_t*>(l.d_raw), raw_bytes / 2, d_flags, l.st);
         if (rc) return rc;
     } else {         // a block with an odd byte count: the reference drops that byte (N = size >> 1)
         for (int b = 0; b < l.n; ++b) {
-            rc = launch(kFlagstat, reinterpret_cast<const uint16_t*>(l.d_raw + l.h_desc[b].raw_off),
+            rc = launch(mode, reinterpret_cast<const uint16_t*>(l.d_raw + l.h_desc[b].raw_off),
                         l.h_desc[b].raw_size / 2, d_flags, l.st);
             if (rc) return rc;
         }
@@ -285,7 +285,7 @@ int lz4_index(ByteSource& src, int fd, uint64_t total, std::vector<BlockInfo>& i
     return 0;
 }
 
-int consume_lz4(ByteSource& src, uint64_t* totals, uint64_t* n_records)
+int consume_lz4(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records)
 {
     int fd = -1;
     uint64_t total = src.size;
@@ -377,7 +377,7 @@ int consume_lz4(ByteSource& src, uint64_t* totals, uint64_t* n_records)
             }
         }
         if (err.load()) return err.load();
-        rc = lz4_lane_ship(l, c, r, all_even, d_flags);
+        rc = lz4_lane_ship(mode, l, c, r, all_even, d_flags);
         if (rc) return rc;
         cur ^= 1;
         first = last;
@@ -505,10 +505,10 @@ int consume_staged(int mode, uint64_t size, size_t slot_bytes, Fill fill, uint64
     return 0;
 }
 
-int consume_raw_fd(int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
+int consume_raw_fd(int mode, int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
 {
     const int rc = consume_staged(
-        kFlagstat, size, kRawSlotBytes,
+        mode, size, kRawSlotBytes,
         [fd](unsigned char* h, uint64_t off, size_t len) {
             size_t got = 0;
             while (got < len) {
@@ -546,17 +546,17 @@ int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals
         totals);
 }
 
-int consume_raw(ByteSource& src, uint64_t* totals, uint64_t* n_records)
+int consume_raw(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records)
 {
     if (src.fp) {
         struct stat sb;
         const int fd = ::fileno(src.fp);
         if (fd < 0 || ::fstat(fd, &sb) != 0) return FLAGSTAT_CUDA_EIO;
-        return consume_raw_fd(fd, (uint64_t)sb.st_size, totals, n_records);
+        return consume_raw_fd(mode, fd, (uint64_t)sb.st_size, totals, n_records);
     }
     // already in host memory: the host-pointer path of FLAGSTAT_cuda_u64 (chunked, overlapped staging)
     *n_records = src.size >> 1;
-    return run_sync(kFlagstat, reinterpret_cast<const uint16_t*>(src.mem), src.size >> 1, totals);
+    return run_sync(mode, reinterpret_cast<const uint16_t*>(src.mem), src.size >> 1, totals);
 }
 
 int consume(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
@@ -565,8 +565,12 @@ int consume(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     uint64_t t[32] = {0}, n = 0;
     int rc;
-    if (format == FLAGSTAT_CUDA_FILE_RAW) rc = consume_raw(src, t, &n);
-    else if (format == FLAGSTAT_CUDA_FILE_LZ4) rc = consume_lz4(src, t, &n);
+    // _SAMTOOLS: the reference's "samtools" callers of the same files (flagstat_loop over every
+    // block, benchmark/flagstats.cpp:496-519 raw, :547-590 LZ4): counters + exact n_pair_all
+    const int mode = (format & FLAGSTAT_CUDA_FILE_SAMTOOLS) ? kSamtools : kFlagstat;
+    format &= ~FLAGSTAT_CUDA_FILE_SAMTOOLS;
+    if (format == FLAGSTAT_CUDA_FILE_RAW) rc = consume_raw(mode, src, t, &n);
+    else if (format == FLAGSTAT_CUDA_FILE_LZ4) rc = consume_lz4(mode, src, t, &n);
     else return FLAGSTAT_CUDA_EINVAL;
     if (rc) return rc;
     for (int i = 0; i < 32; ++i) flags[i] += t[i];

@@ -97,9 +97,16 @@ const KernelCfg kKernels[kNumVariants] = {
      kThreads, (size_t)4 * kStageBytes},
 };
 
+// kSamtools (exact n_pair_all in slots 0 / 16) has one instantiation whatever variant is
+// selected: the group kernel with the FMA-pipe mask forms (flagstat_kernels.cuh: mask_select_fx)
+const KernelCfg kSamtoolsKernel = {
+    {flagstat_kernel_group<kSamtools, 3, 2>, flagstat_kernel_group<kSamtools, 3, 2>},
+    kThreads, (size_t)4 * kStageBytes};
+
 struct DeviceInfo {
     int sms = 0;
     int occ[kNumVariants][2];  // resident CTAs per SM
+    int occ_samtools = 2;
     bool ok = false;
 };
 
@@ -148,6 +155,18 @@ int device_info(int dev, DeviceInfo** out)
                 }
                 d.occ[v][m] = nb < 1 ? 1 : nb;
             }
+        {
+            const KernelCfg& k = kSamtoolsKernel;
+            CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(k.fn[0]),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &nb, reinterpret_cast<const void*>(k.fn[0]), k.threads, k.smem) != cudaSuccess) {
+                cudaGetLastError();
+                nb = 2;
+            }
+            d.occ_samtools = nb < 1 ? 1 : nb;
+        }
         if (cur != dev && cur >= 0) CK(cudaSetDevice(cur));
         d.ok = true;
     }
@@ -172,20 +191,22 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
         g_variant.store(variant);
     }
     if (variant < 0 || variant >= kNumVariants) variant = 0;
-    const KernelCfg& k = kKernels[variant];
+    const bool sam = mode == kSamtools;
+    const KernelCfg& k = sam ? kSamtoolsKernel : kKernels[variant];
+    const KernelFn fn = sam ? k.fn[0] : k.fn[mode];
 
     const uint64_t addr = reinterpret_cast<uintptr_t>(d_array);
     uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
     if (head > n) head = n;
     const uint64_t nb = ((n - head) >> 3) / kVecPerBatch;
     int per_sm = g_ctas_per_sm.load();
-    if (per_sm <= 0) per_sm = di->occ[variant][mode];
+    if (per_sm <= 0) per_sm = sam ? di->occ_samtools : di->occ[variant][mode];
     uint64_t grid = (uint64_t)per_sm * (uint64_t)di->sms;
     if (grid > nb + 1) grid = nb + 1;
 
     XchgArgs none;
     std::memset(&none, 0, sizeof(none));
-    k.fn[mode]<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
+    fn<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
         d_array, n, reinterpret_cast<unsigned long long*>(d_out), xa ? *xa : none);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
@@ -459,6 +480,95 @@ int FLAGSTAT_cuda_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flag
     if (!d_flags || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     return launch(kFlagstat, d_array, len, d_flags, static_cast<cudaStream_t>(stream));
+}
+
+// ---- samtools mode: counters + exact n_pair_all (benchmark/flagstats.cpp:43-71) ----
+
+int FLAGSTAT_cuda_samtools_u64(const uint16_t* array, uint64_t len, uint64_t* flags)
+{
+    if (!flags) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[32];
+    const int rc = run_sync(kSamtools, array, len, t);
+    if (rc) return rc;
+    for (int i = 0; i < 32; ++i) flags[i] += t[i];
+    return 0;
+}
+
+int FLAGSTAT_cuda_samtools_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, void* stream)
+{
+    if (!d_flags || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    return launch(kSamtools, d_array, len, d_flags, static_cast<cudaStream_t>(stream));
+}
+
+int FLAGSTAT_cuda_samtools_from_counters(const uint64_t* flags, FLAGSTAT_cuda_bam_flagstat* s)
+{
+    if (!flags || !s) return FLAGSTAT_CUDA_EINVAL;
+    for (int w = 0; w < 2; ++w) {
+        const uint64_t* f = flags + 16 * w;
+        const uint64_t total = flags[w ? 25 : 9];
+        s->n_reads[w] += (long long)total;
+        s->n_mapped[w] += (long long)(total - f[2]);
+        s->n_pair_all[w] += (long long)f[0];
+        s->n_pair_map[w] += (long long)f[14];
+        s->n_pair_good[w] += (long long)f[12];
+        s->n_sgltn[w] += (long long)f[13];
+        s->n_read1[w] += (long long)f[6];
+        s->n_read2[w] += (long long)f[7];
+        s->n_dup[w] += (long long)f[10];
+        s->n_secondary[w] += (long long)f[8];
+        s->n_supp[w] += (long long)f[11];
+    }
+    return 0;
+}
+
+int FLAGSTAT_cuda_samtools(const uint16_t* array, uint64_t len, FLAGSTAT_cuda_bam_flagstat* s)
+{
+    if (!s) return FLAGSTAT_CUDA_EINVAL;
+    uint64_t t[32];
+    const int rc = run_sync(kSamtools, array, len, t);
+    if (rc) return rc;
+    return FLAGSTAT_cuda_samtools_from_counters(t, s);
+}
+
+int FLAGSTAT_cuda_samtools_report(const FLAGSTAT_cuda_bam_flagstat* s, char* buf, size_t capacity)
+{
+    if (!s || (!buf && capacity)) return FLAGSTAT_CUDA_EINVAL;
+    // percent(), benchmark/flagstats.cpp:73-78: float division, then * 100.0 in double
+    char b0[32], b1[32];
+    auto pct = [](char* b, long long n, long long total) -> const char* {
+        if (total != 0) std::snprintf(b, 32, "%.2f%%", (float)n / total * 100.0);
+        else std::strcpy(b, "N/A");
+        return b;
+    };
+    std::string o;
+    char line[160];
+    auto put = [&](const char* fmt, long long a, long long b) {
+        std::snprintf(line, sizeof line, fmt, a, b);
+        o += line;
+    };
+    auto put_pct = [&](const char* fmt, const long long* v, const long long* tot) {
+        std::snprintf(line, sizeof line, fmt, v[0], v[1], pct(b0, v[0], tot[0]), pct(b1, v[1], tot[1]));
+        o += line;
+    };
+    // the lines of benchmark/flagstats.cpp:577-588 (the two diffchr lines are commented out there)
+    put("%lld + %lld in total (QC-passed reads + QC-failed reads)\n", s->n_reads[0], s->n_reads[1]);
+    put("%lld + %lld secondary\n", s->n_secondary[0], s->n_secondary[1]);
+    put("%lld + %lld supplementary\n", s->n_supp[0], s->n_supp[1]);
+    put("%lld + %lld duplicates\n", s->n_dup[0], s->n_dup[1]);
+    put_pct("%lld + %lld mapped (%s : %s)\n", s->n_mapped, s->n_reads);
+    put("%lld + %lld paired in sequencing\n", s->n_pair_all[0], s->n_pair_all[1]);
+    put("%lld + %lld read1\n", s->n_read1[0], s->n_read1[1]);
+    put("%lld + %lld read2\n", s->n_read2[0], s->n_read2[1]);
+    put_pct("%lld + %lld properly paired (%s : %s)\n", s->n_pair_good, s->n_pair_all);
+    put("%lld + %lld with itself and mate mapped\n", s->n_pair_map[0], s->n_pair_map[1]);
+    put_pct("%lld + %lld singletons (%s : %s)\n", s->n_sgltn, s->n_pair_all);
+    if (capacity) {
+        const size_t n = o.size() < capacity - 1 ? o.size() : capacity - 1;
+        std::memcpy(buf, o.data(), n);
+        buf[n] = '\0';
+    }
+    return (int)o.size();
 }
 
 int POSPOPCNT_cuda_u16_u64(const uint16_t* data, uint64_t len, uint64_t* out)
@@ -757,6 +867,12 @@ int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_arra
     return xchg_launch(x, kFlagstat, d_array, len, d_flags, accumulate, stream);
 }
 
+int FLAGSTAT_cuda_samtools_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
+                                            uint64_t* d_flags, int accumulate, void* stream)
+{
+    return xchg_launch(x, kSamtools, d_array, len, d_flags, accumulate, stream);
+}
+
 int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
                                     uint64_t* d_out, int accumulate, void* stream)
 {
@@ -839,13 +955,14 @@ const char* FLAGSTAT_cuda_kernel_name(int mode)
         {"fsb200::flagstat_kernel_ring<0, 2, 4, 2>", "fsb200::flagstat_kernel_ring<1, 0, 4, 2>"},
         {"fsb200::flagstat_kernel_group<0, 0, 2>", "fsb200::flagstat_kernel_group<1, 0, 2>"},
     };
-    static_assert(kFlagstat == 0 && kPospopcnt == 1, "names above spell the MODE template argument");
+    static_assert(kFlagstat == 0 && kPospopcnt == 1 && kSamtools == 2, "names above spell the MODE template argument");
     int v = g_variant.load();
     if (v == -1) {
         v = 0;
         if (const char* e = std::getenv("FLAGSTAT_CUDA_VARIANT")) v = std::atoi(e);
     }
     if (v < 0 || v >= kNumVariants) v = 0;
+    if (mode == kSamtools) return "fsb200::flagstat_kernel_group<2, 3, 2>";
     return kNames[v][mode == kPospopcnt ? 1 : 0];
 }
 
@@ -934,7 +1051,7 @@ int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters && rc == 0; ++i)
-        rc = launch(pospopcnt_mode ? kPospopcnt : kFlagstat, d_array, len, d_flags, st);
+        rc = launch(pospopcnt_mode == 2 ? kSamtools : pospopcnt_mode ? kPospopcnt : kFlagstat, d_array, len, d_flags, st);
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;

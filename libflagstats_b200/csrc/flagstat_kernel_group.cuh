@@ -172,7 +172,7 @@ struct GroupLanes {
     __device__ __forceinline__ void clear()
     {
         all.clear();
-        if (MODE == kFlagstat) fail.clear();
+        if (MODE != kPospopcnt) fail.clear();
         fail_open = false;
         fail_dirty = false;
     }
@@ -200,7 +200,17 @@ struct GroupLanes {
         const bool has_fail = (wany & 0x02000200u) != 0u;  // a QC-fail record
 
         uint32_t y[16];
-        if (VARIANT == 1) {
+        if (MODE == kSamtools) {
+            // position 4 must be the clean class-K indicator on every path
+            static_assert(MODE != kSamtools || VARIANT == 3, "kSamtools builds on the FMA-pipe forms");
+            if (has_sec) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] = mask_select_fx<true>(w[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] = mask_select_fx<false>(w[i]);
+            }
+        } else if (VARIANT == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] = mask_select_i(w[i]);
         } else if (VARIANT == 3 && (has_sec || has_fail)) {
@@ -233,7 +243,7 @@ struct GroupLanes {
     __device__ __forceinline__ void close()
     {
         all.close();
-        if (MODE == kFlagstat && fail_open) {
+        if (MODE != kPospopcnt && fail_open) {
             fail.close();
             fail_open = false;
         }
@@ -379,7 +389,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
             rem_done = true;
         }
         acc_all += st.all.flush_warp(lane);
-        if (MODE == kFlagstat && st.fail_dirty) acc_fail += st.fail.flush_warp(lane);
+        if (MODE != kPospopcnt && st.fail_dirty) acc_fail += st.fail.flush_warp(lane);
         st.clear();
         groups = 0;
     } while (g < ngroups || !rem_done);

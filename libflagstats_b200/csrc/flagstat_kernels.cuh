@@ -45,7 +45,9 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kU = 4;                      // 128-bit loads per thread per batch
 constexpr int kVecPerBatch = kThreads * kU;  // uint4 per CTA batch (16 KiB)
 
-enum Mode { kFlagstat = 0, kPospopcnt = 1 };
+// kSamtools = kFlagstat plus the exact "paired in sequencing" count (n_pair_all of the
+// reference benchmark's flagstat_loop, benchmark/flagstats.cpp:58-59) in slots 0 / 16.
+enum Mode { kFlagstat = 0, kPospopcnt = 1, kSamtools = 2 };
 
 // ---------------------------------------------------------------------------
 // mask select
@@ -185,6 +187,30 @@ __device__ __forceinline__ uint32_t mask_select_f(uint32_t w)
     return w & k;
 }
 
+// kSamtools form of the above: position 4 becomes the indicator of class K (paired,
+// primary) = one count of n_pair_all per record (benchmark/flagstats.cpp:58-59).  The
+// class constants gain bit 4 (0xD0 / 0xDB ulp: 0x0FD4 / 0x0FDF, still < 2048 ulp, so
+// still exact) and the final AND sees the input with bit 4 forced on:
+//     y = k & (w | 0x0010)        one LOP3 (0xE0), like the plain AND it replaces
+// so K records carry a 1 at position 4 whatever their REVERSE bit says and all other
+// records (k = 0x0F04 / 0x0704) a 0.  Same instruction count as mask_select_f.
+template <bool HAS_SEC>
+__device__ __forceinline__ uint32_t mask_select_fx(uint32_t w)
+{
+    const uint32_t q = w & 0x09050905u;
+    uint32_t g1, x1, k;
+    asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(g1) : "r"(q), "r"(0x00010001u));
+    asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(x1) : "r"(q), "r"(0x00050005u));
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(x1), "r"(0x03400340u), "r"(0x0F040F04u));
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(g1), "r"(0x036C036Cu), "r"(k));
+    if (HAS_SEC) {  // SUPPLEMENTARY does not count for SECONDARY records (see mask_select_f)
+        uint32_t z;
+        asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(z) : "r"(q), "r"(0x7A007A00u), "r"(0xC608C608u));
+        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(k) : "r"(z), "r"(0x8D438D43u), "r"(k));
+    }
+    return lop3<0xE0>(k, w, 0x00100010u);  // k & (w | 0x0010)
+}
+
 // QC-fail gating of a variant-F word without an integer mask: bit 9 of the record,
 // read as fp16, is the subnormal 2^-15; times 2^15 it is 1.0 or 0.0, and y * 1.0
 // is y exactly (y <= 0x0FCF is a finite non-negative fp16 -- this needs the CLEAN
@@ -321,8 +347,10 @@ __device__ __forceinline__ void load_batch(uint4 (&v)[kU], const uint4* p)
 }
 
 // position (within a 16-bit record) -> primary output slot, -1 = not a counter
+template <int MODE>
 __device__ __forceinline__ int slot_of_position(int p)
 {
+    if (MODE == kSamtools && p == 4) return 0;  // K -> n_pair_all
     switch (p) {
         case 0: return 14;  // G; position 3 is subtracted below
         case 1: return 12;
@@ -351,7 +379,7 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
         if (a) atomicAdd(out + lane, a);
         return;
     }
-    const int slot = slot_of_position((int)lane);
+    const int slot = slot_of_position<MODE>((int)lane);
     if (slot >= 0) {
         if (a - f) atomicAdd(out + slot, a - f);
         if (f) atomicAdd(out + 16 + slot, f);

@@ -55,13 +55,13 @@ def allreduce_counters(counters, group=None):
     return counters
 
 
-def flagstat_sharded(local_values, out=None, group=None, stream=None):
+def flagstat_sharded(local_values, out=None, group=None, stream=None, samtools: bool = False):
     """Each rank passes its own shard (a CUDA tensor of 16-bit FLAG words already
     resident in its GPU's HBM).  Returns the int64[32] CUDA tensor holding the
     GLOBAL counters on every rank.  Asynchronous with respect to the host."""
     from . import flagstat_device
 
-    out = flagstat_device(local_values, out=out, stream=stream)
+    out = flagstat_device(local_values, out=out, stream=stream, samtools=samtools)
     return allreduce_counters(out, group=group)
 
 
@@ -111,10 +111,12 @@ class FusedExchange:
                   "FLAGSTAT_cuda_xchg_set_timeout_ms")
 
     def flagstat(self, local_values, out=None, accumulate: bool = False, stream=None,
-                 pospopcnt: bool = False):
+                 pospopcnt: bool = False, samtools: bool = False):
         """Count this rank's shard and return the GLOBAL counters in `out`
         (int64[32] CUDA tensor, or [16] for pospopcnt) on every rank.  One
-        kernel launch; asynchronous with respect to the host.  Collective."""
+        kernel launch; asynchronous with respect to the host.  Collective.
+        ``samtools``: also the exact n_pair_all in slots 0 / 16
+        (FLAGSTAT_cuda_samtools_device_allreduce)."""
         import torch
 
         from . import _device_view, _stream_ptr
@@ -127,7 +129,10 @@ class FusedExchange:
             raise ValueError(f"out must be a CUDA int64[{nout}] tensor")
         if stream is None:
             stream = torch.cuda.current_stream(local_values.device)
+        if pospopcnt and samtools:
+            raise ValueError("pospopcnt and samtools are different modes")
         fn = (self._lib.POSPOPCNT_cuda_device_allreduce if pospopcnt
+              else self._lib.FLAGSTAT_cuda_samtools_device_allreduce if samtools
               else self._lib.FLAGSTAT_cuda_device_allreduce)
         with torch.cuda.device(local_values.device):
             self._check(fn(self._h, ptr, n, out.data_ptr(), 1 if accumulate else 0,

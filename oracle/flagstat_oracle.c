@@ -149,6 +149,44 @@ int oracle_flagstat_maskselect_u64(const uint16_t* a, uint64_t n, uint64_t* flag
 }
 
 /*
+ * The reference benchmark's samtools-style accumulator: bam_flagstat_t
+ * (benchmark/flagstats.cpp:43-49) filled by flagstat_loop (:51-71), the caller
+ * that prints the report (:577-588).  s[] is that struct seen as 13 pairs of
+ * long long, [pass, fail] each, in declaration order:
+ *   0 n_reads  1 n_mapped  2 n_pair_all  3 n_pair_map  4 n_pair_good  5 n_sgltn
+ *   6 n_read1  7 n_read2   8 n_dup  9 n_diffchr  10 n_diffhigh  11 n_secondary
+ *   12 n_supp
+ * n_diffchr / n_diffhigh need RNAME / MAPQ and are never written (:577-588 has
+ * them commented out).  Accumulates.
+ */
+enum { S_READS = 0, S_MAPPED, S_PAIR_ALL, S_PAIR_MAP, S_PAIR_GOOD, S_SGLTN, S_READ1, S_READ2,
+       S_DUP, S_DIFFCHR, S_DIFFHIGH, S_SECONDARY, S_SUPP, S_FIELDS };
+
+int oracle_samtools_loop(const uint16_t* a, uint64_t n, long long* s)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t c = a[i];
+        const int w = BIT(c, B_QCFAIL) ? 1 : 0;                               /* :52 */
+        s[2 * S_READS + w] += 1;                                             /* :53 */
+        if (BIT(c, B_SECONDARY)) {                                           /* :54 */
+            s[2 * S_SECONDARY + w] += 1;
+        } else if (BIT(c, B_SUPP)) {                                         /* :56 */
+            s[2 * S_SUPP + w] += 1;
+        } else if (BIT(c, B_PAIRED)) {                                       /* :58 */
+            s[2 * S_PAIR_ALL + w] += 1;                                      /* :59 */
+            if (BIT(c, B_PROPER) && !BIT(c, B_UNMAP)) s[2 * S_PAIR_GOOD + w] += 1;   /* :60 */
+            if (BIT(c, B_READ1)) s[2 * S_READ1 + w] += 1;                    /* :61 */
+            if (BIT(c, B_READ2)) s[2 * S_READ2 + w] += 1;                    /* :62 */
+            if (BIT(c, B_MUNMAP) && !BIT(c, B_UNMAP)) s[2 * S_SGLTN + w] += 1;       /* :63 */
+            if (!BIT(c, B_UNMAP) && !BIT(c, B_MUNMAP)) s[2 * S_PAIR_MAP + w] += 1;   /* :64-66 */
+        }
+        if (!BIT(c, B_UNMAP)) s[2 * S_MAPPED + w] += 1;                      /* :68 */
+        if (BIT(c, B_DUP)) s[2 * S_DUP + w] += 1;                            /* :69 */
+    }
+    return 0;
+}
+
+/*
  * Raw positional popcount: zero out[0..15], then out[j] = #records with bit j
  * set (libalgebra.h:3497-3498 memset, :565-574 naive kernel).  64-bit variant
  * for lengths whose counts exceed 2^32.

@@ -76,6 +76,8 @@ def oracle():
             f = getattr(lib, name)
             f.argtypes = [_u16p, C.c_uint32, _u32p]
             f.restype = C.c_int
+        lib.oracle_samtools_loop.argtypes = [_u16p, C.c_uint64, C.POINTER(C.c_longlong)]
+        lib.oracle_samtools_loop.restype = C.c_int
         lib.oracle_mask_select.argtypes = [C.c_uint16]
         lib.oracle_mask_select.restype = C.c_uint16
         lib.oracle_pospopcnt_u16_u64.argtypes = [_u16p, C.c_uint64, _u64p]
@@ -126,6 +128,72 @@ def flagstat_maskselect(a) -> np.ndarray:
 
 def mask_select(v: int) -> int:
     return int(oracle().oracle_mask_select(int(v) & 0xFFFF))
+
+
+SAMTOOLS_FIELDS = ("n_reads", "n_mapped", "n_pair_all", "n_pair_map", "n_pair_good", "n_sgltn",
+                   "n_read1", "n_read2", "n_dup", "n_diffchr", "n_diffhigh", "n_secondary", "n_supp")
+"""bam_flagstat_t in declaration order, benchmark/flagstats.cpp:43-49; each field is [pass, fail]."""
+
+
+def samtools_loop(a, s: Optional[np.ndarray] = None) -> np.ndarray:
+    """flagstat_loop (benchmark/flagstats.cpp:51-71) over a column; int64[13, 2], accumulates."""
+    a = _as_u16(a)
+    s = np.zeros((13, 2), np.int64) if s is None else s
+    oracle().oracle_samtools_loop(_ptr(a, _u16p), a.size, _ptr(s, C.POINTER(C.c_longlong)))
+    return s
+
+
+def samtools_from_counters(flags) -> np.ndarray:
+    """bam_flagstat_t implied by the 32 flagstat counters (SIMD convention) with the exact
+    n_pair_all in slots 0 / 16 -- the identities FLAGSTAT_cuda_samtools relies on."""
+    f = [int(x) for x in np.asarray(flags)]
+    s = np.zeros((13, 2), np.int64)
+    for w in (0, 1):
+        o = 16 * w
+        total = f[9] if w == 0 else f[25]
+        s[0, w] = total
+        s[1, w] = total - f[o + 2]
+        s[2, w] = f[o + 0]
+        s[3, w] = f[o + 14]
+        s[4, w] = f[o + 12]
+        s[5, w] = f[o + 13]
+        s[6, w] = f[o + 6]
+        s[7, w] = f[o + 7]
+        s[8, w] = f[o + 10]
+        s[11, w] = f[o + 8]
+        s[12, w] = f[o + 11]
+    return s
+
+
+def samtools_percent(n: int, total: int) -> str:
+    """percent(), benchmark/flagstats.cpp:73-78: "%.2f%%" of (float)n / total * 100.0."""
+    if total == 0:
+        return "N/A"
+    return "%.2f%%" % (float(np.float32(n) / np.float32(total)) * 100.0)
+
+
+def samtools_report(s) -> str:
+    """The report of benchmark/flagstats.cpp:577-588 (diffchr lines are commented out there)."""
+    s = np.asarray(s).reshape(13, 2)
+    g = {k: (int(s[i, 0]), int(s[i, 1])) for i, k in enumerate(SAMTOOLS_FIELDS)}
+    pc = samtools_percent
+    lines = [
+        "%d + %d in total (QC-passed reads + QC-failed reads)" % g["n_reads"],
+        "%d + %d secondary" % g["n_secondary"],
+        "%d + %d supplementary" % g["n_supp"],
+        "%d + %d duplicates" % g["n_dup"],
+        "%d + %d mapped (%s : %s)" % (g["n_mapped"] + (pc(g["n_mapped"][0], g["n_reads"][0]),
+                                                        pc(g["n_mapped"][1], g["n_reads"][1]))),
+        "%d + %d paired in sequencing" % g["n_pair_all"],
+        "%d + %d read1" % g["n_read1"],
+        "%d + %d read2" % g["n_read2"],
+        "%d + %d properly paired (%s : %s)" % (g["n_pair_good"] + (
+            pc(g["n_pair_good"][0], g["n_pair_all"][0]), pc(g["n_pair_good"][1], g["n_pair_all"][1]))),
+        "%d + %d with itself and mate mapped" % g["n_pair_map"],
+        "%d + %d singletons (%s : %s)" % (g["n_sgltn"] + (
+            pc(g["n_sgltn"][0], g["n_pair_all"][0]), pc(g["n_sgltn"][1], g["n_pair_all"][1]))),
+    ]
+    return "\n".join(lines) + "\n"
 
 
 def pospopcnt(a) -> np.ndarray:
@@ -248,6 +316,11 @@ def reference():
     lib.ref_flagstat_mt.argtypes = [C.c_char_p, _u16p, C.c_uint64, C.c_int, _u64p,
                                     C.POINTER(C.c_double)]
     lib.ref_flagstat_mt.restype = C.c_int
+    if hasattr(lib, "ref_samtools_loop"):
+        lib.ref_samtools_loop.argtypes = [_u16p, C.c_uint64, C.POINTER(C.c_longlong)]
+        lib.ref_samtools_loop.restype = C.c_int
+        lib.ref_samtools_percent.argtypes = [C.c_longlong, C.c_longlong, C.c_char_p]
+        lib.ref_samtools_percent.restype = C.c_int
     lib._path = p
     _ref = lib
     return _ref
@@ -285,6 +358,29 @@ def ref_flagstats_u16(a, flags: Optional[np.ndarray] = None) -> np.ndarray:
     f = np.zeros(32, np.uint32) if flags is None else flags
     lib.ref_FLAGSTATS_u16(_ptr(a, _u16p), a.size, _ptr(f, _u32p))
     return f
+
+
+def ref_samtools_loop(a) -> Optional[np.ndarray]:
+    """The reference's own flagstat_loop macro (benchmark/flagstats.cpp:51-71) compiled into
+    oracle/_ref; None when the prebuilt shim predates it."""
+    lib = reference()
+    if lib is None or not hasattr(lib, "ref_samtools_loop"):
+        return None
+    a = _as_u16(a)
+    s = np.zeros((13, 2), np.int64)
+    if lib.ref_samtools_loop(_ptr(a, _u16p), a.size, _ptr(s, C.POINTER(C.c_longlong))) != 0:
+        return None
+    return s
+
+
+def ref_samtools_percent(n: int, total: int) -> Optional[str]:
+    lib = reference()
+    if lib is None or not hasattr(lib, "ref_samtools_percent"):
+        return None
+    buf = C.create_string_buffer(64)
+    if lib.ref_samtools_percent(n, total, buf) != 0:
+        return None
+    return buf.value.decode()
 
 
 def ref_dispatch_name(n: int) -> str:

@@ -29,6 +29,16 @@
 #include "libalgebra.h"    /* /root/reference/libalgebra/libalgebra.h */
 #include "libflagstats.h"  /* /root/reference/libflagstats.h */
 
+/* The samtools-style caller of the reference benchmark: bam_flagstat_t, the
+ * flagstat_loop macro and percent() (benchmark/flagstats.cpp:43-71,73-78).  That
+ * file cannot be compiled here (it needs lz4.h / zstd.h), so oracle/Makefile cuts
+ * exactly those definitions out of it at build time into a temporary include,
+ * compiles them into this TU unmodified and deletes the temporary again. */
+#ifdef REF_SAMTOOLS_INC
+#include <cstdio>
+#include REF_SAMTOOLS_INC
+#endif
+
 namespace {
 
 struct Entry {
@@ -192,6 +202,34 @@ int ref_flagstat_mt(const char* name, const uint16_t* array, uint64_t len,
     std::free(jobs);
     std::free(th);
     return 0;
+}
+
+/* flagstat_loop over a column into a bam_flagstat_t seen as 26 long long
+ * (benchmark/flagstats.cpp:43-71); accumulates.  -1 when the shim was built
+ * without the benchmark source. */
+int ref_samtools_loop(const uint16_t* array, uint64_t len, long long* s26)
+{
+#ifdef REF_SAMTOOLS_INC
+    static_assert(sizeof(bam_flagstat_t) == 26 * sizeof(long long), "bam_flagstat_t layout");
+    bam_flagstat_t* s = reinterpret_cast<bam_flagstat_t*>(s26);
+    for (uint64_t i = 0; i < len; ++i) flagstat_loop(s, array[i]);
+    return 0;
+#else
+    (void)array; (void)len; (void)s26;
+    return -1;
+#endif
+}
+
+/* percent(), benchmark/flagstats.cpp:73-78; buf >= 16 bytes */
+int ref_samtools_percent(long long n, long long total, char* buf)
+{
+#ifdef REF_SAMTOOLS_INC
+    percent(buf, n, total);
+    return 0;
+#else
+    (void)n; (void)total; (void)buf;
+    return -1;
+#endif
 }
 
 }  /* extern "C" */

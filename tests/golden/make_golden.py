@@ -13,6 +13,8 @@ Every expected vector in the output comes from reference code:
   simd      -> agreed CORE19 + slot 9 of FLAGSTAT_sse4/avx2/avx512 (those the
                host can run), asserted identical before being written
   pospopcnt -> STORM_pospopcnt_u16             (libalgebra.h:3496-3551)
+  samtools  -> flagstat_loop into bam_flagstat_t (benchmark/flagstats.cpp:43-71), the
+               macro itself compiled into oracle/_ref; 13 x [pass, fail]
 """
 import json
 import os
@@ -85,6 +87,14 @@ def reference_answers(a, valid_sam):
         out["dispatch"] = O.ref_flagstats_u16(a).astype(np.uint64).tolist()
         out["dispatch_kernel"] = O.ref_dispatch_name(a.size)
     out["pospopcnt"] = O.ref_pospopcnt(a).astype(np.uint64).tolist()
+    st = O.ref_samtools_loop(a)
+    assert st is not None, "oracle/_ref predates ref_samtools_loop: make -C oracle"
+    # ten of the eleven FLAG-derived fields follow from the counters (any input: the loop
+    # tests bits 0..11 only, like the scalar rule)
+    implied = O.samtools_from_counters(expect)
+    implied[2] = st[2]
+    assert (implied == st).all(), a.size
+    out["samtools"] = st.tolist()
     return out
 
 
@@ -165,8 +175,23 @@ def main():
     pp = np.zeros(16, np.uint64)
     for lo in range(0, N, 1 << 30):
         pp += O.ref_pospopcnt(e[lo:lo + (1 << 30)]).astype(np.uint64)
+    print("flagstat_loop over KAT-E ...", flush=True)
+    st_e = O.ref_samtools_loop(e)
+    assert int(st_e[2, 0]) == readme["paired"] and int(st_e[2, 1]) == 0
+    implied = O.samtools_from_counters(core20_only(fe))
+    implied[2] = st_e[2]
+    assert (implied == st_e).all()
+    report_e = O.samtools_report(st_e)
+    # README.md:179-189 verbatim (the two diffchr lines are not FLAG-derivable)
+    assert report_e == (
+        "824541892 + 0 in total (QC-passed reads + QC-failed reads)\n0 + 0 secondary\n"
+        "5393628 + 0 supplementary\n0 + 0 duplicates\n805383403 + 0 mapped (97.68% : N/A)\n"
+        "819148264 + 0 paired in sequencing\n409574132 + 0 read1\n409574132 + 0 read2\n"
+        "781085884 + 0 properly paired (95.35% : N/A)\n797950890 + 0 with itself and mate mapped\n"
+        "2038885 + 0 singletons (0.25% : N/A)\n")
     kat_e = {
         "name": "KAT-E HiSeqX-shaped, README.md:179-191",
+        "samtools": st_e.tolist(), "samtools_report": report_e,
         "spec": {"gen": "hiseqx", "n": N},
         "category_values": vals.tolist(), "category_counts": cnts.tolist(),
         "reference_kernel": kernel,

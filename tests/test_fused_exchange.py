@@ -40,6 +40,14 @@ def test_world1_overwrite_and_accumulate(cuda_lib):
     d = synth.uniform_device(100_003, 0, 5, 0xFFFF)
     out = x.flagstat(d, pospopcnt=True)
     assert out.cpu().numpy().view(np.uint64).tolist() == O.pospopcnt(O.synth_uniform(0, 100_003, 5, 0xFFFF)).tolist()
+    # samtools mode (exact n_pair_all in slots 0 / 16) through the same exchange
+    a = O.synth_uniform(0, 100_003, 5, 0xFFFF)
+    want = O.flagstat_simd(a)
+    st = O.samtools_loop(a)
+    want[0], want[16] = np.uint64(st[2, 0]), np.uint64(st[2, 1])
+    out = x.flagstat(d, samtools=True)
+    assert out.cpu().numpy().view(np.uint64).tolist() == want.tolist()
+    assert sharded.flagstat_sharded(d, samtools=True).cpu().numpy().view(np.uint64).tolist() == want.tolist()
     x.status()
     x.close()
 

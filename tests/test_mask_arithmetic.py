@@ -55,3 +55,43 @@ def test_keep_mask_and_fail_gate_are_exact_for_every_flag_word():
     assert set(f1.tolist()) == {0.0, 1.0}
     yf = _rn16(y.view(np.float16).astype(np.float64) * f1).view(np.uint16)
     assert (yf == np.where((w & 0x0200) != 0, y, 0)).all()
+
+
+def test_samtools_form_counts_n_pair_all_at_position_4_for_every_flag_word():
+    """mask_select_fx (kSamtools): the class constants gain bit 4 and the final LOP3 is
+    k & (w | 0x0010), so position 4 is 1 exactly for the records flagstat_loop counts in
+    n_pair_all (benchmark/flagstats.cpp:54-59) and every other position is mask_select_f's."""
+    w = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    q = w & 0x0905
+    qf = q.view(np.float16).astype(np.float64)
+    g1 = (q == 0x0001).astype(np.float64)
+    x1 = (q == 0x0005).astype(np.float64)
+    paired = (w & 1) != 0
+    sec, supp = (w & 0x100) != 0, (w & 0x800) != 0
+    kk = paired & ~sec & ~supp
+    for has_sec in (True, False):
+        k = _fma(x1, _f(0x0340), _f(0x0F04))
+        k = _fma(g1, _f(0x036C), k)
+        if has_sec:
+            z = _fma(qf, _f(0x7A00), _f(0xC608), sat=True)
+            k = _rn16(z * _f(0x8D43) + k)
+        else:
+            k = _rn16(k)
+        k = k.view(np.uint16)
+        assert sorted(set(k.tolist())) == ([0x0704] if has_sec else []) + [0x0F04, 0x0FD4, 0x0FDF]
+        y = k & (w | 0x0010)
+        sel = np.ones(65536, bool) if has_sec else ~sec   # the no-SECONDARY form only sees such batches
+        assert (((y & 0x0010) != 0) == kk)[sel].all()
+        assert ((y & 0xF020) == 0).all()                 # positions 5, 12..15 stay clean for fail_gate_f
+
+        # all other positions: the plain keep-mask
+        unmap = (w & 4) != 0
+        keep = np.full(65536, 0x0F04, dtype=np.uint16)
+        keep[kk] |= 0x00C0
+        keep[kk & ~unmap] |= 0x000B
+        keep[sec & supp] &= 0xF7FF
+        assert ((y & 0xFFEF) == (w & keep & 0xFFEF))[sel].all()
+
+        f1 = _rn16((w & 0x0200).view(np.float16).astype(np.float64) * _f(0x7800)).astype(np.float64)
+        yf = _rn16(y.view(np.float16).astype(np.float64) * f1).view(np.uint16)
+        assert (yf == np.where((w & 0x0200) != 0, y, 0)).all()
