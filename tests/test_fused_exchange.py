@@ -76,11 +76,13 @@ def _worker(rank, world, port, n, reps, q):
     acc = torch.zeros(32, dtype=torch.int64, device=f"cuda:{rank}")
     for _ in range(3):
         sharded.flagstat_sharded_fused(local, x, out=acc, accumulate=True)
+    # the samtools mode is one more collective in the same epoch sequence
+    sam = x.flagstat(local, samtools=True)
     torch.cuda.synchronize()
     x.status()
     same = all(torch.equal(o, outs[0]) for o in outs)
     q.put((rank, outs[0].cpu().numpy().view(np.uint64).tolist(), same,
-           acc.cpu().numpy().view(np.uint64).tolist()))
+           acc.cpu().numpy().view(np.uint64).tolist(), sam.cpu().numpy().view(np.uint64).tolist()))
     dist.barrier()
     x.close()
     dist.destroy_process_group()
@@ -104,11 +106,16 @@ def test_one_process_per_gpu_ipc_matches_oracle():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    want = O.numpy_flagstat(O.synth_hiseqx(0, n, 4, 5000))
-    for rank, first, same, acc in got:
+    a = O.synth_hiseqx(0, n, 4, 5000)
+    want = O.numpy_flagstat(a)
+    st = O.samtools_loop(a)
+    want_sam = want.copy()
+    want_sam[0], want_sam[16] = np.uint64(st[2, 0]), np.uint64(st[2, 1])
+    for rank, first, same, acc, sam in got:
         assert first == want.tolist(), rank
         assert same, rank
         assert acc == (3 * want).tolist(), rank
+        assert sam == want_sam.tolist(), rank
 
 
 def test_ranks_in_one_process_peer_access(cuda_lib):

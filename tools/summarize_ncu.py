@@ -91,6 +91,8 @@ if os.path.exists(ll):
         # 1.65 GB shard (the timed steps, ~240 us) and 8-block groups of the stream leg (~12 us)
         if "flagstat_kernel" in name:
             name = ("[shard 1.65 GB] " if t > 100e3 else "[stream group 8 x 1,024,000 B] ") + name
+        if "hbm_read_probe" in name:
+            name = "[bench.py's read-only roofline probe, outside the timed steps] " + name
         key = (name, r[gi])
         agg.setdefault(key, []).append(t)
     tot = sum(sum(v) for v in agg.values())
