@@ -240,6 +240,17 @@ int FLAGSTAT_cuda_samtools_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_
                                             void* stream);
 int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
                                     uint64_t* d_out /*[16]*/, int accumulate, void* stream);
+/* Overlapped steps (default off; returns the previous setting).  When on, a *_allreduce call
+ * on this handle may START before the previous kernel of the same stream has finished
+ * (programmatic dependent launch): its CTAs stream their input while the previous call's
+ * last CTA is still exchanging counters, which hides the exchange latency and the kernel
+ * tail of back-to-back calls.  Everything a call writes (d_flags, the exchange buffers) still
+ * happens after the previous kernel has completed, in stream order.  The caller's side of
+ * the contract: d_array must not be written by the kernel enqueued immediately before the
+ * call on that stream (data produced earlier, or on the other side of an event / a
+ * synchronisation, is fine).  Needs a stream that accepts the attribute (not the NULL
+ * stream on every driver); otherwise the call falls back to a plain launch. */
+int FLAGSTAT_cuda_xchg_set_overlap(FLAGSTAT_cuda_xchg* x, int on);
 /* Peers that never show up: the kernel gives up after the timeout (default 20 s),
  * leaves d_flags untouched and _status returns FLAGSTAT_CUDA_ETIMEOUT.
  * _status synchronises with the device. */

@@ -56,6 +56,7 @@ SIGNATURES = {
                                                  C.c_int, C.c_void_p]),
     "POSPOPCNT_cuda_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                                   C.c_int, C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "FLAGSTAT_cuda_xchg_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_uint32]),
     "FLAGSTAT_cuda_xchg_status": (C.c_int, [C.c_void_p]),
     "FLAGSTAT_cuda_xchg_destroy": (C.c_int, [C.c_void_p]),

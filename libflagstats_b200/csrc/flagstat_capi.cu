@@ -175,8 +175,13 @@ int device_info(int dev, DeviceInfo** out)
 }
 
 // Enqueue one kernel on the current device.
+// overlap: launch with the programmatic-stream-serialization attribute, so that this kernel's
+// CTAs may start (and read d_array) before the previous kernel of `st` has finished; everything
+// it publishes still waits for that kernel (flagstat_kernels.cuh, "Overlapped steps").
+std::atomic<int> g_pdl_unsupported{0};
+
 int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaStream_t st,
-           const XchgArgs* xa = nullptr)
+           const XchgArgs* xa = nullptr, bool overlap = false)
 {
     if ((reinterpret_cast<uintptr_t>(d_array) & 1u) != 0) return FLAGSTAT_CUDA_EINVAL;
     int dev = 0;
@@ -206,6 +211,28 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
 
     XchgArgs none;
     std::memset(&none, 0, sizeof(none));
+    if (overlap && !g_pdl_unsupported.load(std::memory_order_relaxed)) {
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(k.threads);
+        cfg.dynamicSmemBytes = k.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, fn, d_array, (uint64_t)n,
+                                                 reinterpret_cast<unsigned long long*>(d_out),
+                                                 xa ? *xa : none);
+        if (e == cudaSuccess) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return 0;
+        }
+        cudaGetLastError();  // e.g. a stream kind that cannot take the attribute: plain launch from now on
+        g_pdl_unsupported.store(1, std::memory_order_relaxed);
+    }
     fn<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
         d_array, n, reinterpret_cast<unsigned long long*>(d_out), xa ? *xa : none);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -446,6 +473,7 @@ struct FLAGSTAT_cuda_xchg {
     unsigned long long* peer[fsb200::kMaxRanks] = {};  // every rank's buffer as mapped here
     uint64_t epoch = 0;
     uint64_t timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    bool overlap = false;  // FLAGSTAT_cuda_xchg_set_overlap
 };
 
 extern "C" {
@@ -858,7 +886,7 @@ static int xchg_launch(FLAGSTAT_cuda_xchg* x, int mode, const uint16_t* d_array,
     xa.rank = x->rank;
     xa.world = x->world;
     xa.accumulate = accumulate ? 1 : 0;
-    return launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa);
+    return launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa, x->overlap);
 }
 
 int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
@@ -877,6 +905,14 @@ int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_dat
                                     uint64_t* d_out, int accumulate, void* stream)
 {
     return xchg_launch(x, kPospopcnt, d_data, len, d_out, accumulate, stream);
+}
+
+int FLAGSTAT_cuda_xchg_set_overlap(FLAGSTAT_cuda_xchg* x, int on)
+{
+    if (!x) return FLAGSTAT_CUDA_EINVAL;
+    const int prev = x->overlap ? 1 : 0;
+    x->overlap = on != 0;
+    return prev;
 }
 
 int FLAGSTAT_cuda_xchg_set_timeout_ms(FLAGSTAT_cuda_xchg* x, uint32_t ms)

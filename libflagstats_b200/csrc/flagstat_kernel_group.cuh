@@ -275,6 +275,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
 {
     constexpr int DEPTH = 4;  // ring depth == group size
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_launch_dependents();  // overlapped launches: the next kernel may take SM slots as they free up
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t addr = reinterpret_cast<uint64_t>(base);

@@ -410,7 +410,19 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 //   3. waits until all `world` flags in its OWN buffer carry this epoch
 //      (ld.acquire.sys), adds the `world` slots and writes the global counters.
 // The exchange is 256 bytes per peer and overlaps the tail of the slower ranks'
-// kernels; there is no separate collective launch.  Slots are double-buffered
+// kernels; there is no separate collective launch.
+//
+// Overlapped steps (opt-in, FLAGSTAT_cuda_xchg_set_overlap): the launch carries the
+// programmatic-stream-serialization attribute, every CTA executes
+// griddepcontrol.launch_dependents at its start and griddepcontrol.wait only at the top
+// of its epilogue.  The CTAs of step k+1 then take the SM slots the CTAs of step k free
+// and stream their input while the last CTA of k is still waiting for its peers: the
+// exchange latency, the kernel tail and the slowest rank's skew of one step hide behind
+// the counting of the next.  Everything a step PUBLISHES (accumulator, ticket, peer
+// slots, out[]) happens after the wait, i.e. after the previous kernel of the stream has
+// completed and flushed, so the protocol above is unchanged; only the input column is
+// read early, which is why the caller has to opt in (it must not be produced by the
+// kernel launched just before on the same stream).  Slots are double-buffered
 // by epoch parity: a rank can start epoch e+2 only after every rank finished
 // epoch e (it needs their e+1 data to finish e+1), so a slot is never rewritten
 // while a peer may still read it.
@@ -452,6 +464,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// Programmatic dependent launch; both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grids()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -522,6 +543,9 @@ __device__ __forceinline__ void cta_epilogue(unsigned long long* __restrict__ ou
     }
     __syncthreads();
     if (warp != 0) return;
+    // nothing is published before the previous kernel of the stream has completed
+    // (overlapped launches only; returns at once otherwise)
+    pdl_wait_prior_grids();
     unsigned long long a = 0ull, f = 0ull;
 #pragma unroll
     for (int i = 0; i < kWarps; ++i) {

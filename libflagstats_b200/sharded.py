@@ -76,7 +76,7 @@ class FusedExchange:
     communication happens on the path.
     """
 
-    def __init__(self, group=None, device=None, timeout_ms: int = 20000):
+    def __init__(self, group=None, device=None, timeout_ms: int = 20000, overlap: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -109,6 +109,13 @@ class FusedExchange:
                 dist.barrier(group=group)
             check(self._lib.FLAGSTAT_cuda_xchg_set_timeout_ms(self._h, int(timeout_ms)),
                   "FLAGSTAT_cuda_xchg_set_timeout_ms")
+        self.set_overlap(overlap)
+
+    def set_overlap(self, on: bool) -> bool:
+        """Overlapped steps (FLAGSTAT_cuda_xchg_set_overlap): back-to-back calls on one stream
+        may start before the previous one has finished exchanging; the caller guarantees the
+        shard is not written by the kernel enqueued immediately before a call."""
+        return bool(self._lib.FLAGSTAT_cuda_xchg_set_overlap(self._h, 1 if on else 0))
 
     def flagstat(self, local_values, out=None, accumulate: bool = False, stream=None,
                  pospopcnt: bool = False, samtools: bool = False):

@@ -209,6 +209,20 @@ def main():
     assert (np.sum([np.array(s["cuda_expected"], np.uint64) for s in kat_e["shards8"]], axis=0)[CORE20]
             == fe[CORE20]).all()
 
+    # BASELINE configs[3]: 2^34 records of the same periodic generator = 20 periods + a prefix
+    n16 = 1 << 34
+    q16, r16 = divmod(n16, N)
+    fp, _ = O.ref_flagstat_mt(kernel, e[:r16], os.cpu_count() or 1)
+    fps, _ = O.ref_flagstat_mt("scalar", e[:r16], os.cpu_count() or 1)
+    assert (fp[CORE19] == fps[CORE19]).all()
+    kat_16g = {
+        "name": "BASELINE configs[3]: 2^34 HiSeqX-shaped records (20 periods + 689,031,344)",
+        "spec": {"gen": "hiseqx", "n": n16}, "periods": q16, "prefix": r16,
+        "prefix_cuda_expected": core20_only(fp).tolist(),
+        "cuda_expected": (np.uint64(q16) * core20_only(fe) + core20_only(fp)).tolist(),
+        "n_pair_all": int(q16 * int(st_e[2, 0]) + int(O.ref_samtools_loop(e[:r16])[2, 0])),
+    }
+
     doc = {
         "generated_by": "tests/golden/make_golden.py",
         "reference": "mklarqvist/libflagstats @93f68238 (libalgebra @bff182e8), unmodified, "
@@ -218,6 +232,7 @@ def main():
         "cases": cases,
         "kat_c": {"cuda_expected": kat_c.tolist()},
         "kat_e": kat_e,
+        "kat_16g": kat_16g,
     }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "flagstat_golden.json")
     with open(path, "w") as fh:

@@ -233,6 +233,34 @@ def test_more_than_2_pow_32_records_and_epoch_flush(cuda_lib, golden):
         fs.lib().FLAGSTAT_cuda_set_ctas_per_sm(prev)
 
 
+def test_baseline_config3_16g_records_on_one_gpu(cuda_lib, golden):
+    """BASELINE configs[3] at its full size on ONE B200: 2^34 HiSeqX-shaped records (34.4 GB of
+    HBM) = 20 periods of the generator + a 689,031,344-record prefix; the expected counters were
+    made with the reference (tests/golden/make_golden.py, kat_16g).  Also the 8 range shards of
+    the multi-GPU layout, counted one after the other, must add up to the same answer."""
+    fs = cuda_lib
+    torch = _torch()
+    from libflagstats_b200 import sharded, synth
+    k = golden["kat_16g"]
+    n = k["spec"]["n"]
+    free, _total = torch.cuda.mem_get_info()
+    if free < 2 * n + (2 << 30):
+        pytest.skip("needs 36 GB of free device memory")
+    d = synth.hiseqx_device(n)
+    got = fs.flagstat_u64(d)
+    assert got.tolist() == k["cuda_expected"]
+    sam = fs.flagstat_samtools_u64(d)
+    assert int(sam[0]) == k["n_pair_all"] and int(sam[16]) == 0
+    assert sam[CORE20].tolist() == got[CORE20].tolist()
+    acc = np.zeros(32, np.uint64)
+    for r in range(8):
+        lo, hi = sharded.shard_range(n, 8, r)
+        fs.flagstat_u64(d[lo:hi], acc)
+    assert acc.tolist() == got.tolist()
+    del d
+    torch.cuda.empty_cache()
+
+
 def test_async_device_entry_and_stream_blocks(cuda_lib):
     fs = cuda_lib
     torch = _torch()

@@ -52,6 +52,42 @@ def test_world1_overwrite_and_accumulate(cuda_lib):
     x.close()
 
 
+def test_world1_overlapped_steps(cuda_lib):
+    """Overlapped launches (programmatic dependent launch, FLAGSTAT_cuda_xchg_set_overlap):
+    back-to-back calls on a non-default stream over different shards, accumulate and
+    overwrite mixed, plain launches in between -- every result as if strictly serialised."""
+    import torch
+    from libflagstats_b200 import sharded, synth
+    from oracle import oracle as O
+
+    x = sharded.FusedExchange(overlap=True)
+    sizes = [5_000_011, 16384 * 8 * 40, 1, 777_777, 30_000_001]
+    shards = [synth.uniform_device(n, 1000 * i, 3 + i, 0x0FFF) for i, n in enumerate(sizes)]
+    wants = [O.flagstat_simd(O.synth_uniform(1000 * i, n, 3 + i, 0x0FFF)) for i, n in enumerate(sizes)]
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    reps = 25
+    with torch.cuda.stream(s):
+        acc = torch.zeros(32, dtype=torch.int64, device="cuda")
+        outs = []
+        for rep in range(reps):
+            for d in shards:
+                x.flagstat(d, out=acc, accumulate=True, stream=s)
+            o = torch.full((32,), -1, dtype=torch.int64, device="cuda")
+            x.flagstat(shards[rep % len(shards)], out=o, accumulate=False, stream=s)
+            outs.append(o)
+            # a plain accumulate launch between two collectives
+            cuda_lib.flagstat_device(shards[0], out=acc, stream=s)
+    s.synchronize()
+    x.status()
+    total = sum(wants) * np.uint64(reps) + wants[0] * np.uint64(reps)
+    assert acc.cpu().numpy().view(np.uint64).tolist() == total.tolist()
+    for rep, o in enumerate(outs):
+        assert o.cpu().numpy().view(np.uint64).tolist() == wants[rep % len(shards)].tolist(), rep
+    assert x.set_overlap(False) is True
+    x.close()
+
+
 def _worker(rank, world, port, n, reps, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -79,8 +115,24 @@ def _worker(rank, world, port, n, reps, q):
     # the samtools mode is one more collective in the same epoch sequence
     sam = x.flagstat(local, samtools=True)
     torch.cuda.synchronize()
+    # overlapped steps on a non-default stream: same answers, skewed ranks
+    x.set_overlap(True)
+    side = torch.cuda.Stream()
+    ov = []
+    with torch.cuda.stream(side):
+        acc2 = torch.zeros(32, dtype=torch.int64, device=f"cuda:{rank}")
+        for i in range(reps):
+            if i % 4 == rank % 4:
+                torch.cuda._sleep(1_000_000)
+            o = torch.full((32,), -1, dtype=torch.int64, device=f"cuda:{rank}")
+            x.flagstat(local, out=o, stream=side)
+            ov.append(o)
+            x.flagstat(local, out=acc2, accumulate=True, stream=side)
+    side.synchronize()
+    same_ov = all(torch.equal(o, outs[0]) for o in ov) and torch.equal(acc2, outs[0] * reps)
+    x.set_overlap(False)
     x.status()
-    same = all(torch.equal(o, outs[0]) for o in outs)
+    same = all(torch.equal(o, outs[0]) for o in outs) and same_ov
     q.put((rank, outs[0].cpu().numpy().view(np.uint64).tolist(), same,
            acc.cpu().numpy().view(np.uint64).tolist(), sam.cpu().numpy().view(np.uint64).tolist()))
     dist.barrier()
