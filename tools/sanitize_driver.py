@@ -27,6 +27,28 @@ d = synth.hiseqx_device(700_001, 0, 1, 3000)
 out = x.flagstat(d)
 torch.cuda.synchronize()
 assert out.cpu().numpy().view(np.uint64).tolist() == O.flagstat_simd(O.synth_hiseqx(0, 700_001, 1, 3000)).tolist()
+# samtools mode (exact n_pair_all) through the host, device and exchange entries
+u = O.synth_uniform(0, 400_003, 5, 0xFFFF)
+assert fs.samtools_stats(u).tolist() == O.samtools_loop(u).tolist()
+du = synth.uniform_device(400_003 + 3, 0, 5, 0xFFFF)[3:]
+want = O.flagstat_simd(O.synth_uniform(3, 400_003, 5, 0xFFFF))
+st = O.samtools_loop(O.synth_uniform(3, 400_003, 5, 0xFFFF))
+want[0], want[16] = np.uint64(st[2, 0]), np.uint64(st[2, 1])
+assert fs.flagstat_samtools_u64(du).tolist() == want.tolist()
+assert x.flagstat(du, samtools=True).cpu().numpy().view(np.uint64).tolist() == want.tolist()
+# overlapped steps (programmatic dependent launch) on a side stream
+x.set_overlap(True)
+side = torch.cuda.Stream()
+torch.cuda.synchronize()
+with torch.cuda.stream(side):
+    acc = torch.zeros(32, dtype=torch.int64, device="cuda")
+    for _ in range(6):
+        x.flagstat(d, out=acc, accumulate=True, stream=side)
+        x.flagstat(du, out=acc, accumulate=True, stream=side)
+side.synchronize()
+w6 = 6 * (O.flagstat_simd(O.synth_hiseqx(0, 700_001, 1, 3000)) + O.flagstat_simd(O.synth_uniform(3, 400_003, 5, 0xFFFF)))
+assert acc.cpu().numpy().view(np.uint64).tolist() == w6.tolist()
+x.status()
 x.close()
 a = O.synth_uniform(0, 300_000, 9, 0x0FFF)
 for mode in (0, 1):
