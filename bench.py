@@ -535,6 +535,9 @@ def ours(args) -> int:
             "read_only_probe_gbs": read_probe_gbs,
             "frac_of_read_only_probe": (achieved / read_probe_gbs) if read_probe_gbs else None,
             "algorithmic_bytes_per_launch": 2 * n,
+            # the same bytes over the timed step (launch gaps, kernel tail and exchange included;
+            # with overlapped steps this exceeds `achieved`, which times launches one by one)
+            "step_gbs_per_gpu": 2.0 * n / (step_ms * 1e-3) / 1e9,
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),
         },
