@@ -3,6 +3,8 @@
 #   oracle/_ref/dropin_check            C++ driver using the PATCHED reference header
 #   oracle/_ref/pyflagstats*.so         the reference's UNCHANGED python/libflagstats.pyx,
 #                                       compiled against the patched header
+#   oracle/_ref/samtools_caller         plain-C twin of the benchmark's "RAW SAMTOOLS" reader
+#                                       (needs nothing from the reference tree)
 # The reference sources are copied to a temp dir, patched there and compiled;
 # nothing but binaries lands in the repo (oracle/_ref/ is git-ignored and ships
 # to the GPU box with gpurun).
@@ -11,9 +13,11 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(dirname "$HERE")
 REF=${REF:-/root/reference}
 OUT=$ROOT/oracle/_ref
-[ -f "$REF/libflagstats.h" ] || { echo "no reference tree at $REF: keeping prebuilt artefacts"; exit 0; }
 [ -f "$ROOT/libflagstats_b200/libflagstats_cuda.so" ] || python -m libflagstats_b200.build
 mkdir -p "$OUT"
+gcc -std=c99 -O2 -Wall -Wextra -I"$ROOT/include" "$HERE/samtools_caller.c" -o "$OUT/samtools_caller" \
+    -L"$ROOT/libflagstats_b200" -lflagstats_cuda -Wl,-rpath,\$ORIGIN/../../libflagstats_b200
+[ -f "$REF/libflagstats.h" ] || { echo "no reference tree at $REF: keeping prebuilt artefacts"; exit 0; }
 TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 cp "$REF/libflagstats.h" "$REF/libalgebra/libalgebra.h" "$REF/python/libflagstats.pyx" "$TMP/"

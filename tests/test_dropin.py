@@ -97,3 +97,36 @@ def test_unchanged_pyx_runs_on_the_gpu():
         assert {k: int(v) for k, v in d["passed"].items()} == {k: int(v) for k, v in ours["passed"].items()}
         assert {k: int(v) for k, v in d["failed"].items()} == {k: int(v) for k, v in ours["failed"].items()}
     assert fs.lib().FLAGSTAT_cuda_launch_count() > before  # same process, same .so: CUDA really ran
+
+
+SAMCALL = os.path.join(REF_DIR, "samtools_caller")
+
+
+@pytest.mark.skipif(not os.path.exists(SAMCALL), reason="integration/build_dropin.sh not run")
+def test_plain_c_samtools_caller_has_no_cpu_fallback(tmp_path):
+    """integration/samtools_caller.c (C99, only include/flagstats_cuda.h): without a device the
+    reference's block loop around FLAGSTAT_cuda_samtools must fail, not count on the CPU."""
+    if _have_gpu():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    p = tmp_path / "flags.bin"
+    O.synth_uniform(0, 10_000, 1, 0x0FFF).tofile(p)
+    r = subprocess.run([SAMCALL, str(p)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_plain_c_samtools_caller_prints_the_references_report(tmp_path):
+    """The benchmark's 'RAW SAMTOOLS' reader (flagstats.cpp:490-519, report :577-588) with
+    flagstat_loop replaced by FLAGSTAT_cuda_samtools: block by block, whole file, LZ4 container."""
+    assert os.path.exists(SAMCALL), "oracle/_ref/samtools_caller missing (integration/build_dropin.sh)"
+    a = O.synth_hiseqx(0, 5 * 512_000 + 4321, 2, 25_000)
+    want = O.samtools_report(O.samtools_loop(a))
+    raw = tmp_path / "flags.bin"
+    a.tofile(raw)
+    lz = tmp_path / "flags.lz4"
+    lz.write_bytes(O.write_lz4_container(a))
+    for args in ([str(raw)], ["--file", str(raw)], ["--lz4", str(lz)]):
+        r = subprocess.run([SAMCALL] + args, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == want, (args, r.stdout)
+        assert f"{a.size} flags" in r.stderr

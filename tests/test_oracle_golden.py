@@ -112,3 +112,23 @@ def test_kat_e_full_hiseqx_column(golden):
     for s in e["shards8"]:
         tot += np.array(s["cuda_expected"], np.uint64)
     assert tot[CORE20].tolist() == f[CORE20].tolist()
+
+
+def test_kat_16g_is_twenty_periods_plus_a_prefix(golden):
+    """BASELINE configs[3] (2^34 records): the generator is periodic, so the golden answer is
+    20 x KAT-E + the counters of a 689,031,344-record prefix; the restatement recomputes the
+    prefix in 2^26-record slices (the GPU test counts all 2^34 records on one device)."""
+    k = golden["kat_16g"]
+    n, per, rem = k["spec"]["n"], k["periods"], k["prefix"]
+    assert n == 1 << 34 and per * O.HISEQX_N + rem == n and 0 < rem < O.HISEQX_N
+    f = np.zeros(32, np.uint64)
+    pair_all = 0
+    step = 1 << 26
+    for lo in range(0, rem, step):
+        a = O.synth_hiseqx(lo, min(step, rem - lo))
+        O.flagstat_simd(a, f)
+        pair_all += int(O.samtools_loop(a)[2, 0])
+    assert f.tolist() == k["prefix_cuda_expected"]
+    e = np.array(golden["kat_e"]["cuda_expected"], np.uint64)
+    assert (np.uint64(per) * e + f).tolist() == k["cuda_expected"]
+    assert per * golden["kat_e"]["samtools"][2][0] + pair_all == k["n_pair_all"]
