@@ -145,12 +145,16 @@ def pospopcnt_u16(values) -> np.ndarray:
     return out
 
 
-def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False, samtools: bool = False):
+def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False, samtools: bool = False,
+                    overlap: bool = False):
     """Asynchronous, device-resident form (FLAGSTAT_cuda_device /
     POSPOPCNT_cuda_device / FLAGSTAT_cuda_samtools_device).  ``values``: torch CUDA
     tensor of 16-bit integers.  ``out``: torch.int64[32] (or [16]) CUDA tensor that is
     ACCUMULATED into; allocated zeroed if omitted.  Returns ``out`` without
-    synchronising.  ``samtools``: also the exact n_pair_all in slots 0 / 16."""
+    synchronising.  ``samtools``: also the exact n_pair_all in slots 0 / 16.
+    ``overlap`` (flagstat mode): FLAGSTAT_cuda_device_overlapped -- the kernel may start
+    before the previous kernel of the stream has finished; ``values`` must not be written
+    by that kernel."""
     import torch
 
     ptr, n, _keep = _device_view(values)
@@ -163,8 +167,11 @@ def flagstat_device(values, out=None, stream=None, pospopcnt: bool = False, samt
         stream = torch.cuda.current_stream(values.device)
     if pospopcnt and samtools:
         raise ValueError("pospopcnt and samtools are different modes")
+    if overlap and (pospopcnt or samtools):
+        raise ValueError("overlap is available for the flagstat mode only")
     fn = (lib().POSPOPCNT_cuda_device if pospopcnt
-          else lib().FLAGSTAT_cuda_samtools_device if samtools else lib().FLAGSTAT_cuda_device)
+          else lib().FLAGSTAT_cuda_samtools_device if samtools
+          else lib().FLAGSTAT_cuda_device_overlapped if overlap else lib().FLAGSTAT_cuda_device)
     with torch.cuda.device(values.device):
         check(fn(ptr, n, out.data_ptr(), _stream_ptr(stream)), "FLAGSTAT_cuda_device")
     return out

@@ -21,6 +21,7 @@ SIGNATURES = {
     "FLAGSTAT_cuda": (C.c_int, [C.c_void_p, C.c_uint32, u32p]),
     "FLAGSTAT_cuda_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
     "FLAGSTAT_cuda_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "FLAGSTAT_cuda_device_overlapped": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "FLAGSTAT_cuda_available": (C.c_int, []),
     "FLAGSTAT_cuda_min_len": (C.c_uint32, []),
     "FLAGSTAT_cuda_set_min_len": (None, [C.c_uint32]),

@@ -212,8 +212,7 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
     XchgArgs none;
     std::memset(&none, 0, sizeof(none));
     if (overlap && !g_pdl_unsupported.load(std::memory_order_relaxed)) {
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(k.threads);
         cfg.dynamicSmemBytes = k.smem;
@@ -597,6 +596,13 @@ int FLAGSTAT_cuda_samtools_report(const FLAGSTAT_cuda_bam_flagstat* s, char* buf
         buf[n] = '\0';
     }
     return (int)o.size();
+}
+
+int FLAGSTAT_cuda_device_overlapped(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, void* stream)
+{
+    if (!d_flags || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    return launch(kFlagstat, d_array, len, d_flags, static_cast<cudaStream_t>(stream), nullptr, true);
 }
 
 int POSPOPCNT_cuda_u16_u64(const uint16_t* data, uint64_t len, uint64_t* out)

@@ -76,8 +76,8 @@ def test_world1_overlapped_steps(cuda_lib):
             o = torch.full((32,), -1, dtype=torch.int64, device="cuda")
             x.flagstat(shards[rep % len(shards)], out=o, accumulate=False, stream=s)
             outs.append(o)
-            # a plain accumulate launch between two collectives
-            cuda_lib.flagstat_device(shards[0], out=acc, stream=s)
+            # plain accumulate launches between two collectives, serialised and overlapped
+            cuda_lib.flagstat_device(shards[0], out=acc, stream=s, overlap=(rep % 2 == 0))
     s.synchronize()
     x.status()
     total = sum(wants) * np.uint64(reps) + wants[0] * np.uint64(reps)
