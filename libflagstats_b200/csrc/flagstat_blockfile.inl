@@ -251,7 +251,12 @@ int lz4_ctx_acquire(Lz4Ctx** out)
     Lz4Ctx* c = new (std::nothrow) Lz4Ctx();
     if (!c) return FLAGSTAT_CUDA_ENOMEM;
     c->dev = dev;
-    CK(cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t)));
+    const cudaError_t e = cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return (int)e;
+    }
     *out = c;
     return 0;
 }
@@ -428,10 +433,24 @@ int raw_ctx_acquire(RawCtx** out)
     if (!c) return FLAGSTAT_CUDA_ENOMEM;
     c->dev = dev;
     c->threads = want;
-    CK(cudaHostAlloc(&c->h, (size_t)want * 2 * kRawSlotBytes, cudaHostAllocPortable));
-    CK(cudaMalloc(&c->d, (size_t)want * 2 * kRawSlotBytes));
-    for (int i = 0; i < 2 * want; ++i) CK(cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t)));
+    auto build = [&]() -> int {
+        CK(cudaHostAlloc(&c->h, (size_t)want * 2 * kRawSlotBytes, cudaHostAllocPortable));
+        CK(cudaMalloc(&c->d, (size_t)want * 2 * kRawSlotBytes));
+        for (int i = 0; i < 2 * want; ++i) CK(cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking));
+        CK(cudaMalloc(&c->d_flags, 32 * sizeof(uint64_t)));
+        return 0;
+    };
+    const int rc = build();
+    if (rc) {  // e.g. not enough pinned memory: give back what was taken
+        cudaGetLastError();
+        for (int i = 0; i < 2 * want; ++i)
+            if (c->st[i]) cudaStreamDestroy(c->st[i]);
+        if (c->h) cudaFreeHost(c->h);
+        if (c->d) cudaFree(c->d);
+        if (c->d_flags) cudaFree(c->d_flags);
+        delete c;
+        return rc;
+    }
     *out = c;
     return 0;
 }
@@ -559,7 +578,13 @@ int consume_raw(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records
     return run_sync(mode, reinterpret_cast<const uint16_t*>(src.mem), src.size >> 1, totals);
 }
 
+int consume_impl(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records);
 int consume(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
+{
+    return guarded([&] { return consume_impl(src, format, flags, n_records); });
+}
+
+int consume_impl(ByteSource& src, int format, uint64_t* flags, uint64_t* n_records)
 {
     if (!flags) return FLAGSTAT_CUDA_EINVAL;
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
@@ -596,9 +621,14 @@ int FLAGSTAT_cuda_file_u64(const char* path, int format, uint64_t* flags, uint64
     src.fp = std::fopen(path, "rb");
     if (!src.fp) return FLAGSTAT_CUDA_EIO;
     static thread_local std::vector<char> iobuf;
-    iobuf.resize(4u << 20);
-    std::setvbuf(src.fp, iobuf.data(), _IOFBF, iobuf.size());
-    const int rc = consume(src, format, flags, n_records);
+    int rc = guarded([&] {
+        iobuf.resize(4u << 20);
+        return 0;
+    });
+    if (rc == 0) {
+        std::setvbuf(src.fp, iobuf.data(), _IOFBF, iobuf.size());
+        rc = consume(src, format, flags, n_records);
+    }
     std::fclose(src.fp);
     return rc;
 }
@@ -622,6 +652,7 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     if (n_blocks == 0) return 0;
     if (!comp || !raw || !status) return FLAGSTAT_CUDA_EINVAL;
+    return guarded([&]() -> int {
     std::vector<Lz4BlockDesc> desc(n_blocks);
     for (uint32_t b = 0; b < n_blocks; ++b) {
         if (comp_off[b] + comp_size[b] > comp_bytes || raw_off[b] + raw_size[b] > raw_total)
@@ -649,6 +680,7 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
     cudaFree(d_desc);
     cudaFree(d_status);
     return rc;
+    });
 }
 
 }  // extern "C"

@@ -49,6 +49,37 @@ std::atomic<uint32_t> g_min_len{0};  // 0 = not initialised
         if (e_ != cudaSuccess) return (int)e_; \
     } while (0)
 
+// Makes `dev` the current device for a scope and puts the caller's device back afterwards, so
+// that a handle bound to one GPU can be used from a thread whose current device is another.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// The C ABI promises that nothing throws: entries that use std::vector / std::string /
+// std::thread run their body through this (allocation failure -> FLAGSTAT_CUDA_ENOMEM).
+template <class F>
+int guarded(F&& body) noexcept
+{
+    try {
+        return body();
+    } catch (...) {
+        return FLAGSTAT_CUDA_ENOMEM;
+    }
+}
+
 // Kernel variants (FLAGSTAT_cuda_set_variant / env FLAGSTAT_CUDA_VARIANT).  All
 // compute the same thing; they differ in how bytes reach the registers and in
 // how the counters are organised, and are kept selectable for A/B measurement
@@ -315,7 +346,13 @@ uint64_t pageable_min_bytes()
 
 // Synchronous run on the CURRENT device; array may be host or device memory.
 // totals: 32 (flagstat) or 16 (pospopcnt) u64, overwritten.
+int run_sync_impl(int mode, const uint16_t* array, uint64_t len, uint64_t* totals);
 int run_sync(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
+{
+    return guarded([&] { return run_sync_impl(mode, array, len, totals); });
+}
+
+int run_sync_impl(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
 {
     const int nout = mode == kPospopcnt ? 16 : 32;
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
@@ -561,6 +598,7 @@ int FLAGSTAT_cuda_samtools(const uint16_t* array, uint64_t len, FLAGSTAT_cuda_ba
 int FLAGSTAT_cuda_samtools_report(const FLAGSTAT_cuda_bam_flagstat* s, char* buf, size_t capacity)
 {
     if (!s || (!buf && capacity)) return FLAGSTAT_CUDA_EINVAL;
+    return guarded([&]() -> int {
     // percent(), benchmark/flagstats.cpp:73-78: float division, then * 100.0 in double
     char b0[32], b1[32];
     auto pct = [](char* b, long long n, long long total) -> const char* {
@@ -596,6 +634,7 @@ int FLAGSTAT_cuda_samtools_report(const FLAGSTAT_cuda_bam_flagstat* s, char* buf
         buf[n] = '\0';
     }
     return (int)o.size();
+    });
 }
 
 int FLAGSTAT_cuda_device_overlapped(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, void* stream)
@@ -645,7 +684,8 @@ int FLAGSTAT_cuda_stream_open_ex(FLAGSTAT_cuda_stream** out, int device, uint32_
     if (n_slots < 2 || n_slots > 64 || coalesce < 1 || coalesce > 256) return FLAGSTAT_CUDA_EINVAL;
     if (mode != FLAGSTAT_CUDA_STREAM_DMA && mode != FLAGSTAT_CUDA_STREAM_ZEROCOPY)
         return FLAGSTAT_CUDA_EINVAL;
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     FLAGSTAT_cuda_stream* s = new (std::nothrow) FLAGSTAT_cuda_stream();
     if (!s) return FLAGSTAT_CUDA_ENOMEM;
     s->dev = device;
@@ -657,15 +697,25 @@ int FLAGSTAT_cuda_stream_open_ex(FLAGSTAT_cuda_stream** out, int device, uint32_
     s->done.assign(n_slots, nullptr);
     s->busy.assign(n_slots, 0);
     const size_t bytes = (size_t)n_slots * coalesce * block_records * sizeof(uint16_t);
-    CK(cudaHostAlloc(&s->h_base, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-    if (mode == FLAGSTAT_CUDA_STREAM_DMA) CK(cudaMalloc(&s->d_base, bytes));
-    for (int i = 0; i < n_slots; ++i) {
-        CK(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming));
+    // a failure half-way must not leak the pinned ring: _close() copes with a partly built handle
+    auto build = [&]() -> int {
+        CK(cudaHostAlloc(&s->h_base, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        if (mode == FLAGSTAT_CUDA_STREAM_DMA) CK(cudaMalloc(&s->d_base, bytes));
+        for (int i = 0; i < n_slots; ++i) {
+            CK(cudaStreamCreateWithFlags(&s->st[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming));
+        }
+        CK(cudaMalloc(&s->d_flags, 32 * sizeof(uint64_t)));
+        CK(cudaMallocHost(&s->h_flags, 32 * sizeof(uint64_t)));
+        CK(cudaMemset(s->d_flags, 0, 32 * sizeof(uint64_t)));
+        return 0;
+    };
+    const int rc = build();
+    if (rc) {
+        cudaGetLastError();
+        FLAGSTAT_cuda_stream_close(s);
+        return rc;
     }
-    CK(cudaMalloc(&s->d_flags, 32 * sizeof(uint64_t)));
-    CK(cudaMallocHost(&s->h_flags, 32 * sizeof(uint64_t)));
-    CK(cudaMemset(s->d_flags, 0, 32 * sizeof(uint64_t)));
     *out = s;
     return 0;
 }
@@ -700,9 +750,8 @@ int FLAGSTAT_cuda_stream_submit(FLAGSTAT_cuda_stream* s, uint32_t n_records)
     s->cur_fill += 1;
     // a short block ends the contiguous run: ship the group right away
     if (s->cur_fill == s->coalesce || n_records < s->block_records) {
-        int cur = -1;
-        CK(cudaGetDevice(&cur));
-        if (cur != s->dev) CK(cudaSetDevice(s->dev));
+        DeviceGuard guard(s->dev);
+        if (guard.err != cudaSuccess) return (int)guard.err;
         return stream_flush_group(s);
     }
     return 0;
@@ -722,9 +771,8 @@ int FLAGSTAT_cuda_stream_finish(FLAGSTAT_cuda_stream* s, uint64_t* flags)
 {
     if (!s || !flags) return FLAGSTAT_CUDA_EINVAL;
     if (s->acquired) return FLAGSTAT_CUDA_ESTATE;
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
-    if (cur != s->dev) CK(cudaSetDevice(s->dev));
+    DeviceGuard guard(s->dev);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     const int rc = stream_flush_group(s);
     if (rc) return rc;
     for (int i = 0; i < s->n_groups; ++i) {
@@ -755,7 +803,7 @@ int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, ui
 int FLAGSTAT_cuda_stream_close(FLAGSTAT_cuda_stream* s)
 {
     if (!s) return FLAGSTAT_CUDA_EINVAL;
-    cudaSetDevice(s->dev);
+    DeviceGuard guard(s->dev);
     for (int i = 0; i < s->n_groups; ++i) {
         if (s->st[i]) cudaStreamSynchronize(s->st[i]);
         if (s->done[i]) cudaEventDestroy(s->done[i]);
@@ -777,6 +825,7 @@ int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags
     const int have = probe_devices();
     if (have <= 0) return FLAGSTAT_CUDA_ENODEV;
     if (n_devices <= 0 || n_devices > have) n_devices = have;
+    return guarded([&]() -> int {
     std::vector<std::thread> th;
     std::vector<int> rcs(n_devices, 0);
     std::vector<uint64_t> part((size_t)n_devices * 32, 0);
@@ -798,6 +847,7 @@ int FLAGSTAT_cuda_multi_u64(const uint16_t* array, uint64_t len, uint64_t* flags
     for (int g = 0; g < n_devices; ++g)
         for (int i = 0; i < 32; ++i) flags[i] += part[(size_t)g * 32 + i];
     return 0;
+    });
 }
 
 // ---- fused count + counter exchange over peer memory ------------------------------
@@ -809,20 +859,30 @@ int FLAGSTAT_cuda_xchg_create(FLAGSTAT_cuda_xchg** out, int rank, int world, voi
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     FLAGSTAT_cuda_xchg* x = new (std::nothrow) FLAGSTAT_cuda_xchg();
     if (!x) return FLAGSTAT_CUDA_ENOMEM;
-    CK(cudaGetDevice(&x->dev));
     x->rank = rank;
     x->world = world;
-    CK(cudaMalloc(&x->mine, kXchgWords * sizeof(unsigned long long)));
-    CK(cudaMemset(x->mine, 0, kXchgWords * sizeof(unsigned long long)));
-    CK(cudaDeviceSynchronize());
-    x->peer[rank] = x->mine;
-    x->connected = world == 1;
-    if (handle_out) {
-        static_assert(sizeof(cudaIpcMemHandle_t) == FLAGSTAT_CUDA_XCHG_HANDLE_BYTES, "IPC handle size");
-        cudaIpcMemHandle_t h;
-        std::memset(&h, 0, sizeof(h));
-        if (world > 1) CK(cudaIpcGetMemHandle(&h, x->mine));
-        std::memcpy(handle_out, &h, sizeof(h));
+    auto build = [&]() -> int {
+        CK(cudaGetDevice(&x->dev));
+        CK(cudaMalloc(&x->mine, kXchgWords * sizeof(unsigned long long)));
+        CK(cudaMemset(x->mine, 0, kXchgWords * sizeof(unsigned long long)));
+        CK(cudaDeviceSynchronize());
+        x->peer[rank] = x->mine;
+        x->connected = world == 1;
+        if (handle_out) {
+            static_assert(sizeof(cudaIpcMemHandle_t) == FLAGSTAT_CUDA_XCHG_HANDLE_BYTES, "IPC handle size");
+            cudaIpcMemHandle_t h;
+            std::memset(&h, 0, sizeof(h));
+            if (world > 1) CK(cudaIpcGetMemHandle(&h, x->mine));
+            std::memcpy(handle_out, &h, sizeof(h));
+        }
+        return 0;
+    };
+    const int rc = build();
+    if (rc) {  // nothing may leak from a half-built handle
+        cudaGetLastError();
+        if (x->mine) cudaFree(x->mine);
+        delete x;
+        return rc;
     }
     *out = x;
     return 0;
@@ -832,21 +892,28 @@ int FLAGSTAT_cuda_xchg_connect(FLAGSTAT_cuda_xchg* x, const void* all_handles)
 {
     if (!x || !all_handles) return FLAGSTAT_CUDA_EINVAL;
     if (x->connected) return 0;
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
-    if (cur != x->dev) CK(cudaSetDevice(x->dev));
+    DeviceGuard guard(x->dev);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     const char* hs = static_cast<const char*>(all_handles);
     for (int r = 0; r < x->world; ++r) {
         if (r == x->rank) continue;
         cudaIpcMemHandle_t h;
         std::memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
         void* p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {  // unmap what was mapped so far; the handle stays unconnected
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (q != x->rank && x->peer[q]) {
+                    cudaIpcCloseMemHandle(x->peer[q]);
+                    x->peer[q] = nullptr;
+                }
+            return (int)e;
+        }
         x->peer[r] = static_cast<unsigned long long*>(p);
     }
     x->ipc = true;
     x->connected = true;
-    if (cur != x->dev && cur >= 0) CK(cudaSetDevice(cur));
     return 0;
 }
 
@@ -855,8 +922,11 @@ int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs, int world)
     if (!xs || world < 1 || world > kMaxRanks) return FLAGSTAT_CUDA_EINVAL;
     for (int r = 0; r < world; ++r)
         if (!xs[r] || xs[r]->world != world || xs[r]->rank != r) return FLAGSTAT_CUDA_EINVAL;
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
+    struct Restore {  // every return path puts the caller's current device back
+        int dev = -1;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore;
+    CK(cudaGetDevice(&restore.dev));
     for (int a = 0; a < world; ++a) {
         CK(cudaSetDevice(xs[a]->dev));
         for (int b = 0; b < world; ++b) {
@@ -872,7 +942,6 @@ int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs, int world)
         }
         xs[a]->connected = true;
     }
-    if (cur >= 0) CK(cudaSetDevice(cur));
     return 0;
 }
 
@@ -887,12 +956,14 @@ static int xchg_launch(FLAGSTAT_cuda_xchg* x, int mode, const uint16_t* d_array,
     XchgArgs xa;
     std::memset(&xa, 0, sizeof(xa));
     for (int r = 0; r < x->world; ++r) xa.buf[r] = x->peer[r];
-    xa.epoch = ++x->epoch;
+    xa.epoch = x->epoch + 1;
     xa.timeout_ns = x->timeout_ns;
     xa.rank = x->rank;
     xa.world = x->world;
     xa.accumulate = accumulate ? 1 : 0;
-    return launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa, x->overlap);
+    const int rc = launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa, x->overlap);
+    if (rc == 0) ++x->epoch;  // a launch that never happened must not consume an epoch
+    return rc;
 }
 
 int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
@@ -931,19 +1002,17 @@ int FLAGSTAT_cuda_xchg_set_timeout_ms(FLAGSTAT_cuda_xchg* x, uint32_t ms)
 int FLAGSTAT_cuda_xchg_status(FLAGSTAT_cuda_xchg* x)
 {
     if (!x) return FLAGSTAT_CUDA_EINVAL;
-    int cur = -1;
-    CK(cudaGetDevice(&cur));
-    if (cur != x->dev) CK(cudaSetDevice(x->dev));
+    DeviceGuard guard(x->dev);
+    if (guard.err != cudaSuccess) return (int)guard.err;
     unsigned long long err = 0;
     CK(cudaMemcpy(&err, x->mine + kXchgErr, sizeof(err), cudaMemcpyDeviceToHost));
-    if (cur != x->dev && cur >= 0) CK(cudaSetDevice(cur));
     return err ? FLAGSTAT_CUDA_ETIMEOUT : 0;
 }
 
 int FLAGSTAT_cuda_xchg_destroy(FLAGSTAT_cuda_xchg* x)
 {
     if (!x) return FLAGSTAT_CUDA_EINVAL;
-    cudaSetDevice(x->dev);
+    DeviceGuard guard(x->dev);
     cudaDeviceSynchronize();
     if (x->ipc)
         for (int r = 0; r < x->world; ++r)
