@@ -55,7 +55,8 @@ _oracle = None
 
 def build_oracle(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, "flagstat_oracle.c"), os.path.join(HERE, "lz4_oracle.c")]
+    srcs = [os.path.join(HERE, "flagstat_oracle.c"), os.path.join(HERE, "lz4_oracle.c"),
+            os.path.join(HERE, "zstd_oracle.c")]
     if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in srcs):
         subprocess.check_call(
             ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", so] + srcs
@@ -92,6 +93,8 @@ def oracle():
         lib.oracle_lz4_decompress.restype = C.c_int64
         lib.oracle_lz4_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         lib.oracle_lz4_compress.restype = C.c_int64
+        lib.oracle_zstd_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        lib.oracle_zstd_decompress.restype = C.c_int64
         _oracle = lib
     return _oracle
 
@@ -481,6 +484,83 @@ def read_lz4_container(blob: bytes, decompressor=None):
         chunk = decompressor(blob[pos:pos + comp_size], raw_size)
         pos += comp_size
         yield np.frombuffer(chunk[: (raw_size >> 1) * 2], dtype=np.uint16)
+
+
+# --------------------------------------------------------------------------
+# Zstd block containers (benchmark/flagstats.cpp:192-215 writer, :636-676 reader)
+# --------------------------------------------------------------------------
+def zstd_decompress(frame: bytes, raw_size: int) -> bytes:
+    """oracle/zstd_oracle.c restatement of ZSTD_decompress for one frame (RFC 8878)."""
+    out = C.create_string_buffer(max(raw_size, 1))
+    got = oracle().oracle_zstd_decompress(frame, len(frame), out, raw_size)
+    if got != raw_size:
+        raise ValueError(f"malformed Zstd frame (decoder returned {got}, expected {raw_size})")
+    return out.raw[:raw_size]
+
+
+_libzstd = None
+
+
+def libzstd():
+    """The real libzstd runtime of this image (libzstd.so.1; no headers are installed, the three
+    entry points used here have had this signature since zstd 1.0), or None."""
+    global _libzstd
+    if _libzstd is None:
+        try:
+            z = C.CDLL("libzstd.so.1")
+        except OSError:
+            _libzstd = False
+            return None
+        z.ZSTD_compressBound.restype = C.c_size_t
+        z.ZSTD_compressBound.argtypes = [C.c_size_t]
+        z.ZSTD_compress.restype = C.c_size_t
+        z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        z.ZSTD_decompress.restype = C.c_size_t
+        z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        z.ZSTD_isError.restype = C.c_uint
+        z.ZSTD_isError.argtypes = [C.c_size_t]
+        z.ZSTD_versionString.restype = C.c_char_p
+        _libzstd = z
+    return _libzstd or None
+
+
+def libzstd_compress(raw: bytes, level: int = 1) -> bytes:
+    """ZSTD_compress(out, cap, in, n, level): what the reference's ZstdCompress calls (:90-93)."""
+    z = libzstd()
+    cap = z.ZSTD_compressBound(len(raw))
+    dst = C.create_string_buffer(max(cap, 1))
+    n = z.ZSTD_compress(dst, cap, raw, len(raw), level)
+    if z.ZSTD_isError(n):
+        raise ValueError("ZSTD_compress failed")
+    return dst.raw[:n]
+
+
+def libzstd_decompress(frame: bytes, raw_size: int) -> bytes:
+    z = libzstd()
+    dst = C.create_string_buffer(max(raw_size, 1))
+    n = z.ZSTD_decompress(dst, raw_size, frame, len(frame))
+    if z.ZSTD_isError(n) or n != raw_size:
+        raise ValueError("ZSTD_decompress failed")
+    return dst.raw[:raw_size]
+
+
+def write_zstd_container(a, level: int = 1, block_bytes: int = REF_BLOCK_BYTES) -> bytes:
+    """The file zstd() writes (benchmark/flagstats.cpp:192-215) for the FLAG column `a`."""
+    import struct
+
+    raw = _as_u16(a).tobytes()
+    out = []
+    for lo in range(0, len(raw), block_bytes):
+        chunk = raw[lo:lo + block_bytes]
+        comp = libzstd_compress(chunk, level)
+        out.append(struct.pack("<ii", len(chunk), len(comp)))
+        out.append(comp)
+    return b"".join(out)
+
+
+def read_zstd_container(blob: bytes, decompressor=None):
+    """Block loop of zstd_decompress() (benchmark/flagstats.cpp:636-676)."""
+    return read_lz4_container(blob, decompressor or zstd_decompress)
 
 
 # --------------------------------------------------------------------------

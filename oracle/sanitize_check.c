@@ -14,6 +14,13 @@
 
 #include "flagstat_oracle.c"
 #include "lz4_oracle.c"
+#include "zstd_oracle.c"
+
+#ifdef HAVE_LIBZSTD  /* the image has the runtime but no zstd.h: the three stable prototypes, by hand */
+size_t ZSTD_compressBound(size_t n);
+size_t ZSTD_compress(void* dst, size_t cap, const void* src, size_t n, int level);
+unsigned ZSTD_isError(size_t code);
+#endif
 
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "sanitize_check: %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
@@ -113,6 +120,51 @@ int main(void)
             free(a);
         }
     }
+#ifdef HAVE_LIBZSTD
+    /* Zstd frames from the real compressor: decode, then byte-flip / truncation fuzz */
+    for (int kind = 0; kind < 4; ++kind) {
+        const uint64_t n = kind == 3 ? 70001 : 200000;
+        uint16_t* a = (uint16_t*)malloc(n * sizeof(uint16_t));
+        CHECK(a);
+        if (kind == 0) oracle_synth_hiseqx(a, 0, n, 1, 3000);
+        else if (kind == 1) oracle_synth_uniform(a, 0, n, 5, 0x0FFF);
+        else if (kind == 2) for (uint64_t i = 0; i < n; ++i) a[i] = (uint16_t)((i / 37) % 11 * 16 + 99);
+        else oracle_synth_uniform(a, 0, n, 6, 0x0003);
+        const uint64_t raw = n * 2;
+        for (int level = 1; level <= 19; level += 6) {
+            const size_t cap = ZSTD_compressBound(raw);
+            uint8_t* tmp = (uint8_t*)malloc(cap);
+            CHECK(tmp);
+            const size_t c = ZSTD_compress(tmp, cap, a, raw, level);
+            CHECK(!ZSTD_isError(c) && c > 0);
+            uint8_t* frame = (uint8_t*)malloc(c);  /* exact size: red zone right behind the frame */
+            uint8_t* back = (uint8_t*)malloc(raw);
+            CHECK(frame && back);
+            memcpy(frame, tmp, c);
+            CHECK(oracle_zstd_decompress(frame, c, back, raw) == (int64_t)raw);
+            CHECK(memcmp(back, a, raw) == 0);
+            for (int t = 0; t < 400; ++t) {
+                uint8_t* f = (uint8_t*)malloc(c);
+                CHECK(f);
+                memcpy(f, frame, c);
+                const int flips = 1 + (int)(rnd() % 4);
+                for (int k = 0; k < flips; ++k) f[4 + rnd() % (c - 4)] ^= (uint8_t)(1u << (rnd() % 8));
+                const uint64_t cut = (t % 4 == 0) ? (uint64_t)(rnd() % (c + 1)) : (uint64_t)c;
+                const uint64_t ocap = (t % 5 == 0) ? (uint64_t)(rnd() % (raw + 1)) : raw;
+                uint8_t* o = (uint8_t*)malloc(ocap ? ocap : 1);  /* exact-size output too */
+                CHECK(o);
+                const int64_t got = oracle_zstd_decompress(f, cut, o, ocap);
+                CHECK(got <= (int64_t)ocap);
+                free(o);
+                free(f);
+            }
+            free(back);
+            free(frame);
+            free(tmp);
+        }
+        free(a);
+    }
+#endif
     /* every 16-bit word through the per-record forms */
     for (uint32_t x = 0; x < 65536; ++x) {
         uint64_t f[32] = {0};

@@ -2,7 +2,8 @@
 section 5: the reference has no sanitizer runs; the new build's oracle gets them).
 oracle/sanitize_check.c compiles both oracle C files as one TU with
 -fsanitize=address,undefined and drives them over exact-size heap buffers, including a
-byte-flip / truncation fuzz of the LZ4 block decoder and the container walk.  CPU only;
+byte-flip / truncation fuzz of the LZ4 block decoder, the container walk and the Zstd frame
+decoder (frames from the real libzstd).  CPU only;
 the CUDA side has its own compute-sanitizer run (tools/sanitize.sh, profiles/)."""
 import os
 import shutil
@@ -18,10 +19,12 @@ def test_oracle_is_clean_under_asan_and_ubsan(tmp_path):
     if gcc is None:
         pytest.skip("no gcc")
     exe = tmp_path / "sanitize_check"
+    from oracle import oracle as O
+    zstd = ["-DHAVE_LIBZSTD", "-l:libzstd.so.1"] if O.libzstd() is not None else []  # frames for the Zstd fuzz
     build = subprocess.run(
         [gcc, "-std=c11", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
          "-fno-omit-frame-pointer", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "oracle"),
-         os.path.join(ROOT, "oracle", "sanitize_check.c"), "-o", str(exe)],
+         os.path.join(ROOT, "oracle", "sanitize_check.c"), "-o", str(exe)] + zstd,
         capture_output=True, text=True, timeout=300)
     if build.returncode != 0 and "sanitize" in build.stderr and "cannot find" in build.stderr:
         pytest.skip("toolchain has no sanitizer runtime")
