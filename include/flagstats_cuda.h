@@ -177,11 +177,17 @@ int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, ui
  *       (:288-358): repeated [int32 raw_size][int32 comp_size][LZ4 block].  The
  *       blocks cross PCIe COMPRESSED and are decoded on the GPU (one warp per
  *       block), then counted from HBM.  N = raw_size >> 1 records per block like
- *       :323.  Zstd containers (:188-215) are not supported.
+ *       :323.
+ * _ZSTD: the container zstd() writes (:192-215) and zstd_decompress() reads (:636-676): the
+ *       same records around one Zstandard FRAME each (ZSTD_compress / ZSTD_decompress,
+ *       :90-98).  Shipped compressed, decoded on the GPU (RFC 8878: Huffman / FSE / repeat
+ *       offsets; no dictionaries, checksum not verified; first version: one thread per
+ *       frame, ~1600 frames per file in flight), counted from HBM.
  * flags[32] is accumulated into; *n_records (may be NULL) receives the number of
  * records counted.  Runs on the current device; synchronous. */
 #define FLAGSTAT_CUDA_FILE_RAW 0
 #define FLAGSTAT_CUDA_FILE_LZ4 1
+#define FLAGSTAT_CUDA_FILE_ZSTD 2
 /* OR into `format`: count like FLAGSTAT_cuda_samtools_u64 (flags[0] / flags[16] =
  * n_pair_all) -- the reference's "samtools" readers of the same files
  * (flagstat_loop per block, flagstats.cpp:496-519 raw, :547-590 LZ4). */
@@ -197,6 +203,12 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
                              const uint32_t* comp_size, const uint64_t* raw_off,
                              const uint32_t* raw_size, uint32_t n_blocks, void* raw,
                              uint64_t raw_total, int* status);
+
+/* The same for Zstandard frames (one frame per block, as in the _ZSTD container). */
+int FLAGSTAT_cuda_zstd_decode(const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+                              const uint32_t* comp_size, const uint64_t* raw_off,
+                              const uint32_t* raw_size, uint32_t n_blocks, void* raw,
+                              uint64_t raw_total, int* status);
 
 /* ---- FLAG ingest (benchmark/utility.cpp:29-32) -------------------------------
  * `samtools view FILE | cut -f 2` text -- one decimal FLAG per line -- to the

@@ -48,6 +48,8 @@ SIGNATURES = {
     "FLAGSTAT_cuda_container_u64": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, u64p, u64p]),
     "FLAGSTAT_cuda_lz4_decode": (C.c_int, [C.c_void_p, C.c_uint64, u64p, u32p, u64p, u32p, C.c_uint32,
                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]),
+    "FLAGSTAT_cuda_zstd_decode": (C.c_int, [C.c_void_p, C.c_uint64, u64p, u32p, u64p, u32p, C.c_uint32,
+                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]),
     "FLAGSTAT_cuda_ingest_text": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, u64p]),
     "FLAGSTAT_cuda_multi_u64": (C.c_int, [C.c_void_p, C.c_uint64, u64p, C.c_int]),
     "FLAGSTAT_cuda_xchg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),

@@ -6,6 +6,8 @@
   LZ4  the container lz4f()/lz4hc() write (:110-186) and lz4_decompress() reads
        (:288-358): [int32 raw_size][int32 comp_size][LZ4 block] ...  The blocks
        cross PCIe compressed and are decoded on the GPU (one warp per block).
+  ZSTD the container zstd() writes (:192-215) and zstd_decompress() reads (:636-676):
+       the same records around one Zstandard frame each; decoded on the GPU too.
 
 Thin ctypes front-end of FLAGSTAT_cuda_file_u64 / _container_u64 / _lz4_decode;
 no CPU decoder or fallback lives here.
@@ -21,11 +23,11 @@ import numpy as np
 from . import _capi
 from ._capi import check, lib
 
-RAW, LZ4 = 0, 1
+RAW, LZ4, ZSTD = 0, 1, 2
 SAMTOOLS = 0x100
 """OR into the format: count like FLAGSTAT_cuda_samtools_u64 (flags[0] / flags[16] = the exact
 n_pair_all) -- the reference's 'samtools' readers of the same files (flagstats.cpp:496-519, 547-590)."""
-_EXT = {".bin": RAW, ".raw": RAW, ".lz4": LZ4}
+_EXT = {".bin": RAW, ".raw": RAW, ".lz4": LZ4, ".zst": ZSTD, ".zstd": ZSTD}
 
 
 def _format_of(path: str, fmt: Optional[int]) -> int:
@@ -68,7 +70,12 @@ def flagstat_container(blob, fmt: int, flags: Optional[np.ndarray] = None,
     return f, int(n.value)
 
 
-def lz4_decode(blocks: Sequence[bytes], raw_sizes: Sequence[int]):
+def zstd_decode(frames: Sequence[bytes], raw_sizes: Sequence[int]):
+    """Decode Zstandard frames on the GPU (FLAGSTAT_cuda_zstd_decode); same return as lz4_decode."""
+    return lz4_decode(frames, raw_sizes, _entry="FLAGSTAT_cuda_zstd_decode")
+
+
+def lz4_decode(blocks: Sequence[bytes], raw_sizes: Sequence[int], _entry: str = "FLAGSTAT_cuda_lz4_decode"):
     """Decode LZ4 blocks on the GPU.  Returns (list of bytes, list of status); status is
     the decoded size, or a negative code for a malformed block (its bytes are undefined)."""
     nb = len(blocks)
@@ -88,10 +95,10 @@ def lz4_decode(blocks: Sequence[bytes], raw_sizes: Sequence[int]):
         comp[int(comp_off[i]):int(comp_off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
     raw = np.zeros(max(r, 1), np.uint8)
     status = np.zeros(max(nb, 1), np.int32)
-    check(lib().FLAGSTAT_cuda_lz4_decode(
+    check(getattr(lib(), _entry)(
         comp.ctypes.data, c, comp_off.ctypes.data_as(_capi.u64p), comp_size.ctypes.data_as(_capi.u32p),
         raw_off.ctypes.data_as(_capi.u64p), raw_size.ctypes.data_as(_capi.u32p), nb, raw.ctypes.data, r,
-        status.ctypes.data_as(C.POINTER(C.c_int))), "FLAGSTAT_cuda_lz4_decode")
+        status.ctypes.data_as(C.POINTER(C.c_int))), _entry)
     out = [raw[int(raw_off[i]):int(raw_off[i]) + int(raw_size[i])].tobytes() for i in range(nb)]
     return out, status[:nb].tolist()
 

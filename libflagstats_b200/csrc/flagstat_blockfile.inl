@@ -104,6 +104,19 @@ int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4Block
     return 0;
 }
 
+// codec of the [int32 raw][int32 comp][payload] records
+enum Codec { kCodecLz4 = 0, kCodecZstd = 1 };
+
+// Zstd frames (zstd_frame.cuh): one frame per CTA slot, per-frame workspace in global memory
+int zstd_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status,
+                uint32_t n_blocks, zstd::Work* d_work, cudaStream_t st)
+{
+    zstd_decode_kernel<<<n_blocks, 32, 0, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks, d_work);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 struct BlockInfo {
     uint64_t src_off;  // payload position in the file / memory image
     uint32_t comp, raw;
@@ -118,8 +131,9 @@ struct Lz4Lane {
     Lz4BlockDesc* d_desc = nullptr;
     int* h_status = nullptr;           // pinned
     int* d_status = nullptr;
+    zstd::Work* d_work = nullptr;      // Zstd only: one workspace per block of the batch
     size_t comp_cap = 0, raw_cap = 0;
-    int blk_cap = 0;
+    int blk_cap = 0, work_cap = 0;
     cudaStream_t st = nullptr;
     int n = 0;            // blocks in flight
     bool busy = false;
@@ -135,13 +149,22 @@ void lz4_lane_free(Lz4Lane& l)
     if (l.d_desc) cudaFree(l.d_desc);
     if (l.h_status) cudaFreeHost(l.h_status);
     if (l.d_status) cudaFree(l.d_status);
+    if (l.d_work) cudaFree(l.d_work);
     if (l.st) cudaStreamDestroy(l.st);
     l = Lz4Lane();
 }
 
-int lz4_lane_reserve(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, int blocks)
+int lz4_lane_reserve(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, int blocks, int codec)
 {
     if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    if (codec == kCodecZstd && blocks > l.work_cap) {
+        if (l.d_work) cudaFree(l.d_work);
+        l.d_work = nullptr;
+        l.work_cap = 0;
+        const int cap = blocks + blocks / 4 + 16;
+        CK(cudaMalloc(&l.d_work, (size_t)cap * sizeof(zstd::Work)));
+        l.work_cap = cap;
+    }
     if (comp_bytes > l.comp_cap) {
         if (l.h_comp) cudaFreeHost(l.h_comp);
         if (l.d_comp) cudaFree(l.d_comp);
@@ -190,7 +213,8 @@ int lz4_lane_retire(Lz4Lane& l)
     return 0;
 }
 
-int lz4_lane_ship(int mode, Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even, uint64_t* d_flags)
+int lz4_lane_ship(int mode, int codec, Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, bool all_even,
+                  uint64_t* d_flags)
 {
     if (l.n == 0) return 0;
     CK(cudaMemcpyAsync(l.d_comp, l.h_comp, comp_bytes, cudaMemcpyHostToDevice, l.st));
@@ -201,14 +225,16 @@ int lz4_lane_ship(int mode, Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, boo
         CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0, l.st));
     }
-    int rc = lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st);
+    int rc = codec == kCodecZstd
+                 ? zstd_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.d_work, l.st)
+                 : lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st);
     if (rc) return rc;
     if (file_debug()) {
         CK(cudaEventRecord(e1, l.st));
         CK(cudaEventSynchronize(e1));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        std::fprintf(stderr, "[flagstat_cuda] lz4 decode: %d blocks, %zu -> %zu bytes, %.3f ms (%.1f GB/s out)\n",
+        std::fprintf(stderr, "[flagstat_cuda] block decode: %d blocks, %zu -> %zu bytes, %.3f ms (%.1f GB/s out)\n",
                      l.n, comp_bytes, raw_bytes, ms, raw_bytes / (ms * 1e6));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
@@ -290,7 +316,7 @@ int lz4_index(ByteSource& src, int fd, uint64_t total, std::vector<BlockInfo>& i
     return 0;
 }
 
-int consume_lz4(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records)
+int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t* n_records)
 {
     int fd = -1;
     uint64_t total = src.size;
@@ -339,7 +365,7 @@ int consume_lz4(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records
         Lz4Lane& l = lanes[cur];
         rc = lz4_lane_retire(l);  // its previous batch must be off the staging buffers
         if (rc) return rc;
-        rc = lz4_lane_reserve(l, comp_bytes, raw_bytes, (int)(last - first));
+        rc = lz4_lane_reserve(l, comp_bytes, raw_bytes, (int)(last - first), codec);
         if (rc) return rc;
         l.n = (int)(last - first);
         size_t c = 0, r = 0;
@@ -382,7 +408,7 @@ int consume_lz4(int mode, ByteSource& src, uint64_t* totals, uint64_t* n_records
             }
         }
         if (err.load()) return err.load();
-        rc = lz4_lane_ship(mode, l, c, r, all_even, d_flags);
+        rc = lz4_lane_ship(mode, codec, l, c, r, all_even, d_flags);
         if (rc) return rc;
         cur ^= 1;
         first = last;
@@ -595,7 +621,8 @@ int consume_impl(ByteSource& src, int format, uint64_t* flags, uint64_t* n_recor
     const int mode = (format & FLAGSTAT_CUDA_FILE_SAMTOOLS) ? kSamtools : kFlagstat;
     format &= ~FLAGSTAT_CUDA_FILE_SAMTOOLS;
     if (format == FLAGSTAT_CUDA_FILE_RAW) rc = consume_raw(mode, src, t, &n);
-    else if (format == FLAGSTAT_CUDA_FILE_LZ4) rc = consume_lz4(mode, src, t, &n);
+    else if (format == FLAGSTAT_CUDA_FILE_LZ4) rc = consume_lz4(mode, kCodecLz4, src, t, &n);
+    else if (format == FLAGSTAT_CUDA_FILE_ZSTD) rc = consume_lz4(mode, kCodecZstd, src, t, &n);
     else return FLAGSTAT_CUDA_EINVAL;
     if (rc) return rc;
     for (int i = 0; i < 32; ++i) flags[i] += t[i];
@@ -643,11 +670,11 @@ int FLAGSTAT_cuda_container_u64(const void* bytes, uint64_t n_bytes, int format,
     return consume(src, format, flags, n_records);
 }
 
-// Decode-only entry (tests, tools): n_blocks LZ4 blocks described by host arrays; the decoded
+// Decode-only entries (tests, tools): n_blocks payloads described by host arrays; the decoded
 // bytes are returned in `raw` (host, raw_total bytes).  status[b] = decoded size or < 0.
-int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
-                             const uint32_t* comp_size, const uint64_t* raw_off, const uint32_t* raw_size,
-                             uint32_t n_blocks, void* raw, uint64_t raw_total, int* status)
+static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+                         const uint32_t* comp_size, const uint64_t* raw_off, const uint32_t* raw_size,
+                         uint32_t n_blocks, void* raw, uint64_t raw_total, int* status)
 {
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     if (n_blocks == 0) return 0;
@@ -662,6 +689,7 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
     unsigned char *d_comp = nullptr, *d_raw = nullptr;
     Lz4BlockDesc* d_desc = nullptr;
     int* d_status = nullptr;
+    zstd::Work* d_work = nullptr;
     int rc = 0;
     do {
         if ((rc = (int)cudaMalloc(&d_comp, comp_bytes ? comp_bytes : 1))) break;
@@ -671,7 +699,12 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
         if ((rc = (int)cudaMemcpy(d_comp, comp, comp_bytes, cudaMemcpyHostToDevice))) break;
         if ((rc = (int)cudaMemset(d_raw, 0, raw_total ? raw_total : 1))) break;
         if ((rc = (int)cudaMemcpy(d_desc, desc.data(), n_blocks * sizeof(Lz4BlockDesc), cudaMemcpyHostToDevice))) break;
-        if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr))) break;
+        if (codec == kCodecZstd) {
+            if ((rc = (int)cudaMalloc(&d_work, (size_t)n_blocks * sizeof(zstd::Work)))) break;
+            if ((rc = zstd_launch(d_comp, d_raw, d_desc, d_status, n_blocks, d_work, nullptr))) break;
+        } else if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr))) {
+            break;
+        }
         if ((rc = (int)cudaMemcpy(raw, d_raw, raw_total, cudaMemcpyDeviceToHost))) break;
         if ((rc = (int)cudaMemcpy(status, d_status, n_blocks * sizeof(int), cudaMemcpyDeviceToHost))) break;
     } while (0);
@@ -679,8 +712,25 @@ int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64
     cudaFree(d_raw);
     cudaFree(d_desc);
     cudaFree(d_status);
+    cudaFree(d_work);
     return rc;
     });
+}
+
+int FLAGSTAT_cuda_lz4_decode(const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+                             const uint32_t* comp_size, const uint64_t* raw_off, const uint32_t* raw_size,
+                             uint32_t n_blocks, void* raw, uint64_t raw_total, int* status)
+{
+    return decode_blocks(kCodecLz4, comp, comp_bytes, comp_off, comp_size, raw_off, raw_size, n_blocks, raw,
+                         raw_total, status);
+}
+
+int FLAGSTAT_cuda_zstd_decode(const void* comp, uint64_t comp_bytes, const uint64_t* comp_off,
+                              const uint32_t* comp_size, const uint64_t* raw_off, const uint32_t* raw_size,
+                              uint32_t n_blocks, void* raw, uint64_t raw_total, int* status)
+{
+    return decode_blocks(kCodecZstd, comp, comp_bytes, comp_off, comp_size, raw_off, raw_size, n_blocks, raw,
+                         raw_total, status);
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@
 #include "synth.cuh"
 #include "lz4_block.cuh"
 #include "lz4_block_group.cuh"
+#include "zstd_block.cuh"
 #include "ingest_text.cuh"
 #include <cub/device/device_scan.cuh>
 

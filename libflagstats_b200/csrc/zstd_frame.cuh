@@ -1,0 +1,555 @@
+// zstd_frame.cuh -- Zstandard *frame* decoder for the reference's Zstd block files
+// (benchmark/flagstats.cpp:192-215 writes [int32 raw_size][int32 comp_size][Zstd frame]
+// records with ZSTD_compress, :90-93; zstd_decompress(), :636-676, decodes every record with
+// ZSTD_decompress and feeds N = raw_size >> 1 records to the flagstat kernel).
+//
+// zstd is a system library the reference links; what is implemented here is the published
+// format, RFC 8878: frame header, raw / RLE / compressed blocks, literals (raw, RLE, Huffman
+// with 1 or 4 streams, treeless), Huffman tree descriptions (direct or FSE-compressed
+// weights), sequences (predefined / RLE / FSE / repeat tables, backward bitstream), repeat
+// offsets, sequence execution.  No dictionaries; the content checksum is skipped.
+//
+// First version, correctness first: ONE THREAD decodes one frame, start to end (the file has
+// ~1600 independent frames of 1,024,000 bytes, so a launch still keeps every SM busy; the
+// compressed bytes are what crosses PCIe).  All state lives in a per-frame workspace in
+// global memory; there is no allocation, no recursion and no unaligned multi-byte access.
+// The whole decoder is FSB_HD (__host__ __device__): tests/test_zstd_frame_host.py compiles
+// this very file with g++ and holds it to the real libzstd on the CPU; the GPU tests then only
+// have to show that the same code gives the same bytes on the device.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FSB_HD __host__ __device__ __forceinline__
+#define FSB_HDN __host__ __device__ __noinline__
+#else
+#define FSB_HD inline
+#define FSB_HDN inline
+#endif
+
+namespace fsb200 {
+namespace zstd {
+
+constexpr int kErrTrunc = -1, kErrMagic = -2, kErrHeader = -3, kErrBlock = -4, kErrLiterals = -5, kErrHuf = -6,
+              kErrFse = -7, kErrSeq = -8, kErrOut = -9;
+constexpr uint32_t kBlockMax = 128u << 10;  // Block_Maximum_Size
+constexpr int kFseMaxLog = 9, kHufMaxBits = 11;
+
+struct FseTab {
+    int log;  // accuracy log; -1 = no table yet
+    uint8_t sym[1 << kFseMaxLog];
+    uint8_t nbits[1 << kFseMaxLog];
+    uint16_t base[1 << kFseMaxLog];
+};
+struct HufTab {
+    int bits;  // 0 = no table yet
+    uint8_t sym[1 << kHufMaxBits];
+    uint8_t len[1 << kHufMaxBits];
+};
+// per-frame workspace (global memory on the device)
+struct Work {
+    FseTab ll, of, ml, wt;  // wt: the table of FSE-compressed Huffman weights
+    HufTab huf;
+    uint64_t rep[3];
+    int16_t freq[256];
+    uint16_t next[256];
+    uint8_t w[260];
+    uint8_t lit[kBlockMax + 32];
+};
+
+FSB_HD int highbit(uint32_t v)  // floor(log2(v)), v > 0
+{
+    int h = 0;
+    while (v >>= 1) ++h;
+    return h;
+}
+
+// little-endian value of n <= 8 bytes, byte loads only
+FSB_HD uint64_t le(const uint8_t* p, int n)
+{
+    uint64_t v = 0;
+    for (int i = 0; i < n; ++i) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+// ---- bit readers -------------------------------------------------------------------
+
+// forward stream, bit 0 of byte 0 first (FSE table descriptions)
+struct Fwd {
+    const uint8_t* p;
+    uint64_t nbits, pos;
+    FSB_HD uint32_t read(int n)  // n <= 16
+    {
+        uint32_t v = 0;
+        if (pos + 24 <= nbits) {
+            const uint64_t b = pos >> 3;
+            v = (uint32_t)((le(p + b, 3) >> (pos & 7)) & ((1u << n) - 1u));
+        } else {
+            for (int i = 0; i < n; ++i)
+                if (pos + i < nbits) v |= (uint32_t)((p[(pos + i) >> 3] >> ((pos + i) & 7)) & 1u) << i;
+        }
+        pos += (uint64_t)n;
+        return v;
+    }
+};
+
+// backward stream: the last byte carries a 1 above the payload; reads walk towards byte 0
+// and bits "before" the stream are zeros
+struct Back {
+    const uint8_t* p;
+    int64_t pos;
+    FSB_HD bool init(const uint8_t* q, uint64_t n)
+    {
+        if (n == 0 || q[n - 1] == 0) return false;
+        p = q;
+        pos = (int64_t)(n - 1) * 8 + highbit(q[n - 1]);
+        return true;
+    }
+    FSB_HD uint32_t read(int n)  // n <= 32
+    {
+        pos -= n;
+        if (n == 0) return 0u;
+        if (pos >= 0) {
+            // bits [pos, pos + n) lie inside bytes [pos >> 3, (pos + n - 1) >> 3], at most 5 of them,
+            // all below the end marker's byte
+            const int64_t b = pos >> 3;
+            const int nb = (int)(((pos + n - 1) >> 3) - b) + 1;
+            const uint64_t v = le(p + b, nb) >> (pos & 7);
+            return (uint32_t)(v & (((uint64_t)1 << n) - 1u));
+        }
+        uint32_t v = 0;
+        for (int i = 0; i < n; ++i) {
+            const int64_t q = pos + i;
+            if (q >= 0) v |= (uint32_t)((p[q >> 3] >> (q & 7)) & 1u) << i;
+        }
+        return v;
+    }
+};
+
+// ---- FSE (RFC 8878 4.1) ---------------------------------------------------------------
+
+FSB_HDN int fse_build(FseTab& t, const int16_t* freq, int nsym, int log, uint16_t* next)
+{
+    const int size = 1 << log;
+    int high = size;
+    if (log > kFseMaxLog || nsym > 256) return kErrFse;
+    for (int s = 0; s < nsym; ++s)
+        if (freq[s] == -1) {
+            t.sym[--high] = (uint8_t)s;
+            next[s] = 1;
+        }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < nsym; ++s) {
+        if (freq[s] <= 0) continue;
+        next[s] = (uint16_t)freq[s];
+        for (int i = 0; i < freq[s]; ++i) {
+            t.sym[pos] = (uint8_t)s;
+            do pos = (pos + step) & mask; while (pos >= high);
+        }
+    }
+    if (pos != 0) return kErrFse;
+    for (int i = 0; i < size; ++i) {
+        const uint16_t n = next[t.sym[i]]++;
+        t.nbits[i] = (uint8_t)(log - highbit(n));
+        t.base[i] = (uint16_t)(((uint32_t)n << t.nbits[i]) - (uint32_t)size);
+    }
+    t.log = log;
+    return 0;
+}
+
+// table description -> table; returns bytes consumed or < 0
+FSB_HDN int64_t fse_read(FseTab& t, const uint8_t* p, uint64_t n, int max_log, int max_sym, Work& w)
+{
+    Fwd b{p, n * 8, 0};
+    const int log = 5 + (int)b.read(4);
+    if (log > max_log) return kErrFse;
+    int remaining = 1 << log, s = 0;
+    while (remaining > 0 && s <= max_sym) {
+        const int bits = highbit((uint32_t)remaining + 1u) + 1;
+        uint32_t v = b.read(bits);
+        const uint32_t lower = (1u << (bits - 1)) - 1u;
+        const uint32_t thresh = (1u << bits) - 1u - ((uint32_t)remaining + 1u);
+        if ((v & lower) < thresh) {
+            b.pos -= 1;
+            v &= lower;
+        } else if (v > lower) {
+            v -= thresh;
+        }
+        const int proba = (int)v - 1;
+        remaining -= proba < 0 ? 1 : proba;
+        w.freq[s++] = (int16_t)proba;
+        if (proba == 0) {
+            for (;;) {
+                const int rep = (int)b.read(2);
+                for (int i = 0; i < rep && s <= max_sym; ++i) w.freq[s++] = 0;
+                if (rep != 3) break;
+            }
+        }
+        if (b.pos > b.nbits) return kErrTrunc;
+    }
+    if (remaining != 0 || s > max_sym + 1) return kErrFse;
+    const int rc = fse_build(t, w.freq, s, log, w.next);
+    if (rc) return rc;
+    return (int64_t)((b.pos + 7) >> 3);
+}
+
+// ---- Huffman (RFC 8878 4.2) --------------------------------------------------------------
+
+FSB_HDN int huf_build(HufTab& h, uint8_t* wt, int n)  // wt[0..n-1] given, wt[n] implied
+{
+    uint32_t sum = 0;
+    for (int i = 0; i < n; ++i) {
+        if (wt[i] > kHufMaxBits) return kErrHuf;
+        if (wt[i]) sum += 1u << (wt[i] - 1);
+    }
+    if (sum == 0 || n >= 256) return kErrHuf;
+    const int max_bits = highbit(sum) + 1;
+    if (max_bits > kHufMaxBits) return kErrHuf;
+    const uint32_t left = (1u << max_bits) - sum;
+    if ((left & (left - 1u)) != 0u) return kErrHuf;
+    wt[n++] = (uint8_t)(highbit(left) + 1);
+    uint32_t start[kHufMaxBits + 2];
+    for (int k = 0; k < kHufMaxBits + 2; ++k) start[k] = 0;
+    for (int i = 0; i < n; ++i)
+        if (wt[i]) start[wt[i] + 1] += 1u << (wt[i] - 1);
+    for (int k = 1; k < kHufMaxBits + 2; ++k) start[k] += start[k - 1];
+    for (int i = 0; i < n; ++i) {  // by increasing weight, then by symbol value
+        if (!wt[i]) continue;
+        const uint32_t span = 1u << (wt[i] - 1);
+        const uint8_t len = (uint8_t)(max_bits + 1 - wt[i]);
+        const uint32_t at = start[wt[i]];
+        for (uint32_t k = 0; k < span; ++k) {
+            h.sym[at + k] = (uint8_t)i;
+            h.len[at + k] = len;
+        }
+        start[wt[i]] = at + span;
+    }
+    h.bits = max_bits;
+    return 0;
+}
+
+// tree description; returns bytes consumed or < 0
+FSB_HDN int64_t huf_read_tree(Work& w, const uint8_t* p, uint64_t n)
+{
+    if (n < 1) return kErrTrunc;
+    const int hb = p[0];
+    if (hb >= 128) {  // direct: 4 bits per weight
+        const int cnt = hb - 127;
+        const uint64_t bytes = ((uint64_t)cnt + 1) / 2;
+        if (n < 1 + bytes) return kErrTrunc;
+        for (int i = 0; i < cnt; ++i) w.w[i] = (i & 1) ? (uint8_t)(p[1 + i / 2] & 15) : (uint8_t)(p[1 + i / 2] >> 4);
+        const int rc = huf_build(w.huf, w.w, cnt);
+        return rc ? rc : (int64_t)(1 + bytes);
+    }
+    if (hb == 0 || n < 1 + (uint64_t)hb) return kErrTrunc;
+    const int64_t used = fse_read(w.wt, p + 1, (uint64_t)hb, 6, 255, w);
+    if (used < 0) return used;
+    if (used >= hb) return kErrHuf;
+    Back b;
+    if (!b.init(p + 1 + used, (uint64_t)hb - (uint64_t)used)) return kErrHuf;
+    const FseTab& t = w.wt;
+    uint32_t s1 = b.read(t.log), s2 = b.read(t.log);
+    if (b.pos < 0) return kErrHuf;
+    int cnt = 0;
+    for (;;) {  // two interleaved states until the stream runs dry
+        if (cnt >= 254) return kErrHuf;
+        w.w[cnt++] = t.sym[s1];
+        s1 = t.base[s1] + b.read(t.nbits[s1]);
+        if (b.pos < 0) {
+            w.w[cnt++] = t.sym[s2];
+            break;
+        }
+        if (cnt >= 254) return kErrHuf;
+        w.w[cnt++] = t.sym[s2];
+        s2 = t.base[s2] + b.read(t.nbits[s2]);
+        if (b.pos < 0) {
+            w.w[cnt++] = t.sym[s1];
+            break;
+        }
+    }
+    const int rc = huf_build(w.huf, w.w, cnt);
+    return rc ? rc : (int64_t)(1 + hb);
+}
+
+// one Huffman stream -> exactly `want` symbols
+FSB_HDN int huf_stream(const HufTab& h, const uint8_t* p, uint64_t n, uint8_t* out, uint64_t want)
+{
+    Back b;
+    if (!b.init(p, n)) return kErrHuf;
+    const uint32_t mask = (1u << h.bits) - 1u;
+    uint32_t state = b.read(h.bits);
+    uint64_t got = 0;
+    while (b.pos > -(int64_t)h.bits) {
+        if (got == want) return kErrHuf;
+        out[got++] = h.sym[state];
+        const int l = h.len[state];
+        state = ((state << l) + b.read(l)) & mask;
+    }
+    if (b.pos != -(int64_t)h.bits || got != want) return kErrHuf;
+    return 0;
+}
+
+// ---- sequences (RFC 8878 3.1.1.3.2) ----------------------------------------------------------
+
+FSB_HD uint32_t ll_base(int c) { return c < 16 ? (uint32_t)c : c < 20 ? 16u + 2u * (uint32_t)(c - 16) : c < 22 ? 24u + 4u * (uint32_t)(c - 20) : c < 24 ? 32u + 8u * (uint32_t)(c - 22) : c == 24 ? 48u : 64u << (c - 25); }
+FSB_HD int ll_bits(int c) { return c < 16 ? 0 : c < 20 ? 1 : c < 22 ? 2 : c < 24 ? 3 : c == 24 ? 4 : c - 19; }
+FSB_HD uint32_t ml_base(int c)
+{
+    return c < 32 ? 3u + (uint32_t)c : c < 36 ? 35u + 2u * (uint32_t)(c - 32) : c < 38 ? 43u + 4u * (uint32_t)(c - 36)
+         : c < 40 ? 51u + 8u * (uint32_t)(c - 38) : c < 42 ? 67u + 16u * (uint32_t)(c - 40) : c == 42 ? 99u
+         : (128u << (c - 43)) + 3u;
+}
+FSB_HD int ml_bits(int c) { return c < 32 ? 0 : c < 36 ? 1 : c < 38 ? 2 : c < 40 ? 3 : c < 42 ? 4 : c == 42 ? 5 : c - 36; }
+
+// predefined distributions, RFC 8878 3.1.1.3.2.2 (written as code so that no static table has to
+// live in device constant memory: -1 entries are the "less than 1" probabilities)
+FSB_HD int16_t ll_default(int s)
+{
+    return s == 0 ? 4 : s == 1 ? 3 : s <= 12 ? 2 : s <= 15 ? 1 : s <= 24 ? 2 : s == 25 ? 3 : s == 26 ? 2 : s <= 31 ? 1 : -1;
+}
+FSB_HD int16_t ml_default(int s) { return s == 0 ? 1 : s == 1 ? 4 : s == 2 ? 3 : s <= 8 ? 2 : s <= 45 ? 1 : -1; }
+FSB_HD int16_t of_default(int s) { return s <= 5 ? 1 : s <= 8 ? 2 : s <= 23 ? 1 : -1; }
+
+// one of the three tables of a sequences section; which: 0 = LL, 1 = OF, 2 = ML.
+// Returns bytes consumed or < 0.
+FSB_HDN int64_t seq_table(FseTab& t, int mode, const uint8_t* p, uint64_t n, int which, Work& w)
+{
+    const int def_n = which == 0 ? 36 : which == 1 ? 29 : 53;
+    const int def_log = which == 1 ? 5 : 6;
+    const int max_log = which == 1 ? 8 : 9;
+    const int max_sym = which == 0 ? 35 : which == 1 ? 31 : 52;
+    if (mode == 0) {
+        for (int s = 0; s < def_n; ++s) w.freq[s] = which == 0 ? ll_default(s) : which == 1 ? of_default(s) : ml_default(s);
+        const int rc = fse_build(t, w.freq, def_n, def_log, w.next);
+        return rc ? rc : 0;
+    }
+    if (mode == 1) {
+        if (n < 1) return kErrTrunc;
+        if (p[0] > max_sym) return kErrSeq;
+        t.log = 0;
+        t.sym[0] = p[0];
+        t.nbits[0] = 0;
+        t.base[0] = 0;
+        return 1;
+    }
+    if (mode == 2) return fse_read(t, p, n, max_log, max_sym, w);
+    return t.log < 0 ? kErrSeq : 0;  // repeat: the previous table must exist
+}
+
+// a compressed block: literals + sequences -> out[op..]; returns the new op or < 0
+FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t* out, uint64_t op, uint64_t cap)
+{
+    // ---- literals section ----
+    if (n < 1) return kErrTrunc;
+    const int ltype = p[0] & 3, sf = (p[0] >> 2) & 3;
+    uint64_t regen, comp = 0, hdr;
+    const uint8_t* lit;
+    if (ltype < 2) {  // raw / RLE
+        if (sf == 0 || sf == 2) { hdr = 1; regen = p[0] >> 3; }
+        else if (sf == 1) { if (n < 2) return kErrTrunc; hdr = 2; regen = le(p, 2) >> 4; }
+        else { if (n < 3) return kErrTrunc; hdr = 3; regen = le(p, 3) >> 4; }
+        if (regen > kBlockMax) return kErrLiterals;
+        if (ltype == 0) {
+            if (n < hdr + regen) return kErrTrunc;
+            lit = p + hdr;
+            comp = regen;
+        } else {
+            if (n < hdr + 1) return kErrTrunc;
+            const uint8_t v = p[hdr];
+            for (uint64_t i = 0; i < regen; ++i) c.lit[i] = v;
+            lit = c.lit;
+            comp = 1;
+        }
+    } else {  // Huffman-compressed / treeless
+        int streams;
+        if (sf == 0 || sf == 1) {
+            if (n < 3) return kErrTrunc;
+            hdr = 3;
+            const uint64_t v = le(p, 3);
+            regen = (v >> 4) & 0x3FF;
+            comp = (v >> 14) & 0x3FF;
+            streams = sf == 0 ? 1 : 4;
+        } else if (sf == 2) {
+            if (n < 4) return kErrTrunc;
+            hdr = 4;
+            const uint64_t v = le(p, 4);
+            regen = (v >> 4) & 0x3FFF;
+            comp = (v >> 18) & 0x3FFF;
+            streams = 4;
+        } else {
+            if (n < 5) return kErrTrunc;
+            hdr = 5;
+            const uint64_t v = le(p, 5);
+            regen = (v >> 4) & 0x3FFFF;
+            comp = (v >> 22) & 0x3FFFF;
+            streams = 4;
+        }
+        if (regen > kBlockMax || n < hdr + comp) return kErrLiterals;
+        const uint8_t* q = p + hdr;
+        uint64_t left = comp;
+        if (ltype == 2) {
+            const int64_t used = huf_read_tree(c, q, left);
+            if (used < 0) return used;
+            q += used;
+            left -= (uint64_t)used;
+        } else if (c.huf.bits == 0) {
+            return kErrHuf;  // treeless without a previous tree
+        }
+        if (streams == 1) {
+            const int rc = huf_stream(c.huf, q, left, c.lit, regen);
+            if (rc) return rc;
+        } else {
+            if (left < 6) return kErrLiterals;
+            const uint64_t s1 = le(q, 2), s2 = le(q + 2, 2), s3 = le(q + 4, 2);
+            if (6 + s1 + s2 + s3 > left) return kErrLiterals;
+            const uint64_t s4 = left - 6 - s1 - s2 - s3;
+            const uint64_t each = (regen + 3) / 4;
+            if (3 * each > regen) return kErrLiterals;
+            int rc;
+            if ((rc = huf_stream(c.huf, q + 6, s1, c.lit, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1, s2, c.lit + each, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2, s3, c.lit + 2 * each, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2 + s3, s4, c.lit + 3 * each, regen - 3 * each))) return rc;
+        }
+        lit = c.lit;
+    }
+    p += hdr + comp;
+    n -= hdr + comp;
+
+    // ---- sequences section ----
+    if (n < 1) return kErrTrunc;
+    uint64_t nseq;
+    if (p[0] == 0) { nseq = 0; p += 1; n -= 1; }
+    else if (p[0] < 128) { nseq = p[0]; p += 1; n -= 1; }
+    else if (p[0] < 255) { if (n < 2) return kErrTrunc; nseq = ((uint64_t)(p[0] - 128) << 8) + p[1]; p += 2; n -= 2; }
+    else { if (n < 3) return kErrTrunc; nseq = (uint64_t)p[1] + ((uint64_t)p[2] << 8) + 0x7F00; p += 3; n -= 3; }
+    uint64_t lp = 0;  // literals consumed
+    if (nseq) {
+        if (n < 1) return kErrTrunc;
+        const int modes = p[0];
+        if (modes & 3) return kErrSeq;
+        p += 1; n -= 1;
+        int64_t used;
+        if ((used = seq_table(c.ll, modes >> 6, p, n, 0, c)) < 0) return used;
+        p += used; n -= (uint64_t)used;
+        if ((used = seq_table(c.of, (modes >> 4) & 3, p, n, 1, c)) < 0) return used;
+        p += used; n -= (uint64_t)used;
+        if ((used = seq_table(c.ml, (modes >> 2) & 3, p, n, 2, c)) < 0) return used;
+        p += used; n -= (uint64_t)used;
+        Back b;
+        if (!b.init(p, n)) return kErrSeq;
+        uint32_t sl = b.read(c.ll.log), so = b.read(c.of.log), sm = b.read(c.ml.log);
+        for (uint64_t i = 0; i < nseq; ++i) {
+            const int oc = c.of.sym[so], mc = c.ml.sym[sm], lc = c.ll.sym[sl];
+            if (oc > 31 || mc > 52 || lc > 35) return kErrSeq;
+            const uint64_t ov = ((uint64_t)1 << oc) + b.read(oc);
+            const uint64_t ml = ml_base(mc) + b.read(ml_bits(mc));
+            const uint64_t ll = ll_base(lc) + b.read(ll_bits(lc));
+            if (i + 1 < nseq) {
+                sl = c.ll.base[sl] + b.read(c.ll.nbits[sl]);
+                sm = c.ml.base[sm] + b.read(c.ml.nbits[sm]);
+                so = c.of.base[so] + b.read(c.of.nbits[so]);
+            }
+            if (b.pos < 0) return kErrSeq;
+            // repeat offsets, RFC 8878 3.1.1.5
+            uint64_t off;
+            if (ov > 3) {
+                off = ov - 3;
+                c.rep[2] = c.rep[1]; c.rep[1] = c.rep[0]; c.rep[0] = off;
+            } else {
+                const uint64_t idx = ov - 1 + (ll == 0 ? 1 : 0);
+                if (idx == 0) {
+                    off = c.rep[0];
+                } else {
+                    off = idx < 3 ? c.rep[idx] : c.rep[0] - 1;
+                    if (idx > 1) c.rep[2] = c.rep[1];
+                    c.rep[1] = c.rep[0];
+                    c.rep[0] = off;
+                }
+            }
+            // execute: literals, then the match (which may overlap its own output)
+            if (ll > regen - lp || ll + ml > cap - op) return kErrOut;
+            for (uint64_t k = 0; k < ll; ++k) out[op + k] = lit[lp + k];
+            op += ll;
+            lp += ll;
+            if (off == 0 || off > op) return kErrSeq;
+            const uint8_t* src = out + op - off;
+            for (uint64_t k = 0; k < ml; ++k) out[op + k] = src[k];
+            op += ml;
+        }
+        if (b.pos != 0) return kErrSeq;
+    }
+    if (regen - lp > cap - op) return kErrOut;
+    for (uint64_t k = 0; k < regen - lp; ++k) out[op + k] = lit[lp + k];
+    return (int64_t)(op + (regen - lp));
+}
+
+// One frame; returns bytes produced or < 0.  `w` is scratch, its contents on entry do not matter.
+FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, Work& w)
+{
+    if (n < 6) return kErrTrunc;
+    if (le(in, 4) != 0xFD2FB528u) return kErrMagic;
+    const int fhd = in[4];
+    const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, dict = fhd & 3;
+    if (fhd & 0x08) return kErrHeader;
+    uint64_t ip = 5;
+    if (!single) ip += 1;  // window descriptor: the whole frame is decoded into one buffer anyway
+    const int dict_bytes = dict == 3 ? 4 : dict;
+    if (dict_bytes) {
+        if (n < ip + (uint64_t)dict_bytes) return kErrTrunc;
+        if (le(in + ip, dict_bytes) != 0) return kErrHeader;  // dictionaries are not supported
+        ip += (uint64_t)dict_bytes;
+    }
+    const int fcs_bytes = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (n < ip + (uint64_t)fcs_bytes) return kErrTrunc;
+    uint64_t fcs = le(in + ip, fcs_bytes);
+    if (fcs_bytes == 2) fcs += 256;
+    ip += (uint64_t)fcs_bytes;
+    if (fcs_bytes && fcs > cap) return kErrOut;
+
+    w.ll.log = w.of.log = w.ml.log = w.wt.log = -1;
+    w.huf.bits = 0;
+    w.rep[0] = 1; w.rep[1] = 4; w.rep[2] = 8;
+    uint64_t op = 0;
+    for (;;) {
+        if (n < ip + 3) return kErrTrunc;
+        const uint32_t bh = (uint32_t)le(in + ip, 3);
+        ip += 3;
+        const int last = (int)(bh & 1u), type = (int)((bh >> 1) & 3u);
+        const uint64_t size = bh >> 3;
+        if (type == 0) {
+            if (n < ip + size) return kErrTrunc;
+            if (size > cap - op) return kErrOut;
+            for (uint64_t k = 0; k < size; ++k) out[op + k] = in[ip + k];
+            op += size;
+            ip += size;
+        } else if (type == 1) {
+            if (n < ip + 1) return kErrTrunc;
+            if (size > cap - op) return kErrOut;
+            const uint8_t v = in[ip];
+            for (uint64_t k = 0; k < size; ++k) out[op + k] = v;
+            op += size;
+            ip += 1;
+        } else if (type == 2) {
+            if (size > kBlockMax) return kErrBlock;
+            if (n < ip + size) return kErrTrunc;
+            const int64_t r = block_compressed(w, in + ip, size, out, op, cap);
+            if (r < 0) return r;
+            op = (uint64_t)r;
+            ip += size;
+        } else {
+            return kErrBlock;
+        }
+        if (last) break;
+    }
+    if (checksum) {
+        if (n < ip + 4) return kErrTrunc;
+        ip += 4;  // xxh64 of the content, low 32 bits: not verified
+    }
+    if (fcs_bytes && fcs != op) return kErrOut;
+    return (int64_t)op;
+}
+
+}  // namespace zstd
+}  // namespace fsb200

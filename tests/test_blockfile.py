@@ -216,3 +216,95 @@ def test_files_raw_and_lz4(cuda_lib, tmp_path):
     assert ei.value.code == -7
     with pytest.raises(ValueError):
         blockfile.flagstat_file(str(tmp_path / "flags.zst"))
+
+
+# ---------------------------------------------------------------------------- Zstd
+def _zstd_columns():
+    rng = np.random.default_rng(5)
+    cats = np.array([99, 147, 83, 163, 97, 145, 73, 137, 2113, 77], np.uint16)
+    return [
+        ("hiseqx", O.synth_hiseqx(0, 512_000, 2, 1000)),
+        ("iid", cats[rng.integers(0, 10, 300_000)]),
+        ("runs", np.repeat(cats[rng.integers(0, 10, 40_000)], rng.geometric(1 / 8, 40_000))),
+        ("uniform12", O.synth_uniform(0, 100_001, 3, 0x0FFF)),
+        ("uniform16", O.synth_uniform(0, 80_000, 4, 0xFFFF)),
+        ("constant", np.full(512_000, 99, np.uint16)),
+        ("period3", np.tile(np.array([99, 147, 83], np.uint16), 100_000)),
+        ("tiny", np.array([1, 2, 3], np.uint16)),
+    ]
+
+
+needs_libzstd = pytest.mark.skipif(O.libzstd() is None, reason="no libzstd.so.1 to write the frames with")
+
+
+@needs_libzstd
+def test_gpu_zstd_decode_matches_original(cuda_lib):
+    """Frames written by the real libzstd at the levels of the reference's table
+    (README.md:148-175) decode on the GPU to the original bytes (the same source file is held to
+    libzstd on the CPU in tests/test_zstd_frame_host.py)."""
+    from libflagstats_b200 import blockfile
+    frames, raws = [], []
+    for _name, col in _zstd_columns():
+        raw = col.tobytes()
+        for level in (1, 3, 9, 19, -1):
+            frames.append(O.libzstd_compress(raw, level))
+            raws.append(raw)
+    out, status = blockfile.zstd_decode(frames, [len(r) for r in raws])
+    assert status == [len(r) for r in raws]
+    assert all(o == r for o, r in zip(out, raws))
+
+
+@needs_libzstd
+def test_gpu_zstd_decode_rejects_malformed_frames(cuda_lib):
+    from libflagstats_b200 import blockfile
+    raw = O.synth_hiseqx(0, 100_000, 1, 0).tobytes()
+    good = O.libzstd_compress(raw, 3)
+    rng = np.random.default_rng(3)
+    frames = [good, good[:-5], b"\x00" + good[1:]]
+    for t in range(60):
+        bad = bytearray(good)
+        for _k in range(1 + t % 3):
+            bad[int(rng.integers(4, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        frames.append(bytes(bad))
+    out, status = blockfile.zstd_decode(frames, [len(raw)] * len(frames))
+    assert status[0] == len(raw) and out[0] == raw
+    assert status[1] < 0 and status[2] < 0
+    for f, st, o in zip(frames[3:], status[3:], out[3:]):
+        try:  # same verdict and bytes as the oracle's independent decoder
+            want = O.zstd_decompress(f, len(raw))
+        except ValueError:
+            want = None
+        if want is None:
+            assert st != len(raw)
+        else:
+            assert st == len(raw) and o == want
+
+
+@needs_libzstd
+@pytest.mark.parametrize("level,batch", [(1, None), (19, None), (3, "2")])
+def test_zstd_container_counts_match_the_column(cuda_lib, level, batch, monkeypatch, tmp_path):
+    """zstd_decompress() of the reference (benchmark/flagstats.cpp:636-676) on the GPU: container
+    in memory and on disk, plain and samtools counters, several batches."""
+    from libflagstats_b200 import blockfile
+    if batch:
+        monkeypatch.setenv("FLAGSTAT_CUDA_LZ4_BATCH", batch)
+    col = O.synth_hiseqx(0, 5 * 512_000 + 12_345, 1, 15_000)
+    blob = O.write_zstd_container(col, level)
+    want = O.flagstat_simd(col)
+    got, n = blockfile.flagstat_container(blob, blockfile.ZSTD)
+    assert n == col.size and got.tolist() == want.tolist()
+    st = O.samtools_loop(col)
+    want[0], want[16] = np.uint64(st[2, 0]), np.uint64(st[2, 1])
+    got, n = blockfile.flagstat_container(blob, blockfile.ZSTD, samtools=True)
+    assert n == col.size and got.tolist() == want.tolist()
+    path = tmp_path / "flags.zst"
+    path.write_bytes(blob)
+    got, n = blockfile.flagstat_file(str(path), samtools=True)  # format from the extension
+    assert n == col.size and got.tolist() == want.tolist()
+    # a corrupted frame is an error and leaves the counters alone
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x55
+    f = np.full(32, 7, np.uint64)
+    with pytest.raises(cuda_lib.FlagstatCudaError):
+        blockfile.flagstat_container(bytes(bad), blockfile.ZSTD, flags=f)
+    assert f.tolist() == [7] * 32
