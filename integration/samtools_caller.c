@@ -11,6 +11,7 @@
  *   samtools_caller FILE.bin            block by block, like the reference
  *   samtools_caller --file FILE.bin     the whole file in one call (pread threads + pinned ring)
  *   samtools_caller --lz4 FILE.lz4      [int32 raw][int32 comp][LZ4 block] container, decoded on the GPU
+ *   samtools_caller --zstd FILE.zst     the same around Zstandard frames (zstd_decompress_samtools, :684-728)
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -30,7 +31,7 @@ static int fail(const char* what, int rc)
 int main(int argc, char** argv)
 {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s [--file|--lz4] FILE\n", argv[0]);
+        fprintf(stderr, "usage: %s [--file|--lz4|--zstd] FILE\n", argv[0]);
         return 2;
     }
     FLAGSTAT_cuda_bam_flagstat s; /* bam_flagstat_t, :43-49 */
@@ -38,8 +39,11 @@ int main(int argc, char** argv)
     unsigned long long tot_flags = 0;
     int rc;
 
-    if (argc >= 3 && (strcmp(argv[1], "--file") == 0 || strcmp(argv[1], "--lz4") == 0)) {
-        const int fmt = (strcmp(argv[1], "--lz4") == 0 ? FLAGSTAT_CUDA_FILE_LZ4 : FLAGSTAT_CUDA_FILE_RAW) |
+    if (argc >= 3 && (strcmp(argv[1], "--file") == 0 || strcmp(argv[1], "--lz4") == 0 ||
+                      strcmp(argv[1], "--zstd") == 0)) {
+        const int fmt = (strcmp(argv[1], "--lz4") == 0    ? FLAGSTAT_CUDA_FILE_LZ4
+                         : strcmp(argv[1], "--zstd") == 0 ? FLAGSTAT_CUDA_FILE_ZSTD
+                                                          : FLAGSTAT_CUDA_FILE_RAW) |
                         FLAGSTAT_CUDA_FILE_SAMTOOLS;
         uint64_t f[32], n = 0;
         memset(f, 0, sizeof f);

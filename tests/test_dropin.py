@@ -117,7 +117,8 @@ def test_plain_c_samtools_caller_has_no_cpu_fallback(tmp_path):
 @pytest.mark.gpu
 def test_plain_c_samtools_caller_prints_the_references_report(tmp_path):
     """The benchmark's 'RAW SAMTOOLS' reader (flagstats.cpp:490-519, report :577-588) with
-    flagstat_loop replaced by FLAGSTAT_cuda_samtools: block by block, whole file, LZ4 container."""
+    flagstat_loop replaced by FLAGSTAT_cuda_samtools: block by block, whole file, LZ4 and Zstd
+    containers."""
     assert os.path.exists(SAMCALL), "oracle/_ref/samtools_caller missing (integration/build_dropin.sh)"
     a = O.synth_hiseqx(0, 5 * 512_000 + 4321, 2, 25_000)
     want = O.samtools_report(O.samtools_loop(a))
@@ -125,7 +126,12 @@ def test_plain_c_samtools_caller_prints_the_references_report(tmp_path):
     a.tofile(raw)
     lz = tmp_path / "flags.lz4"
     lz.write_bytes(O.write_lz4_container(a))
-    for args in ([str(raw)], ["--file", str(raw)], ["--lz4", str(lz)]):
+    cases = [[str(raw)], ["--file", str(raw)], ["--lz4", str(lz)]]
+    if O.libzstd() is not None:
+        zs = tmp_path / "flags.zst"
+        zs.write_bytes(O.write_zstd_container(a, 3))
+        cases.append(["--zstd", str(zs)])
+    for args in cases:
         r = subprocess.run([SAMCALL] + args, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr
         assert r.stdout == want, (args, r.stdout)

@@ -3,8 +3,9 @@ against the real libzstd of this image (libzstd.so.1 through ctypes, and pyarrow
 frames written by ZSTD_compress at the levels of the reference's table (README.md:148-175:
 1..20, plus the writer's default 22, benchmark/flagstats.cpp:192) must decode to the
 original bytes, malformed frames must be rejected, and the container walk of
-zstd_decompress() (:636-676) must reproduce the column and its counters.  CPU only; the GPU
-decoder for these containers is not built yet."""
+zstd_decompress() (:636-676) must reproduce the column and its counters.  CPU only; the
+product's decoder (libflagstats_b200/csrc/zstd_frame.cuh) is tested against this oracle and
+against libzstd in tests/test_zstd_frame_host.py (host build) and tests/test_blockfile.py (GPU)."""
 import numpy as np
 import pytest
 
