@@ -214,8 +214,11 @@ def test_files_raw_and_lz4(cuda_lib, tmp_path):
     with pytest.raises(FlagstatCudaError) as ei:
         blockfile.flagstat_file(str(tmp_path / "missing.lz4"))
     assert ei.value.code == -7
+    with pytest.raises(FlagstatCudaError) as ei:
+        blockfile.flagstat_file(str(tmp_path / "missing.zst"))
+    assert ei.value.code == -7
     with pytest.raises(ValueError):
-        blockfile.flagstat_file(str(tmp_path / "flags.zst"))
+        blockfile.flagstat_file(str(tmp_path / "flags.xz"))  # no such container format
 
 
 # ---------------------------------------------------------------------------- Zstd
