@@ -22,9 +22,11 @@
 #if defined(__CUDACC__)
 #define FSB_HD __host__ __device__ __forceinline__
 #define FSB_HDN __host__ __device__ __noinline__
+#define FSB_UNROLL _Pragma("unroll")
 #else
 #define FSB_HD inline
 #define FSB_HDN inline
+#define FSB_UNROLL
 #endif
 
 namespace fsb200 {
@@ -70,6 +72,45 @@ FSB_HD uint64_t le(const uint8_t* p, int n)
     uint64_t v = 0;
     for (int i = 0; i < n; ++i) v |= (uint64_t)p[i] << (8 * i);
     return v;
+}
+
+// ---- copies ------------------------------------------------------------------------
+//
+// One thread copying byte by byte pays one memory round trip per byte on the device: the
+// bytes a match reads were stored a moment ago (stores do not allocate in L1), and since
+// source and destination may alias the compiler cannot overlap iterations.  Both copies below
+// therefore move 16 bytes at a time, all loads first, then all stores: one round trip per 16
+// bytes.  Plain byte accesses only (no alignment requirement, same code on the host).
+
+// dst and src do not overlap, or dst - src >= 16
+FSB_HD void copy16(uint8_t* dst, const uint8_t* src, uint64_t n)
+{
+    uint64_t k = 0;
+    for (; k + 16 <= n; k += 16) {
+        uint8_t t[16];
+        FSB_UNROLL
+        for (int j = 0; j < 16; ++j) t[j] = src[k + j];
+        FSB_UNROLL
+        for (int j = 0; j < 16; ++j) dst[k + j] = t[j];
+    }
+    for (; k < n; ++k) dst[k] = src[k];
+}
+
+// LZ77 match: dst[k] = dst[k - off] for k in [0, n), off >= 1, overlap allowed.  A match
+// closer than 16 bytes repeats a pattern of period `off`; once the first (m - 1) * off bytes
+// are out, copying from m * off bytes back gives the same bytes, so the distance is widened to
+// >= 16 and the 16-byte copy applies.
+FSB_HD void copy_match(uint8_t* dst, uint64_t off, uint64_t n)
+{
+    uint64_t k = 0;
+    uint64_t dist = off;
+    if (off < 16) {
+        const uint64_t m = (15 + off) / off;  // smallest m with m * off >= 16
+        dist = m * off;
+        const uint64_t head = dist - off < n ? dist - off : n;
+        for (; k < head; ++k) dst[k] = dst[k - off];
+    }
+    copy16(dst + k, dst + k - dist, n - k);
 }
 
 // ---- bit readers -------------------------------------------------------------------
@@ -470,18 +511,17 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
             }
             // execute: literals, then the match (which may overlap its own output)
             if (ll > regen - lp || ll + ml > cap - op) return kErrOut;
-            for (uint64_t k = 0; k < ll; ++k) out[op + k] = lit[lp + k];
+            copy16(out + op, lit + lp, ll);
             op += ll;
             lp += ll;
             if (off == 0 || off > op) return kErrSeq;
-            const uint8_t* src = out + op - off;
-            for (uint64_t k = 0; k < ml; ++k) out[op + k] = src[k];
+            copy_match(out + op, off, ml);
             op += ml;
         }
         if (b.pos != 0) return kErrSeq;
     }
     if (regen - lp > cap - op) return kErrOut;
-    for (uint64_t k = 0; k < regen - lp; ++k) out[op + k] = lit[lp + k];
+    copy16(out + op, lit + lp, regen - lp);
     return (int64_t)(op + (regen - lp));
 }
 
@@ -521,7 +561,7 @@ FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64
         if (type == 0) {
             if (n < ip + size) return kErrTrunc;
             if (size > cap - op) return kErrOut;
-            for (uint64_t k = 0; k < size; ++k) out[op + k] = in[ip + k];
+            copy16(out + op, in + ip, size);
             op += size;
             ip += size;
         } else if (type == 1) {
