@@ -15,7 +15,9 @@
 // global memory; there is no allocation, no recursion and no unaligned multi-byte access.
 // The whole decoder is FSB_HD (__host__ __device__): tests/test_zstd_frame_host.py compiles
 // this very file with g++ and holds it to the real libzstd on the CPU; the GPU tests then only
-// have to show that the same code gives the same bytes on the device.
+// have to show that the same code gives the same bytes on the device.  The host instantiation
+// exists for those tests only: libflagstats_cuda.so calls decode_frame from zstd_decode_kernel
+// and nowhere else (there is no CPU fallback in the product).
 #pragma once
 #include <stdint.h>
 
