@@ -101,3 +101,28 @@ def test_kat_e_shards_in_golden_use_the_same_ranges(golden):
     for r, s in enumerate(golden["kat_e"]["shards8"]):
         lo, hi = shard_range(n, 8, r)
         assert (lo, hi - lo) == (s["start"], s["n"])
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke()/build() and bench.py's CPU legs
+    may import, link or execute it.  Static check over the product sources and the build recipe."""
+    import re
+    pkg = os.path.join(ROOT, "libflagstats_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle/|liboracle|oracle_[a-z]+\(", re.M)
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+            # comments may NAME the oracle (e.g. "equals the CPU oracle byte for byte"); code may not use it
+            code = "\n".join(ln for ln in text.splitlines()
+                             if not ln.lstrip().startswith(("//", "#", "*", "/*", '"""')) and "oracle/flagstat_oracle.c)" not in ln)
+            assert not pat.search(code), os.path.join(dirpath, f)
+    # the library links nothing from oracle/ either
+    from libflagstats_b200 import build as b
+    assert not any("oracle" in x for x in b.SOURCES + b.HEADERS + b.NVCC_FLAGS)
+    # bench.py: the oracle is imported inside cpu_reference_run() only (cpu_baseline / --impl reference)
+    bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    assert len(uses) == 1
+    assert bench.rfind("def ", 0, uses[0]) == bench.find("def cpu_reference_run")
