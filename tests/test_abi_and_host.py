@@ -126,3 +126,23 @@ def test_product_never_touches_the_oracle():
     uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
     assert len(uses) == 1
     assert bench.rfind("def ", 0, uses[0]) == bench.find("def cpu_reference_run")
+
+
+def test_header_is_plain_c99_and_cxx11(tmp_path):
+    """include/flagstats_cuda.h is what a C host binds (the reference is a C header): it must
+    compile on its own as strict C99 / C11 and C++11, no CUDA or torch types, no extensions."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or shutil.which("g++") is None:
+        pytest.skip("no gcc / g++")
+    src = '#include "flagstats_cuda.h"\nint main(void) { return sizeof(FLAGSTAT_cuda_bam_flagstat) == 26 * sizeof(long long) ? 0 : 1; }\n'
+    inc = os.path.join(ROOT, "include")
+    for cc, std, ext in (("gcc", "c99", "c"), ("gcc", "c11", "c"), ("g++", "c++11", "cpp")):
+        f = tmp_path / f"h_{std.replace('+', 'x')}.{ext}"
+        f.write_text(src)
+        r = subprocess.run([cc, f"-std={std}", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(f),
+                            "-o", str(tmp_path / "h.o")], capture_output=True, text=True)
+        assert r.returncode == 0, (cc, std, r.stderr)
+    text = open(os.path.join(inc, "flagstats_cuda.h"), encoding="utf-8").read()
+    for banned in ("cuda_runtime", "cudaStream_t", "torch", "#include <cuda"):
+        assert banned not in text, banned
