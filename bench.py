@@ -275,11 +275,41 @@ def ours(args) -> int:
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
+    # (the decision to keep going is taken collectively: every rank must issue the same number
+    # of steps, or the epochs of the fused exchange would drift apart between ranks)
     tw = time.perf_counter()
-    while time.perf_counter() - tw < args.settle_s:
+    while True:
+        more = torch.tensor([1 if time.perf_counter() - tw < args.settle_s else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(more, op=dist.ReduceOp.MIN)
+        if int(more.item()) == 0:
+            break
         for _ in range(50):
             step()
         fence()
+
+    # Overlapped launches were validated at 1, 2 and 4 GPUs; should they ever misbehave on a box
+    # (a peer that does not deliver ends in FLAGSTAT_CUDA_ETIMEOUT, not in a hang), all ranks fall
+    # back together to serialised launches on a fresh exchange rather than lose the measurement.
+    overlap_fallback = None
+    if xchg is not None and overlap:
+        ok = 1
+        try:
+            xchg.status()
+        except Exception as exc:  # FlagstatCudaError
+            ok = 0
+            overlap_fallback = repr(exc)
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:
+            overlap_fallback = overlap_fallback or "a peer reported a failed exchange"
+            xchg.close()
+            xchg = sharded.FusedExchange(device=dev, overlap=False)
+            overlap = False
+            for _ in range(max(args.warmup, 3)):
+                step()
+            fence()
 
     # ---- device-resident timed region: exactly K steps ---------------------
     sampler = ClockSampler(local)
@@ -557,6 +587,7 @@ def ours(args) -> int:
                      + ("; consecutive steps overlap (programmatic dependent launch: the next step "
                         "streams its shard while this step's last CTA exchanges counters)" if overlap else "")
                      if xchg is not None else "kernel + memset + NCCL all-reduce of 32 x u64"),
+        "overlap_fallback": overlap_fallback,
         "ms_per_step_serialised_launches": serial_ms,
         "serialised_same_result": (serial_ok if serial_ms is not None else None),
         "ms_per_step_with_nccl_allreduce": alt_ms,
