@@ -118,3 +118,21 @@ def test_product_decoder_under_asan_and_ubsan_fuzz(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "zstd_frame_fuzz ok" in run.stdout and "ERROR" not in run.stderr
+
+
+def test_property_random_structured_inputs_round_trip_product(host):
+    """The same hypothesis property as the oracle's, on the product decoder's host build."""
+    from hypothesis import given, settings, strategies as st
+
+    frag = st.binary(min_size=1, max_size=40)
+
+    @settings(max_examples=120, deadline=None)
+    @given(frags=st.lists(frag, min_size=1, max_size=12), picks=st.lists(st.integers(0, 11), min_size=1, max_size=400),
+           reps=st.lists(st.integers(1, 60), min_size=1, max_size=400), level=st.sampled_from([-3, 1, 2, 3, 5, 9, 13, 19, 22]))
+    def run(frags, picks, reps, level):
+        raw = b"".join(frags[p % len(frags)] * reps[i % len(reps)] for i, p in enumerate(picks))
+        frame = O.libzstd_compress(raw, level)
+        r, out = _decode(host, frame, len(raw))
+        assert r == len(raw) and out == raw
+
+    run()

@@ -85,3 +85,25 @@ def test_container_walk_reproduces_the_column_and_its_counters():
         # libzstd reading the same container agrees block by block
         ref_blocks = list(O.read_zstd_container(blob, O.libzstd_decompress))
         assert all(np.array_equal(a, b) for a, b in zip(blocks, ref_blocks))
+
+
+def test_property_random_structured_inputs_round_trip():
+    """hypothesis: byte strings built from repeated fragments over small alphabets (the shapes
+    that exercise RLE blocks, treeless literals, repeat offsets and all FSE table modes), any
+    level: libzstd's frame decodes here to the input."""
+    from hypothesis import given, settings, strategies as st
+
+    frag = st.binary(min_size=1, max_size=40)
+
+    @settings(max_examples=120, deadline=None)
+    @given(frags=st.lists(frag, min_size=1, max_size=12), picks=st.lists(st.integers(0, 11), min_size=1, max_size=400),
+           reps=st.lists(st.integers(1, 60), min_size=1, max_size=400), level=st.sampled_from([-3, 1, 2, 3, 5, 9, 13, 19, 22]))
+    def run(frags, picks, reps, level):
+        parts = []
+        for i, p in enumerate(picks):
+            parts.append(frags[p % len(frags)] * reps[i % len(reps)])
+        raw = b"".join(parts)
+        frame = O.libzstd_compress(raw, level)
+        assert O.zstd_decompress(frame, len(raw)) == raw
+
+    run()
