@@ -148,3 +148,18 @@ def test_header_is_plain_c99_and_cxx11(tmp_path):
     code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)  # comments may say "a cudaStream_t travels as void*"
     for banned in ("cuda_runtime", "cudaStream_t", "cudaError_t", "torch", "#include <cuda"):
         assert banned not in code, banned
+
+
+def test_tools_and_session_scripts_parse():
+    """tools/ holds the measurement scripts the GPU sessions run (there is no second chance on a
+    box that is charged by the minute): every Python tool byte-compiles, every shell script
+    passes `bash -n`."""
+    import glob
+    import py_compile
+    import subprocess
+    for f in glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py"),
+                                                                 os.path.join(ROOT, "__graft_entry__.py")]:
+        py_compile.compile(f, doraise=True, cfile=os.devnull)
+    for f in glob.glob(os.path.join(ROOT, "tools", "*.sh")) + glob.glob(os.path.join(ROOT, "integration", "*.sh")):
+        r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stderr)
