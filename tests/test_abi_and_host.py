@@ -152,14 +152,13 @@ def test_header_is_plain_c99_and_cxx11(tmp_path):
 
 def test_tools_and_session_scripts_parse():
     """tools/ holds the measurement scripts the GPU sessions run (there is no second chance on a
-    box that is charged by the minute): every Python tool byte-compiles, every shell script
+    box that is charged by the minute): every Python tool compiles, every shell script
     passes `bash -n`."""
     import glob
-    import py_compile
     import subprocess
     for f in glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py"),
                                                                  os.path.join(ROOT, "__graft_entry__.py")]:
-        py_compile.compile(f, doraise=True, cfile=os.devnull)
+        compile(open(f, encoding="utf-8").read(), f, "exec")
     for f in glob.glob(os.path.join(ROOT, "tools", "*.sh")) + glob.glob(os.path.join(ROOT, "integration", "*.sh")):
         r = subprocess.run(["bash", "-n", f], capture_output=True, text=True)
         assert r.returncode == 0, (f, r.stderr)
