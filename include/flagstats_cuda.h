@@ -262,6 +262,20 @@ int FLAGSTAT_cuda_samtools_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_
                                             void* stream);
 int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_data, uint64_t len,
                                     uint64_t* d_out /*[16]*/, int accumulate, void* stream);
+/* Deferred collection: the same count + push, but the call does NOT wait for the peers' totals.
+ * The global counters of this call are written to d_flags by the NEXT *_allreduce* call on the
+ * handle (which first collects what its predecessor left pending, then pushes its own totals)
+ * or by FLAGSTAT_cuda_xchg_collect -- so d_flags must stay valid until then.  For back-to-back
+ * steps: a rank waits only for its peers' PREVIOUS step and may run one step ahead of the
+ * slowest rank; per-step jitter between GPUs no longer adds up.  Every rank must issue the
+ * same sequence of deferred / immediate / collect calls.  With one rank d_flags is written
+ * at once. */
+int FLAGSTAT_cuda_device_allreduce_deferred(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array,
+                                            uint64_t len, uint64_t* d_flags, int accumulate,
+                                            void* stream);
+/* Writes the pending counters of the last deferred call (one warp; asynchronous on `stream`,
+ * which must be ordered after that call).  No-op when nothing is pending. */
+int FLAGSTAT_cuda_xchg_collect(FLAGSTAT_cuda_xchg* x, void* stream);
 /* Overlapped steps (default off; returns the previous setting).  When on, a *_allreduce call
  * on this handle may START before the previous kernel of the same stream has finished
  * (programmatic dependent launch): its CTAs stream their input while the previous call's
@@ -274,7 +288,10 @@ int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_dat
  * stream on every driver); otherwise the call falls back to a plain launch. */
 int FLAGSTAT_cuda_xchg_set_overlap(FLAGSTAT_cuda_xchg* x, int on);
 /* Peers that never show up: the kernel gives up after the timeout (default 20 s),
- * leaves d_flags untouched and _status returns FLAGSTAT_CUDA_ETIMEOUT.
+ * leaves d_flags untouched, marks the exchange failed on every rank it can reach, and
+ * _status returns FLAGSTAT_CUDA_ETIMEOUT.  The failure is sticky: later *_allreduce* calls on
+ * the handle return FLAGSTAT_CUDA_ESTATE, and ALL ranks must destroy and recreate their
+ * handles (the epoch-parity protocol assumes every rank completed every epoch).
  * _status synchronises with the device. */
 int FLAGSTAT_cuda_xchg_set_timeout_ms(FLAGSTAT_cuda_xchg* x, uint32_t ms);
 int FLAGSTAT_cuda_xchg_status(FLAGSTAT_cuda_xchg* x);
@@ -320,6 +337,12 @@ int FLAGSTAT_cuda_sync(void);
  * 1 = pospopcnt, 2 = samtools mode. */
 int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
                               int pospopcnt_mode, float* ms_per_launch);
+/* The same over n_rot copies of the column laid out stride_records apart (launch i reads copy
+ * i % n_rot): columns smaller than the 126 MB L2 are then timed from HBM rather than from the
+ * cache a back-to-back loop over ONE copy would hit.  mode as pospopcnt_mode above. */
+int FLAGSTAT_cuda_time_device_rot(const uint16_t* d_base, uint64_t len, uint64_t stride_records,
+                                  uint32_t n_rot, uint64_t* d_flags, int iters, int mode,
+                                  float* ms_per_launch);
 /* Read-only HBM probe over device memory (16-byte aligned): LDG.128 + one XOR per 16
  * bytes, nothing else; mean milliseconds per pass.  The roofline a stream that only
  * reads can reach on this device (a copy pays bus turn-arounds a read does not). */

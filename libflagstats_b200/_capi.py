@@ -57,6 +57,9 @@ SIGNATURES = {
     "FLAGSTAT_cuda_xchg_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "FLAGSTAT_cuda_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                                  C.c_int, C.c_void_p]),
+    "FLAGSTAT_cuda_device_allreduce_deferred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                          C.c_int, C.c_void_p]),
+    "FLAGSTAT_cuda_xchg_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "POSPOPCNT_cuda_device_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                                   C.c_int, C.c_void_p]),
     "FLAGSTAT_cuda_xchg_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
@@ -84,6 +87,8 @@ SIGNATURES = {
     "FLAGSTAT_cuda_sync": (C.c_int, []),
     "FLAGSTAT_cuda_time_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
                                             C.POINTER(C.c_float)]),
+    "FLAGSTAT_cuda_time_device_rot": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
+                                                C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "FLAGSTAT_cuda_read_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 

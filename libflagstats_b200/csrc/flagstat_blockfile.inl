@@ -55,15 +55,56 @@ bool file_debug()
     return on;
 }
 
+// Staging / reader threads.  Default: 3/4 of the CPUs this process may run on (sched_getaffinity,
+// not the machine's core count: containers and taskset), at least 2, at most kRawMaxThreads --
+// measured on a 16-vCPU B200 host: 6 threads 43 GB/s, 12 threads 45-50 GB/s of a 55 GB/s link
+// (profiles/r4c_pageable.jsonl).  FLAGSTAT_CUDA_IO_THREADS overrides.
 int io_threads()
 {
-    int t = 6;
+    int t = 0;
     if (const char* e = std::getenv("FLAGSTAT_CUDA_IO_THREADS")) t = std::atoi(e);
-    const int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 0 && t > hw) t = hw;
+    if (t <= 0) {
+        int cpus = 0;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+        if (cpus <= 0) cpus = (int)std::thread::hardware_concurrency();
+        t = cpus * 3 / 4;
+        if (t < 2) t = 2;
+    }
     if (t < 1) t = 1;
-    if (t > 16) t = 16;
+    if (t > 24) t = 24;
     return t;
+}
+
+// Copy into a pinned staging slot with non-temporal stores: the slot is written once and then
+// read by the DMA engine, never by this core, so the destination lines need not be read for
+// ownership nor kept in cache -- a quarter less DRAM traffic than memcpy on the staged path
+// (source read + slot write + DMA read instead of + the slot's read-for-ownership), which is
+// what bounds it once enough threads are copying.  dst is 64-byte aligned (slot base + a
+// multiple of 64 KiB).  FLAGSTAT_CUDA_STAGING_NT=0 switches back to memcpy (A/B).
+bool staging_nt()
+{
+    const char* e = std::getenv("FLAGSTAT_CUDA_STAGING_NT");
+    return !(e && std::atoi(e) == 0);
+}
+
+void copy_streaming(unsigned char* dst, const unsigned char* src, size_t n)
+{
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0u) {
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+        }
+        _mm_sfence();
+    }
+    if (i < n) std::memcpy(dst + i, src + i, n - i);
 }
 
 // FLAGSTAT_CUDA_LZ4_VARIANT: 1 = 32 sequences per warp step (lz4_block_group.cuh, default),
@@ -428,7 +469,7 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
 // moves to its other slot, so the page-cache copy of group k+1 overlaps DMA + count of group
 // k, and T such pipelines run side by side (one reader thread tops out at ~5 GB/s).
 constexpr size_t kRawSlotBytes = 8u * (size_t)kRefBlockBytes;
-constexpr int kRawMaxThreads = 16;
+constexpr int kRawMaxThreads = 24;
 
 struct RawCtx {
     int dev = -1;
@@ -582,10 +623,12 @@ int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals
     if (slot < (1u << 20)) slot = 1u << 20;
     if (slot > kRawSlotBytes) slot = kRawSlotBytes & ~(size_t)65535u;
     const unsigned char* base = reinterpret_cast<const unsigned char*>(array);
+    const bool nt = staging_nt();
     return consume_staged(
         mode, size, (size_t)slot,
-        [base](unsigned char* h, uint64_t off, size_t n) {
-            std::memcpy(h, base + off, n);
+        [base, nt](unsigned char* h, uint64_t off, size_t n) {
+            if (nt) copy_streaming(h, base + off, n);
+            else std::memcpy(h, base + off, n);
             return true;
         },
         totals);

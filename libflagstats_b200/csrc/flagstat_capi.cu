@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <emmintrin.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -80,6 +82,19 @@ int guarded(F&& body) noexcept
         return FLAGSTAT_CUDA_ENOMEM;
     }
 }
+
+// RAII for the measurement aids (FLAGSTAT_cuda_time_device*, _read_probe): nothing leaks on an early CK() return
+struct TimerPair {
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool own_stream = false;
+    ~TimerPair()
+    {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (own_stream && st) cudaStreamDestroy(st);
+    }
+};
 
 // Kernel variants (FLAGSTAT_cuda_set_variant / env FLAGSTAT_CUDA_VARIANT).  All
 // compute the same thing; they differ in how bytes reach the registers and in
@@ -278,7 +293,8 @@ struct Lane {
     int dev = -1;
     cudaStream_t copy = nullptr, comp = nullptr;
     uint64_t* d_flags = nullptr;  // 32 x u64
-    uint64_t* h_flags = nullptr;  // pinned
+    uint64_t* h_flags = nullptr;  // pinned, mapped
+    unsigned long long* xbuf = nullptr;  // world-1 exchange buffer: lets one launch OVERWRITE its output
     uint16_t* stage[kStages] = {nullptr, nullptr, nullptr};
     cudaEvent_t copied[kStages] = {nullptr, nullptr, nullptr};
     cudaEvent_t consumed[kStages] = {nullptr, nullptr, nullptr};
@@ -288,15 +304,44 @@ struct Lane {
 std::mutex g_pool_mu;
 std::vector<Lane*> g_pool[kMaxDevices];
 
+void lane_destroy(Lane* l)
+{
+    if (!l) return;
+    for (int i = 0; i < kStages; ++i) {
+        if (l->stage[i]) cudaFree(l->stage[i]);
+        if (l->copied[i]) cudaEventDestroy(l->copied[i]);
+        if (l->consumed[i]) cudaEventDestroy(l->consumed[i]);
+    }
+    if (l->xbuf) cudaFree(l->xbuf);
+    if (l->d_flags) cudaFree(l->d_flags);
+    if (l->h_flags) cudaFreeHost(l->h_flags);
+    if (l->copy) cudaStreamDestroy(l->copy);
+    if (l->comp) cudaStreamDestroy(l->comp);
+    delete l;
+}
+
 int lane_create(int dev, Lane** out)
 {
     Lane* l = new (std::nothrow) Lane();
     if (!l) return FLAGSTAT_CUDA_ENOMEM;
     l->dev = dev;
-    CK(cudaStreamCreateWithFlags(&l->copy, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&l->comp, cudaStreamNonBlocking));
-    CK(cudaMalloc(&l->d_flags, 32 * sizeof(uint64_t)));
-    CK(cudaMallocHost(&l->h_flags, 32 * sizeof(uint64_t)));
+    auto build = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&l->copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&l->comp, cudaStreamNonBlocking));
+        CK(cudaMalloc(&l->d_flags, 32 * sizeof(uint64_t)));
+        // mapped: the one-launch path for short host blocks lets the kernel store the totals here
+        CK(cudaHostAlloc(&l->h_flags, 32 * sizeof(uint64_t), cudaHostAllocMapped));
+        CK(cudaMalloc(&l->xbuf, kXchgWords * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(l->xbuf, 0, kXchgWords * sizeof(unsigned long long), l->comp));
+        CK(cudaStreamSynchronize(l->comp));
+        return 0;
+    };
+    const int rc = build();
+    if (rc) {  // nothing may leak from a half-built lane
+        cudaGetLastError();
+        lane_destroy(l);
+        return rc;
+    }
     *out = l;
     return 0;
 }
@@ -400,14 +445,37 @@ int run_sync_impl(int mode, const uint16_t* array, uint64_t len, uint64_t* total
     // semantics a synchronous C call on a device pointer is expected to have).
     // Host input is ready by definition, so it uses the lane's private streams.
     cudaStream_t comp = (on_device && len) ? cudaStreamLegacy : l->comp;
-    CK(cudaMemsetAsync(l->d_flags, 0, 32 * sizeof(uint64_t), comp));
-    if (on_device || len == 0) {
-        rc = launch(mode, array, len, l->d_flags, comp);
+    const uint64_t chunk_rec = kChunkBytes / sizeof(uint16_t);
+    if (on_device || len <= chunk_rec) {
+        // ONE launch covers the call (device-resident input, or a host block of at most one
+        // staging chunk -- the reference's 512,000-record blocks, benchmark/flagstats.cpp:304-329):
+        // copy, then a launch in overwrite mode (world-1 exchange: the CTA that draws the last
+        // ticket stores the totals) straight into the lane's MAPPED host counters.  No memset,
+        // no device->host copy, no events: memcpy + launch + one synchronisation.
+        const uint16_t* src = array;
+        if (!on_device && len) {
+            rc = lane_ensure_staging(l);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(l->stage[0], array, len * sizeof(uint16_t), cudaMemcpyHostToDevice, comp));
+            src = l->stage[0];
+        }
+        uint64_t* d_host_flags = nullptr;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_host_flags), l->h_flags, 0));
+        XchgArgs xa;
+        std::memset(&xa, 0, sizeof(xa));
+        xa.buf[0] = l->xbuf;
+        xa.epoch = 1;
+        xa.world = 1;
+        rc = launch(mode, src, len, d_host_flags, comp, &xa);
         if (rc) return rc;
-    } else {
+        CK(cudaStreamSynchronize(comp));
+        std::memcpy(totals, l->h_flags, nout * sizeof(uint64_t));
+        return 0;
+    }
+    CK(cudaMemsetAsync(l->d_flags, 0, 32 * sizeof(uint64_t), comp));
+    {
         rc = lane_ensure_staging(l);
         if (rc) return rc;
-        const uint64_t chunk_rec = kChunkBytes / sizeof(uint16_t);
         uint64_t off = 0;
         for (uint64_t c = 0; off < len; ++c) {
             const int s = (int)(c % kStages);
@@ -511,6 +579,12 @@ struct FLAGSTAT_cuda_xchg {
     uint64_t epoch = 0;
     uint64_t timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     bool overlap = false;  // FLAGSTAT_cuda_xchg_set_overlap
+    // deferred collection: the epoch whose global counters the NEXT launch (or _collect) writes
+    uint64_t pending_epoch = 0;
+    uint64_t* pending_out = nullptr;
+    int pending_accumulate = 0;
+    int pending_nout = 0;
+    unsigned long long* h_err = nullptr;  // mapped pinned word: the kernel stores the epoch of a timeout
 };
 
 extern "C" {
@@ -866,6 +940,8 @@ int FLAGSTAT_cuda_xchg_create(FLAGSTAT_cuda_xchg** out, int rank, int world, voi
         CK(cudaGetDevice(&x->dev));
         CK(cudaMalloc(&x->mine, kXchgWords * sizeof(unsigned long long)));
         CK(cudaMemset(x->mine, 0, kXchgWords * sizeof(unsigned long long)));
+        CK(cudaHostAlloc(&x->h_err, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+        *x->h_err = 0ull;
         CK(cudaDeviceSynchronize());
         x->peer[rank] = x->mine;
         x->connected = world == 1;
@@ -882,6 +958,7 @@ int FLAGSTAT_cuda_xchg_create(FLAGSTAT_cuda_xchg** out, int rank, int world, voi
     if (rc) {  // nothing may leak from a half-built handle
         cudaGetLastError();
         if (x->mine) cudaFree(x->mine);
+        if (x->h_err) cudaFreeHost(x->h_err);
         delete x;
         return rc;
     }
@@ -946,25 +1023,50 @@ int FLAGSTAT_cuda_xchg_connect_local(FLAGSTAT_cuda_xchg** xs, int world)
     return 0;
 }
 
-static int xchg_launch(FLAGSTAT_cuda_xchg* x, int mode, const uint16_t* d_array, uint64_t len,
-                       uint64_t* d_out, int accumulate, void* stream)
+static int xchg_fill(FLAGSTAT_cuda_xchg* x, XchgArgs& xa)
 {
-    if (!x || !d_out || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
     if (!x->connected) return FLAGSTAT_CUDA_ESTATE;
+    // an exchange that timed out stays failed: the epoch-parity argument needs every rank to have
+    // completed every epoch.  All ranks destroy and recreate their handles (FLAGSTAT_cuda_xchg_status
+    // tells a time-out from this state).
+    if (*reinterpret_cast<volatile unsigned long long*>(x->h_err) != 0ull) return FLAGSTAT_CUDA_ESTATE;
     int cur = -1;
     CK(cudaGetDevice(&cur));
     if (cur != x->dev) return FLAGSTAT_CUDA_EINVAL;  // the caller launches on the handle's device
-    XchgArgs xa;
     std::memset(&xa, 0, sizeof(xa));
     for (int r = 0; r < x->world; ++r) xa.buf[r] = x->peer[r];
-    xa.epoch = x->epoch + 1;
     xa.timeout_ns = x->timeout_ns;
     xa.rank = x->rank;
     xa.world = x->world;
+    xa.prev_epoch = x->pending_epoch;
+    xa.prev_out = reinterpret_cast<unsigned long long*>(x->pending_out);
+    xa.prev_accumulate = x->pending_accumulate;
+    xa.prev_nout = x->pending_nout;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&xa.host_err), x->h_err, 0));
+    return 0;
+}
+
+static int xchg_launch(FLAGSTAT_cuda_xchg* x, int mode, const uint16_t* d_array, uint64_t len,
+                       uint64_t* d_out, int accumulate, void* stream, bool deferred = false)
+{
+    if (!x || !d_out || (!d_array && len)) return FLAGSTAT_CUDA_EINVAL;
+    XchgArgs xa;
+    int rc = xchg_fill(x, xa);
+    if (rc) return rc;
+    xa.epoch = x->epoch + 1;
     xa.accumulate = accumulate ? 1 : 0;
-    const int rc = launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa, x->overlap);
-    if (rc == 0) ++x->epoch;  // a launch that never happened must not consume an epoch
-    return rc;
+    xa.deferred = (deferred && x->world > 1) ? 1 : 0;  // one rank: nothing to wait for, written at once
+    rc = launch(mode, d_array, len, d_out, static_cast<cudaStream_t>(stream), &xa, x->overlap);
+    if (rc) return rc;  // a launch that never happened must not consume an epoch
+    ++x->epoch;
+    x->pending_epoch = 0;  // whatever was pending rides in this launch
+    if (xa.deferred) {
+        x->pending_epoch = x->epoch;
+        x->pending_out = d_out;
+        x->pending_accumulate = xa.accumulate;
+        x->pending_nout = mode == kPospopcnt ? 16 : 32;
+    }
+    return 0;
 }
 
 int FLAGSTAT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
@@ -983,6 +1085,26 @@ int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_dat
                                     uint64_t* d_out, int accumulate, void* stream)
 {
     return xchg_launch(x, kPospopcnt, d_data, len, d_out, accumulate, stream);
+}
+
+int FLAGSTAT_cuda_device_allreduce_deferred(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array, uint64_t len,
+                                            uint64_t* d_flags, int accumulate, void* stream)
+{
+    return xchg_launch(x, kFlagstat, d_array, len, d_flags, accumulate, stream, true);
+}
+
+int FLAGSTAT_cuda_xchg_collect(FLAGSTAT_cuda_xchg* x, void* stream)
+{
+    if (!x) return FLAGSTAT_CUDA_EINVAL;
+    if (x->pending_epoch == 0) return 0;
+    XchgArgs xa;
+    const int rc = xchg_fill(x, xa);
+    if (rc) return rc;
+    xchg_collect_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(xa);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    x->pending_epoch = 0;
+    return 0;
 }
 
 int FLAGSTAT_cuda_xchg_set_overlap(FLAGSTAT_cuda_xchg* x, int on)
@@ -1019,6 +1141,7 @@ int FLAGSTAT_cuda_xchg_destroy(FLAGSTAT_cuda_xchg* x)
         for (int r = 0; r < x->world; ++r)
             if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
     if (x->mine) cudaFree(x->mine);
+    if (x->h_err) cudaFreeHost(x->h_err);
     delete x;
     return 0;
 }
@@ -1149,30 +1272,35 @@ int FLAGSTAT_cuda_sync(void)
     return 0;
 }
 
+int FLAGSTAT_cuda_time_device_rot(const uint16_t* d_base, uint64_t len, uint64_t stride_records,
+                                  uint32_t n_rot, uint64_t* d_flags, int iters, int mode,
+                                  float* ms_per_launch)
+{
+    if (!d_flags || !ms_per_launch || iters <= 0 || n_rot == 0) return FLAGSTAT_CUDA_EINVAL;
+    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
+    const int m = mode == 2 ? kSamtools : mode ? kPospopcnt : kFlagstat;
+    TimerPair t;
+    CK(cudaStreamCreateWithFlags(&t.st, cudaStreamNonBlocking));
+    t.own_stream = true;
+    CK(cudaEventCreate(&t.e0));
+    CK(cudaEventCreate(&t.e1));
+    int rc = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(t.e0, t.st));
+    for (int i = 0; i < iters && rc == 0; ++i)
+        rc = launch(m, d_base + (uint64_t)((uint32_t)i % n_rot) * stride_records, len, d_flags, t.st);
+    CK(cudaEventRecord(t.e1, t.st));
+    CK(cudaStreamSynchronize(t.st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    *ms_per_launch = ms / (float)iters;
+    return rc;
+}
+
 int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d_flags, int iters,
                               int pospopcnt_mode, float* ms_per_launch)
 {
-    if (!d_flags || !ms_per_launch || iters <= 0) return FLAGSTAT_CUDA_EINVAL;
-    if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
-    cudaStream_t st;
-    cudaEvent_t e0, e1;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    int rc = 0;
-    CK(cudaDeviceSynchronize());
-    CK(cudaEventRecord(e0, st));
-    for (int i = 0; i < iters && rc == 0; ++i)
-        rc = launch(pospopcnt_mode == 2 ? kSamtools : pospopcnt_mode ? kPospopcnt : kFlagstat, d_array, len, d_flags, st);
-    CK(cudaEventRecord(e1, st));
-    CK(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    *ms_per_launch = ms / (float)iters;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaStreamDestroy(st);
-    return rc;
+    return FLAGSTAT_cuda_time_device_rot(d_array, len, 0, 1, d_flags, iters, pospopcnt_mode, ms_per_launch);
 }
 
 // Read-only HBM probe: the same bytes through LDG.128 with one XOR per 16 bytes and no
@@ -1196,25 +1324,40 @@ int FLAGSTAT_cuda_read_probe(const void* d_bytes, uint64_t n_bytes, int iters, f
         Lane* l;
         ~Release() { lane_release(l); }
     } rel{l};
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    TimerPair t;
+    CK(cudaEventCreate(&t.e0));
+    CK(cudaEventCreate(&t.e1));
     CK(cudaDeviceSynchronize());
-    CK(cudaEventRecord(e0, l->comp));
+    CK(cudaEventRecord(t.e0, l->comp));
     for (int i = 0; i < iters; ++i)
         hbm_read_probe_kernel<<<di->sms * 4, kThreads, 0, l->comp>>>(
             static_cast<const uint4*>(d_bytes), n_bytes / 16u,
             reinterpret_cast<unsigned long long*>(l->d_flags));
-    CK(cudaEventRecord(e1, l->comp));
+    CK(cudaEventRecord(t.e1, l->comp));
     CK(cudaStreamSynchronize(l->comp));
     CK(cudaGetLastError());
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventElapsedTime(&ms, t.e0, t.e1));
     *ms_per_launch = ms / (float)iters;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return 0;
 }
+
+#ifdef FSB_TIMELINE
+// probe build only (tools/timeline_probe.py): the per-CTA time stamps of the last group-kernel launch
+int FLAGSTAT_cuda_timeline_fetch(unsigned long long* out, int n_words)
+{
+    if (!out || n_words <= 0 || n_words > 8 * 2048) return FLAGSTAT_CUDA_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, fsb200::g_timeline, (size_t)n_words * sizeof(unsigned long long)));
+    return 0;
+}
+int FLAGSTAT_cuda_timeline_clear(void)
+{
+    static unsigned long long zeros[8 * 2048];
+    CK(cudaMemcpyToSymbol(fsb200::g_timeline, zeros, sizeof(zeros)));
+    return 0;
+}
+#endif
 
 }  // extern "C"
 

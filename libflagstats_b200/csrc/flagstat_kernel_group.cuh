@@ -268,6 +268,18 @@ __device__ __forceinline__ void lds128_imm(uint32_t smem, uint32_t& a, uint32_t&
                  : "r"(smem), "n"(OFF));
 }
 
+// Timeline probe (tools/timeline_probe.py builds a second .so with -DFSB_TIMELINE; never in the
+// product build): thread 0 of every CTA stamps %globaltimer at five points of its life.
+#ifdef FSB_TIMELINE
+__device__ unsigned long long g_timeline[8 * 2048];
+#define FSB_TL(k)                                                                      \
+    do {                                                                               \
+        if (threadIdx.x == 0 && blockIdx.x < 2048u) g_timeline[blockIdx.x * 8u + (k)] = global_timer_ns(); \
+    } while (0)
+#else
+#define FSB_TL(k) do { } while (0)
+#endif
+
 template <int MODE, int VARIANT, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
@@ -276,6 +288,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
     constexpr int DEPTH = 4;  // ring depth == group size
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_launch_dependents();  // overlapped launches: the next kernel may take SM slots as they free up
+    FSB_TL(0);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t addr = reinterpret_cast<uint64_t>(base);
@@ -357,6 +370,11 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
     fetch(P1{});
     fetch(P2{});
     fetch(P3{});
+    FSB_TL(1);
+#ifdef FSB_TIMELINE
+    cp_async_wait<DEPTH - 1>();  // (probe only) when does the first stage land?
+    FSB_TL(2);
+#endif
 
     // One flush site: every pass of the outer loop is one epoch (at most kMaxGroups
     // groups); the ragged last group (my % 4 batches) rides in the last epoch with room.
@@ -389,14 +407,17 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
             st.close();
             rem_done = true;
         }
+        FSB_TL(3);
         acc_all += st.all.flush_warp(lane);
         if (MODE != kPospopcnt && st.fail_dirty) acc_fail += st.fail.flush_warp(lane);
         st.clear();
         groups = 0;
     } while (g < ngroups || !rem_done);
     cp_async_wait<0>();
+    FSB_TL(4);
 
     cta_epilogue<MODE>(out, acc_all, acc_fail, n, warp, lane, true, xa);
+    FSB_TL(5);
 }
 
 }  // namespace fsb200

@@ -412,6 +412,17 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 // The exchange is 256 bytes per peer and overlaps the tail of the slower ranks'
 // kernels; there is no separate collective launch.
 //
+// Deferred collection (FLAGSTAT_cuda_device_allreduce_deferred) splits step 3 off: a launch
+// only does 1-2 for its own epoch, and FIRST finishes step 3 of the epoch its predecessor on
+// the handle left pending (or FLAGSTAT_cuda_xchg_collect does, as a one-warp kernel).  A rank
+// then never waits for the peers' CURRENT step, only for their previous one: it may run one
+// whole step ahead of the slowest rank, so per-step jitter between GPUs no longer adds up
+// (with step 3 in the same launch every step ends with the slowest rank of THAT step).  The
+// parity double buffer is still sufficient: rank r overwrites slot [e & 1] with epoch e + 2
+// only after it has collected e + 1, and a peer raises its flag for e + 1 only after it has
+// collected (i.e. finished reading) e.  tests/test_exchange_protocol_model.py runs both
+// orders, and mixtures of them, under every interleaving.
+//
 // Overlapped steps (opt-in, FLAGSTAT_cuda_xchg_set_overlap): the launch carries the
 // programmatic-stream-serialization attribute, every CTA executes
 // griddepcontrol.launch_dependents at its start and griddepcontrol.wait only at the top
@@ -443,6 +454,16 @@ struct XchgArgs {
     int rank;
     int world;                           // 0 = no exchange: plain accumulate into out
     int accumulate;                      // 1: out[i] += total, 0: out[i] = total
+    // Deferred collection (FLAGSTAT_cuda_device_allreduce_deferred): this launch only PUSHES its
+    // totals; the launch (or FLAGSTAT_cuda_xchg_collect) that follows waits for the peers' totals
+    // of this epoch and writes the global counters.  A launch therefore first collects the epoch
+    // its predecessor left pending, then pushes its own.
+    int deferred;                        // 1: push only
+    int prev_accumulate;
+    int prev_nout;                       // 16 / 32 counters pending
+    unsigned long long prev_epoch;       // != 0: collect this epoch into prev_out first
+    unsigned long long* prev_out;
+    unsigned long long* host_err;        // mapped host word, receives the epoch of a timeout (may be null)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
@@ -481,6 +502,46 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
+// Wait (all lanes of one warp) until every rank's totals of epoch `e` have landed in this rank's
+// buffer, add them and write `nout` global counters to dst.  false = a peer never delivered
+// (or the exchange had already failed): dst untouched, error recorded here, on the host and on
+// every peer, so that nobody keeps waiting for a rank that has given up.
+__device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ dst, uint32_t lane,
+                                             const XchgArgs& xa, unsigned long long e, int accumulate,
+                                             uint32_t nout)
+{
+    unsigned long long* mine = xa.buf[xa.rank];
+    const int world = xa.world;
+    const uint32_t par = (uint32_t)(e & 1ull);
+    bool ok = true;
+    if ((int)lane < world) {
+        const unsigned long long* f = mine + kXchgFlags + par * kMaxRanks + lane;
+        const unsigned long long t0 = global_timer_ns();
+        uint32_t spins = 0;
+        while (ld_acquire_sys(f) != e) {
+            if ((++spins & 63u) == 0u &&
+                (global_timer_ns() - t0 > xa.timeout_ns || ld_relaxed_sys(mine + kXchgErr) != 0ull)) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if ((int)lane < world) st_relaxed_sys(xa.buf[lane] + kXchgErr, e);  // own buffer included
+        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, e);
+        __threadfence_system();
+        return false;
+    }
+    __threadfence_system();
+    if (lane < nout) {
+        unsigned long long v = 0ull;
+        for (int r = 0; r < world; ++r)
+            v += ld_relaxed_sys(mine + kXchgSlots + (par * kMaxRanks + (uint32_t)r) * kXchgSlotWords + lane);
+        dst[lane] = accumulate ? dst[lane] + v : v;
+    }
+    return true;
+}
+
 // Executed by warp 0 of the CTA that drew the last ticket of a launch.
 template <int MODE>
 __device__ __noinline__ void xchg_last_cta(unsigned long long* __restrict__ out, uint32_t lane,
@@ -493,37 +554,40 @@ __device__ __noinline__ void xchg_last_cta(unsigned long long* __restrict__ out,
     if (lane < kOut) v = atomicExch(mine + kXchgAcc + lane, 0ull);
     if (lane == 0) atomicExch(mine + kXchgTicket, 0ull);
     const int world = xa.world;
-    if (world > 1) {
-        const uint32_t par = (uint32_t)(xa.epoch & 1ull);
-        const uint32_t slot = kXchgSlots + (par * kMaxRanks + (uint32_t)xa.rank) * kXchgSlotWords;
-        for (int r = 0; r < world; ++r)
-            if (lane < kOut) st_relaxed_sys(xa.buf[r] + slot + lane, v);
-        __threadfence_system();
-        __syncwarp();
-        if ((int)lane < world)
-            st_release_sys(xa.buf[lane] + kXchgFlags + par * kMaxRanks + (uint32_t)xa.rank, xa.epoch);
-        bool ok = true;
-        if ((int)lane < world) {
-            const unsigned long long* f = mine + kXchgFlags + par * kMaxRanks + lane;
-            const unsigned long long t0 = global_timer_ns();
-            while (ld_acquire_sys(f) != xa.epoch) {
-                if (global_timer_ns() - t0 > xa.timeout_ns) {
-                    ok = false;
-                    break;
-                }
-            }
-        }
-        if (!__all_sync(0xffffffffu, ok)) {
-            if (lane == 0) atomicExch(mine + kXchgErr, xa.epoch);
-            return;  // out[] is left untouched on failure
-        }
-        __threadfence_system();
-        v = 0ull;
-        if (lane < kOut)
-            for (int r = 0; r < world; ++r)
-                v += ld_relaxed_sys(mine + kXchgSlots + (par * kMaxRanks + (uint32_t)r) * kXchgSlotWords + lane);
+    if (world <= 1) {
+        if (lane < kOut) out[lane] = xa.accumulate ? out[lane] + v : v;
+        return;
     }
-    if (lane < kOut) out[lane] = xa.accumulate ? out[lane] + v : v;
+    // a failed exchange stays failed (the parity argument needs every rank to have completed
+    // every epoch): nothing more is pushed or written, the host reports ESTATE / ETIMEOUT
+    if (const unsigned long long err = ld_relaxed_sys(mine + kXchgErr)) {
+        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, err);  // a peer's give-up reaches this host too
+        return;
+    }
+    // 1. the epoch the previous launch left pending: its readers must be done with the slots
+    //    of parity (epoch & 1) before step 2 overwrites them with epoch's own totals -- they are,
+    //    because a peer raises its flag for prev_epoch + 1 = epoch only after ITS step 1
+    if (xa.prev_epoch != 0ull &&
+        !xchg_collect(xa.prev_out, lane, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout))
+        return;
+    // 2. push this launch's totals to every rank, then raise the flags
+    const uint32_t par = (uint32_t)(xa.epoch & 1ull);
+    const uint32_t slot = kXchgSlots + (par * kMaxRanks + (uint32_t)xa.rank) * kXchgSlotWords;
+    for (int r = 0; r < world; ++r)
+        if (lane < kOut) st_relaxed_sys(xa.buf[r] + slot + lane, v);
+    __threadfence_system();
+    __syncwarp();
+    if ((int)lane < world)
+        st_release_sys(xa.buf[lane] + kXchgFlags + par * kMaxRanks + (uint32_t)xa.rank, xa.epoch);
+    // 3. unless deferred: wait for the peers' totals of this very epoch
+    if (!xa.deferred) xchg_collect(out, lane, xa, xa.epoch, xa.accumulate, kOut);
+}
+
+// FLAGSTAT_cuda_xchg_collect: the pending epoch of a deferred launch, on its own (one warp)
+__global__ void xchg_collect_kernel(const __grid_constant__ XchgArgs xa)
+{
+    if (xa.world > 1 && xa.prev_epoch != 0ull && ld_relaxed_sys(xa.buf[xa.rank] + kXchgErr) == 0ull)
+        xchg_collect(xa.prev_out, threadIdx.x, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout);
 }
 
 // Common tail of every kernel variant: CTA reduction of the per-warp position

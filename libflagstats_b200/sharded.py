@@ -91,6 +91,7 @@ class FusedExchange:
         self.world = dist.get_world_size(group) if have_pg else 1
         self.rank = dist.get_rank(group) if have_pg else 0
         self._h = C.c_void_p()
+        self._pending_out = None
         handle = (C.c_ubyte * 64)()
         with torch.cuda.device(self.device):
             check(self._lib.FLAGSTAT_cuda_xchg_create(C.byref(self._h), self.rank, self.world,
@@ -118,12 +119,15 @@ class FusedExchange:
         return bool(self._lib.FLAGSTAT_cuda_xchg_set_overlap(self._h, 1 if on else 0))
 
     def flagstat(self, local_values, out=None, accumulate: bool = False, stream=None,
-                 pospopcnt: bool = False, samtools: bool = False):
+                 pospopcnt: bool = False, samtools: bool = False, deferred: bool = False):
         """Count this rank's shard and return the GLOBAL counters in `out`
         (int64[32] CUDA tensor, or [16] for pospopcnt) on every rank.  One
         kernel launch; asynchronous with respect to the host.  Collective.
         ``samtools``: also the exact n_pair_all in slots 0 / 16
-        (FLAGSTAT_cuda_samtools_device_allreduce)."""
+        (FLAGSTAT_cuda_samtools_device_allreduce).
+        ``deferred`` (flagstat mode): FLAGSTAT_cuda_device_allreduce_deferred -- the launch
+        pushes this rank's totals but does not wait for the peers'; `out` is written by the
+        next ``flagstat`` call on this handle or by ``collect()`` (keep it alive until then)."""
         import torch
 
         from . import _device_view, _stream_ptr
@@ -138,13 +142,31 @@ class FusedExchange:
             stream = torch.cuda.current_stream(local_values.device)
         if pospopcnt and samtools:
             raise ValueError("pospopcnt and samtools are different modes")
+        if deferred and (pospopcnt or samtools):
+            raise ValueError("deferred collection is available for the flagstat mode only")
         fn = (self._lib.POSPOPCNT_cuda_device_allreduce if pospopcnt
               else self._lib.FLAGSTAT_cuda_samtools_device_allreduce if samtools
+              else self._lib.FLAGSTAT_cuda_device_allreduce_deferred if deferred
               else self._lib.FLAGSTAT_cuda_device_allreduce)
+        if deferred:
+            self._pending_out = out  # keeps the tensor alive until it has been written
         with torch.cuda.device(local_values.device):
             self._check(fn(self._h, ptr, n, out.data_ptr(), 1 if accumulate else 0,
                            _stream_ptr(stream)), "FLAGSTAT_cuda_device_allreduce")
         return out
+
+    def collect(self, stream=None) -> None:
+        """FLAGSTAT_cuda_xchg_collect: write the counters of the last deferred call (a one-warp
+        kernel on `stream`, which must be ordered after that call).  Collective."""
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        from . import _stream_ptr
+
+        with torch.cuda.device(self.device):
+            self._check(self._lib.FLAGSTAT_cuda_xchg_collect(self._h, _stream_ptr(stream)),
+                        "FLAGSTAT_cuda_xchg_collect")
 
     def status(self) -> None:
         """Synchronise and raise if a peer never delivered its counters."""

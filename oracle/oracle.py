@@ -319,6 +319,14 @@ def reference():
     lib.ref_flagstat_mt.argtypes = [C.c_char_p, _u16p, C.c_uint64, C.c_int, _u64p,
                                     C.POINTER(C.c_double)]
     lib.ref_flagstat_mt.restype = C.c_int
+    if hasattr(lib, "ref_pospopcnt_mt"):
+        lib.ref_pospopcnt_mt.argtypes = [_u16p, C.c_uint64, C.c_int, _u64p, C.POINTER(C.c_double)]
+        lib.ref_pospopcnt_mt.restype = C.c_int
+        lib.ref_codec_available.argtypes = [C.c_int]
+        lib.ref_codec_available.restype = C.c_int
+        lib.ref_container_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.ref_container_mt.restype = C.c_int
     if hasattr(lib, "ref_samtools_loop"):
         lib.ref_samtools_loop.argtypes = [_u16p, C.c_uint64, C.POINTER(C.c_longlong)]
         lib.ref_samtools_loop.restype = C.c_int
@@ -409,6 +417,43 @@ def ref_flagstat_mt(name: str, a, nthreads: int):
     if rc != 0:
         raise RuntimeError(f"reference kernel {name!r}: rc={rc}")
     return f, sec.value
+
+
+def ref_pospopcnt_mt(a, nthreads: int):
+    """(out u64[16], seconds): STORM_pospopcnt_u16 over contiguous ranges on pthreads."""
+    lib = reference()
+    a = _as_u16(a)
+    out = np.zeros(16, np.uint64)
+    sec = C.c_double(0.0)
+    rc = lib.ref_pospopcnt_mt(_ptr(a, _u16p), a.size, nthreads, _ptr(out, _u64p), C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"ref_pospopcnt_mt: rc={rc}")
+    return out, sec.value
+
+
+REF_CODECS = {"lz4": 0, "zstd": 1}
+
+
+def ref_container_available(codec: str) -> bool:
+    lib = reference()
+    return bool(lib is not None and hasattr(lib, "ref_container_mt")
+                and lib.ref_codec_available(REF_CODECS[codec]))
+
+
+def ref_container_mt(blob, codec: str, nthreads: int):
+    """The reference's block loop (benchmark/flagstats.cpp:311-331 LZ4, 655-669 Zstd:
+    system codec, then FLAGSTATS_get_function(N) per block) over a container in memory.
+    Returns (flags u64[32], n_records, seconds, decode_seconds)."""
+    lib = reference()
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    f = np.zeros(32, np.uint64)
+    n = C.c_uint64(0)
+    sec, dec = C.c_double(0.0), C.c_double(0.0)
+    rc = lib.ref_container_mt(buf.ctypes.data, buf.size, REF_CODECS[codec], nthreads, _ptr(f, _u64p),
+                              C.byref(n), C.byref(sec), C.byref(dec))
+    if rc != 0:
+        raise RuntimeError(f"ref_container_mt({codec}): rc={rc}")
+    return f, int(n.value), sec.value, dec.value
 
 
 def best_reference_kernel() -> Optional[str]:

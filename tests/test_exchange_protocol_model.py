@@ -1,5 +1,5 @@
 """Exhaustive interleaving check of the fused counter-exchange protocol
-(libflagstats_b200/csrc/flagstat_kernels.cuh, xchg_last_cta): every rank's last CTA
+(libflagstats_b200/csrc/flagstat_kernels.cuh, xchg_last_cta / xchg_collect): every rank's last CTA
 
     push   slot[peer][epoch & 1][me] = my totals        one store per peer
     flag   flag[peer][epoch & 1][me] = epoch            one release-store per peer
@@ -24,27 +24,52 @@ import sys
 import pytest
 
 
-def _programs(world, epochs, buffers):
-    """Per rank: a list of atomic steps (op, peer, epoch, buffer index)."""
+def _programs(world, epochs, buffers, modes=None, collect_first=True):
+    """Per rank: a list of atomic steps (op, peer, epoch, buffer index).
+
+    modes: one letter per epoch, "i" = immediate (push, flag, wait, read in the same launch,
+    FLAGSTAT_cuda_device_allreduce) or "d" = deferred (push and flag only; the NEXT launch --
+    or the trailing collect -- waits for and reads this epoch BEFORE it pushes its own,
+    FLAGSTAT_cuda_device_allreduce_deferred / FLAGSTAT_cuda_xchg_collect).  collect_first=False
+    models the wrong order (push own totals first, then collect the pending epoch)."""
+    modes = modes or "i" * epochs
+    assert len(modes) == epochs
     progs = []
     for me in range(world):
         steps = []
+        pending = None
+
+        def collect(e):
+            steps.append(("wait", None, e, e % buffers))
+            for r in range(world):
+                steps.append(("read", r, e, e % buffers))
+
         for e in range(1, epochs + 1):
             b = e % buffers
+            steps.append(("work", None, e, b))  # counting the shard: no communication
+            if pending is not None and collect_first:
+                collect(pending)
+                pending = None
             for r in range(world):
                 steps.append(("push", r, e, b))
             for r in range(world):
                 steps.append(("flag", r, e, b))
-            steps.append(("wait", None, e, b))
-            for r in range(world):
-                steps.append(("read", r, e, b))
+            if pending is not None:
+                collect(pending)
+                pending = None
+            if modes[e - 1] == "i":
+                collect(e)
+            else:
+                pending = e
+        if pending is not None:
+            collect(pending)
         progs.append(steps)
     return progs
 
 
-def _explore(world, epochs, buffers):
+def _explore(world, epochs, buffers, modes=None, collect_first=True):
     """Returns (states visited, first violation or None, deadlocked?)."""
-    progs = _programs(world, epochs, buffers)
+    progs = _programs(world, epochs, buffers, modes, collect_first)
     # memory: slot[owner][buffer][writer] = epoch whose data it holds; flag likewise
     zero = tuple(tuple(tuple(0 for _ in range(world)) for _ in range(buffers)) for _ in range(world))
     start = (tuple(0 for _ in range(world)), zero, zero)
@@ -52,6 +77,15 @@ def _explore(world, epochs, buffers):
     stack = [start]
     violation = None
     deadlock = False
+    # work[me][pc] = shards rank `me` has finished counting when its program counter is pc
+    work = []
+    for prog in progs:
+        acc, done_work = [0], 0
+        for st in prog:
+            done_work += st[0] == "work"
+            acc.append(done_work)
+        work.append(acc)
+    _explore.max_lead = 0
 
     def put(mem, owner, b, writer, v):
         o = list(mem)
@@ -64,6 +98,8 @@ def _explore(world, epochs, buffers):
 
     while stack:
         pcs, slot, flag = stack.pop()
+        w = [work[me][pcs[me]] for me in range(world)]
+        _explore.max_lead = max(_explore.max_lead, max(w) - min(w))
         moved = False
         done = True
         for me in range(world):
@@ -73,7 +109,9 @@ def _explore(world, epochs, buffers):
             done = False
             op, r, e, b = progs[me][pc]
             nslot, nflag = slot, flag
-            if op == "push":
+            if op == "work":
+                pass
+            elif op == "push":
                 nslot = put(slot, r, b, me, e)
             elif op == "flag":
                 nflag = put(flag, r, b, me, e)
@@ -119,6 +157,40 @@ def test_three_buffers_are_not_needed():
     s2, v2, _ = _explore(2, 4, buffers=2)
     s3, v3, _ = _explore(2, 4, buffers=3)
     assert v2 is None and v3 is None and s3 >= s2
+
+
+@pytest.mark.parametrize("world,modes", [(2, "ddddd"), (3, "ddd"), (2, "didid"), (2, "ddiid"), (2, "iddii"), (3, "did")])
+def test_deferred_collection_is_safe_under_every_interleaving(world, modes):
+    """Deferred collection: a launch pushes only, its successor first collects the pending epoch and
+    then pushes.  A rank may now be one whole epoch ahead of a peer; parity double buffering
+    still suffices because a rank overwrites the slots of parity (e & 1) with epoch e + 2 only
+    after it has collected e + 1, and a peer raises its flag for e + 1 only after it has
+    collected e.  All-deferred, and every mixture with immediate calls."""
+    states, violation, deadlock = _explore(world, len(modes), buffers=2, modes=modes)
+    assert violation is None, f"rank {violation[0]} read epoch {violation[3]} of rank {violation[1]} in epoch {violation[2]}"
+    assert not deadlock
+    assert states > 300
+
+
+def test_deferred_lets_a_rank_run_one_epoch_ahead():
+    """What the deferred order buys.  With the wait in the same launch a rank can have counted at
+    most ONE shard more than the slowest rank (it cannot leave epoch e before every peer has
+    pushed e); deferred, it may have counted TWO more (its epoch e + 1 shard is done while a
+    peer is still counting e: only the push of e + 1 waits for that peer's push of e).  That is
+    the slack which keeps per-step jitter between GPUs off the critical path."""
+    _explore(2, 4, buffers=2, modes="iiii")
+    lead_i = _explore.max_lead
+    _explore(2, 4, buffers=2, modes="dddd")
+    lead_d = _explore.max_lead
+    assert (lead_i, lead_d) == (1, 2)
+
+
+def test_the_checker_finds_the_wrong_order_of_deferred_collection():
+    """Pushing one's own totals BEFORE collecting the pending epoch breaks the argument: the
+    flag for e + 1 no longer implies that e has been read, so a fast peer can overwrite
+    parity (e & 1) with e + 2 under a slow reader's nose.  The checker must see it."""
+    _, violation, deadlock = _explore(2, 5, buffers=2, modes="ddddd", collect_first=False)
+    assert violation is not None or deadlock
 
 
 if __name__ == "__main__":

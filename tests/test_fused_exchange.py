@@ -48,6 +48,12 @@ def test_world1_overwrite_and_accumulate(cuda_lib):
     out = x.flagstat(d, samtools=True)
     assert out.cpu().numpy().view(np.uint64).tolist() == want.tolist()
     assert sharded.flagstat_sharded(d, samtools=True).cpu().numpy().view(np.uint64).tolist() == want.tolist()
+    # one rank: a deferred call has nobody to wait for and writes at once; collect is a no-op
+    out = torch.full((32,), 7, dtype=torch.int64, device="cuda")
+    x.flagstat(d, out=out, deferred=True)
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().view(np.uint64).tolist() == O.flagstat_simd(a).tolist()
+    x.collect()
     x.status()
     x.close()
 
@@ -130,6 +136,27 @@ def _worker(rank, world, port, n, reps, q):
             x.flagstat(local, out=acc2, accumulate=True, stream=side)
     side.synchronize()
     same_ov = all(torch.equal(o, outs[0]) for o in ov) and torch.equal(acc2, outs[0] * reps)
+    # deferred collection (push only; the next call or collect() writes the counters), still
+    # overlapped and skewed, mixed with immediate calls and a collect in the middle
+    dv = []
+    with torch.cuda.stream(side):
+        acc3 = torch.zeros(32, dtype=torch.int64, device=f"cuda:{rank}")
+        for i in range(reps):
+            if i % 3 == (rank + 1) % 3:
+                torch.cuda._sleep(1_500_000)
+            o = torch.full((32,), -1, dtype=torch.int64, device=f"cuda:{rank}")
+            x.flagstat(local, out=o, stream=side, deferred=True)
+            dv.append(o)
+            x.flagstat(local, out=acc3, accumulate=True, stream=side, deferred=True)
+            if i == reps // 2:
+                x.collect(stream=side)
+            if i % 5 == 4:
+                o2 = torch.full((32,), -1, dtype=torch.int64, device=f"cuda:{rank}")
+                x.flagstat(local, out=o2, stream=side)  # immediate: collects the pending one first
+                dv.append(o2)
+        x.collect(stream=side)
+    side.synchronize()
+    same_ov = same_ov and all(torch.equal(o, outs[0]) for o in dv) and torch.equal(acc3, outs[0] * reps)
     x.set_overlap(False)
     x.status()
     same = all(torch.equal(o, outs[0]) for o in outs) and same_ov
@@ -202,6 +229,21 @@ def test_ranks_in_one_process_peer_access(cuda_lib):
         torch.cuda.synchronize(r)
         assert outs[r].cpu().numpy().view(np.uint64).tolist() == want, r
         cuda_lib.check(lib.FLAGSTAT_cuda_xchg_status(hs[r]), "status")
+    # deferred collection: three pushes per rank, each collected by the next call, the last by _collect
+    acc = [torch.zeros(32, dtype=torch.int64, device=f"cuda:{r}") for r in range(world)]
+    for rep in range(3):
+        for r in range(world):
+            with torch.cuda.device(r):
+                st = torch.cuda.current_stream(r).cuda_stream
+                cuda_lib.check(lib.FLAGSTAT_cuda_device_allreduce_deferred(
+                    hs[r], shards[r].data_ptr(), shards[r].numel(), acc[r].data_ptr(), 1, st), "deferred")
+    for r in range(world):
+        with torch.cuda.device(r):
+            cuda_lib.check(lib.FLAGSTAT_cuda_xchg_collect(hs[r], torch.cuda.current_stream(r).cuda_stream), "collect")
+    for r in range(world):
+        torch.cuda.synchronize(r)
+        assert acc[r].cpu().numpy().view(np.uint64).tolist() == [3 * v for v in want], r
+        cuda_lib.check(lib.FLAGSTAT_cuda_xchg_status(hs[r]), "status")
     for r in range(world):
         lib.FLAGSTAT_cuda_xchg_destroy(hs[r])
 
@@ -230,5 +272,17 @@ def test_missing_peer_times_out_instead_of_hanging(cuda_lib):
         torch.cuda.synchronize(0)
         assert lib.FLAGSTAT_cuda_xchg_status(hs[0]) == -5
         assert out.cpu().tolist() == [-5] * 32
+        # the failure is sticky: the handle refuses further collectives (ESTATE) until recreated
+        assert lib.FLAGSTAT_cuda_device_allreduce(
+            hs[0], d.data_ptr(), d.numel(), out.data_ptr(), 0, torch.cuda.current_stream(0).cuda_stream) == -4
+    # ... and the rank that gave up told its peer: rank 1 does not wait for a partner that is gone
+    with torch.cuda.device(1):
+        d1 = synth.uniform_device(100_000, 0, 1, 0x0FFF, device="cuda:1")
+        out1 = torch.full((32,), -7, dtype=torch.int64, device="cuda:1")
+        rc = lib.FLAGSTAT_cuda_device_allreduce(
+            hs[1], d1.data_ptr(), d1.numel(), out1.data_ptr(), 0, torch.cuda.current_stream(1).cuda_stream)
+        torch.cuda.synchronize(1)
+        assert rc == 0 and lib.FLAGSTAT_cuda_xchg_status(hs[1]) == -5
+        assert out1.cpu().tolist() == [-7] * 32
     for r in range(2):
         lib.FLAGSTAT_cuda_xchg_destroy(hs[r])
