@@ -171,6 +171,114 @@ def cpu_reference_run(sample_records: int, steps: int, warmup: int, threads: int
     }
 
 
+def cpu_baseline_set(threads: int, n: int = 100_000_000) -> dict:
+    """BASELINE.md section 4 / benchmark/inmemory.cpp:59-102,108-116: the reference's kernels on
+    n records U(0,4095), each at 1 thread (what the reference ships) and on all host cores
+    (our pthread range wrapper around the unmodified kernels).  Best of a few runs, steady_clock
+    inside the shim (the reference's own timer wraps at 65 ms, inmemory.cpp:134)."""
+    from oracle import oracle as O
+
+    if O.reference() is None:
+        return {"unavailable": "oracle/_ref was not prebuilt"}
+    a = O.synth_uniform(0, n, 0, 0x0FFF)
+    want = None
+    out = {"records": n, "input": "U(0,4095) index hash (benchmark/generate.cpp:11 distribution)", "threads_all": threads,
+           "kernels": {}}
+    runnable = set(O.ref_kernels())
+    for k in ("scalar", "avx2", "avx512", "avx512_improved3"):
+        if k not in runnable:
+            out["kernels"][k] = None
+            continue
+        m1 = n // 10 if k == "scalar" else n  # the branchy scalar loop takes ~25 ns/record on uniform flags
+        one = min(O.ref_flagstat_mt(k, a[:m1], 1)[1] for _ in range(2 if k == "scalar" else 3))
+        f, _ = O.ref_flagstat_mt(k, a, threads)
+        alls = min(O.ref_flagstat_mt(k, a, threads)[1] for _ in range(4))
+        if want is None:
+            want = [int(f[i]) for i in O.CORE20 if i != 9]
+        out["kernels"][k] = {
+            "one_thread_grec_s": m1 / one / 1e9, "one_thread_records": m1,
+            "all_cores_grec_s": n / alls / 1e9, "all_cores_gbs": 2 * n / alls / 1e9,
+            "agrees_with_scalar_on_core19": [int(f[i]) for i in O.CORE20 if i != 9] == want,
+        }
+    if hasattr(O.reference(), "ref_pospopcnt_mt"):
+        one = min(O.ref_pospopcnt_mt(a, 1)[1] for _ in range(3))
+        alls = min(O.ref_pospopcnt_mt(a, threads)[1] for _ in range(4))
+        out["kernels"]["STORM_pospopcnt_u16"] = {"one_thread_grec_s": n / one / 1e9, "one_thread_records": n,
+                                                 "all_cores_grec_s": n / alls / 1e9, "all_cores_gbs": 2 * n / alls / 1e9}
+    out["dispatched_by_FLAGSTATS_get_function"] = O.best_reference_kernel()
+    return out
+
+
+def cpu_file_reference(col, blobs: dict, threads: int) -> dict:
+    """The reference's readers of its own FLAG files on this host (benchmark/flagstats.cpp:288-358 LZ4,
+    :636-676 Zstd, :415-468 raw): the system codec per block, then the kernel
+    FLAGSTATS_get_function(N) returns -- as shipped (1 thread, timed on the first blocks only) and with
+    the blocks dealt to all cores.  Returns per file {counters, grec_s_1thread, grec_s_all_cores}."""
+    from oracle import oracle as O
+
+    res = {}
+    if O.reference() is None or not hasattr(O.reference(), "ref_container_mt"):
+        return res
+    kernel = O.best_reference_kernel()
+    sample = col[: min(col.size, 100 * 512_000)]
+    one = min(O.ref_flagstat_mt(kernel, sample, 1)[1] for _ in range(2))
+    f, _ = O.ref_flagstat_mt(kernel, col, threads)
+    alls = min(O.ref_flagstat_mt(kernel, col, threads)[1] for _ in range(3))
+    res["raw"] = {"counters": [int(x) for x in f], "grec_s_1thread": sample.size / one / 1e9,
+                  "grec_s_all_cores": col.size / alls / 1e9, "kernel": kernel,
+                  "note": "kernel over the column in memory (the file read of flagstats.cpp:415-468 not included)"}
+    for name, (codec, blob) in blobs.items():
+        if not O.ref_container_available(codec):
+            continue
+        head = bytes(blob[: _container_prefix(blob, 100)])
+        f1, n1, s1, d1 = O.ref_container_mt(head, codec, 1)
+        fa, na, sa, da = O.ref_container_mt(blob, codec, threads)
+        sa = min([sa] + [O.ref_container_mt(blob, codec, threads)[2] for _ in range(2)])
+        res[name] = {"counters": [int(x) for x in fa], "grec_s_1thread": n1 / s1 / 1e9,
+                     "decode_share_1thread": d1 / s1, "grec_s_all_cores": na / sa / 1e9, "kernel": kernel}
+    return res
+
+
+def _container_prefix(blob, n_blocks: int) -> int:
+    """Byte length of the first n_blocks [int32 raw][int32 comp][payload] records."""
+    import struct
+    pos = 0
+    for _ in range(n_blocks):
+        if pos + 8 > len(blob):
+            break
+        _raw, comp = struct.unpack_from("<ii", blob, pos)
+        pos += 8 + comp
+    return min(pos, len(blob))
+
+
+def cpu_dropin_loop() -> dict:
+    """oracle/_ref/dropin_check --time: the reference's block loop (benchmark/flagstats.cpp:304,328-329)
+    through its own dispatcher compiled with integration/libflagstats_h_cuda.patch -- pageable
+    512,000-record blocks into FLAGSTAT_cuda vs the reference's CPU kernel at 1 thread, and the
+    per-call crossover length."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_check")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/dropin_check was not prebuilt"}
+    try:
+        p = subprocess.run([exe, "--time"], capture_output=True, text=True, timeout=240)
+    except Exception as exc:
+        return {"error": repr(exc)}
+    rows = []
+    for line in p.stdout.splitlines():
+        try:
+            rows.append(json.loads(line))
+        except ValueError:
+            pass
+    out = {"rc": p.returncode, "min_len_default": next((r["cuda_min_len_default"] for r in rows if "cuda_min_len_default" in r), None)}
+    for r in rows:
+        if "loop" in r:
+            out[r["loop"]] = {k: v for k, v in r.items() if k != "loop"}
+        if "crossover_records" in r:
+            out["crossover_records_pageable"] = r["crossover_records"]
+    out["per_call_us_pageable"] = {str(r["n"]): [r["cuda_us"], r["cpu_us"]] for r in rows if r.get("sweep") == "pageable"}
+    return out
+
+
 def cpu_model() -> str:
     try:
         with open("/proc/cpuinfo") as fh:
@@ -217,6 +325,171 @@ def reference_arm(args) -> int:
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+STRONG_N = 1 << 34
+
+
+def strong_scaling_leg(args, fs, sharded, synth, xchg, overlap, dev, stream, world, rank, fence, dist, torch, np) -> dict:
+    """BASELINE.json configs[3]: a FIXED 2^34-record column (the reference's uint32_t len cannot
+    even express it, libflagstats.h:170) split into `world` contiguous ranges."""
+    lo, hi = sharded.shard_range(STRONG_N, world, rank)
+    shard = synth.hiseqx_device(hi - lo, start=lo, device=dev)
+    out = torch.zeros(32, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize(dev)
+    deferred = xchg is not None and overlap and not args.no_deferred
+
+    def run(k, d):
+        for _ in range(k):
+            if xchg is not None:
+                xchg.flagstat(shard, out=out, accumulate=False, stream=stream, deferred=d)
+            else:
+                out.zero_()
+                fs.flagstat_device(shard, out=out, stream=stream)
+                sharded.allreduce_counters(out)
+        if xchg is not None and d:
+            xchg.collect(stream=stream)
+
+    def timed(k, d):
+        run(3, d)
+        fence()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        run(k, d)
+        b.record(stream)
+        fence()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k, out.cpu().numpy().view(np.uint64).tolist()
+
+    k = max(3, min(args.steps, 20))
+    ms, got = timed(k, deferred)
+    ms_serial, got_serial = None, None
+    if xchg is not None and overlap:
+        xchg.set_overlap(False)
+        ms_serial, got_serial = timed(k, False)
+        xchg.set_overlap(True)
+    with open(os.path.join(ROOT, "tests", "golden", "flagstat_golden.json")) as fh:
+        kat = json.load(fh)["kat_16g"]
+    assert kat["spec"]["n"] == STRONG_N
+    verified = got == kat["cuda_expected"] and (got_serial is None or got_serial == kat["cuda_expected"])
+    hint = None
+    try:  # strong-scaling efficiency against the committed 1-GPU measurement of the same leg (a hint:
+        # the driver computes its own from the per-N lines)
+        with open(os.path.join(ROOT, "profiles", "strong_2p34_n1.json")) as fh:
+            n1 = json.load(fh)
+        hint = (STRONG_N / (ms * 1e-3)) / (world * n1["value"])
+    except Exception:
+        pass
+    del shard
+    torch.cuda.empty_cache()
+    return {
+        "workload": "BASELINE configs[3]: 2^34 HiSeqX-shaped records range-sharded over the ranks (strong scaling)",
+        "records": STRONG_N, "records_this_rank": hi - lo, "bytes_per_gpu": 2 * (hi - lo), "steps": k,
+        "ms_per_step": ms, "value": STRONG_N / (ms * 1e-3), "unit": UNIT,
+        "ms_per_step_serialised_launches": ms_serial,
+        "value_serialised": (STRONG_N / (ms_serial * 1e-3)) if ms_serial else None,
+        "gbs_per_gpu": 2 * (hi - lo) / (ms * 1e-3) / 1e9,
+        "verified": bool(verified), "efficiency_vs_n1_hint": hint,
+        "steps_overlapped": overlap, "deferred_collection": deferred,
+    }
+
+
+def inmemory_leg(fs, synth, torch, dev, peak) -> dict:
+    """BASELINE configs[0] on the GPU: 100 M records U(0,4095) (benchmark/inmemory.cpp:108-116 with
+    size 100 M), device-resident.  200 MB is close to the 126 MB L2, so launches rotate over 5
+    distinct copies (1 GB); CUDA events inside the C ABI (FLAGSTAT_cuda_time_device_rot)."""
+    import ctypes as C
+
+    n, copies = 100_000_000, 5
+    stride = (n + 8 + 7) // 8 * 8
+    out = torch.zeros(32, dtype=torch.int64, device=dev)
+    res = {"records": n, "copies_rotated": copies, "timing": "CUDA events around back-to-back launches, mean"}
+    for name, gen, mode in (("flagstat_uniform12", "u12", 0), ("flagstat_hiseqx_shaped", "hx", 0),
+                            ("pospopcnt_uniform16", "u16", 1), ("samtools_uniform12", "u12", 2)):
+        buf = torch.empty(stride * copies, dtype=torch.int16, device=dev)
+        for c in range(copies):
+            view = buf[c * stride: c * stride + n]
+            if gen == "hx":
+                synth.hiseqx_device(n, start=c * n, device=dev, out=view)
+            else:
+                synth.uniform_device(n, c * n, 0 if gen == "u12" else 1, 0x0FFF if gen == "u12" else 0xFFFF,
+                                     device=dev, out=view)
+        torch.cuda.synchronize(dev)
+        ms = C.c_float(0)
+        fs.check(fs.lib().FLAGSTAT_cuda_time_device_rot(buf.data_ptr(), n, stride, copies, out.data_ptr(), 50, mode,
+                                                        C.byref(ms)), "time_device_rot")
+        best = 1e30
+        for _ in range(3):
+            fs.check(fs.lib().FLAGSTAT_cuda_time_device_rot(buf.data_ptr(), n, stride, copies, out.data_ptr(), 500, mode,
+                                                            C.byref(ms)), "time_device_rot")
+            best = min(best, ms.value)
+        gbs = 2 * n / (best * 1e-3) / 1e9
+        res[name] = {"us_per_launch": best * 1e3, "grec_s": n / (best * 1e-3) / 1e9, "gbs": gbs, "frac_of_measured_peak": gbs / peak}
+        del buf
+    torch.cuda.empty_cache()
+    return res
+
+
+def file_leg(fs, torch, dev, threads: int, pcie_gbs: float) -> dict:
+    """the reference's FLAG files end to end on the GPU (file in the page cache ->
+    counters) next to the reference's own readers of the same files on this host's cores
+    (cpu_file_reference).  400 blocks of 1,024,000 bytes (204.8 M records): raw .bin, LZ4 containers of
+    a run-structured column (ratio ~5) and of an i.i.d. one (ratio ~2.2), a Zstd level-1 container."""
+    import tempfile
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import containers
+    from libflagstats_b200 import blockfile
+
+    n = 400 * 512_000 + 12_345
+    cols = {"runs": containers.runs_column(n), "iid": containers.iid_column(n)}
+    blobs = {"lz4_runs": ("lz4", containers.container(cols["runs"], "lz4")),
+             "lz4_iid": ("lz4", containers.container(cols["iid"], "lz4"))}
+    if containers.libzstd() is not None:
+        blobs["zstd1_runs"] = ("zstd", containers.container(cols["runs"], "zstd", 1))
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    res = {"records": n, "blocks": 401, "pcie_h2d_probe_gbs": pcie_gbs, "files": {}}
+    try:
+        cpu = {"runs": cpu_file_reference(cols["runs"], {k: v for k, v in blobs.items() if k.endswith("runs")}, threads),
+               "iid": cpu_file_reference(cols["iid"], {k: v for k, v in blobs.items() if k.endswith("iid")}, threads)}
+        jobs = [("raw_bin", "runs", None, ".bin")] + [(k, k.split("_")[-1], v[1], ".lz4" if v[0] == "lz4" else ".zst")
+                                                      for k, v in blobs.items()]
+        core19 = [i for i in fs.CORE20 if i != 9]
+        for name, colname, blob, ext in jobs:
+            path = os.path.join(tmp, name + ext)
+            if blob is None:
+                cols[colname].tofile(path)
+            else:
+                with open(path, "wb") as fh:
+                    fh.write(blob)
+            size = os.path.getsize(path)
+            best = 1e30
+            for _ in range(4):
+                t0 = time.perf_counter()
+                f, got_n = blockfile.flagstat_file(path)
+                best = min(best, time.perf_counter() - t0)
+            ref = cpu[colname].get("raw" if blob is None else name)
+            ok = got_n == n and int(f[9]) + int(f[25]) == n
+            if ref is not None:  # slot 9 is left out: the reference's scalar tail kernel never writes it (libflagstats.h:127)
+                ok = ok and [int(f[i]) for i in core19] == [ref["counters"][i] for i in core19]
+            res["files"][name] = {
+                "file_bytes": size, "ratio": 2 * n / size, "seconds": best, "grec_s": n / best / 1e9,
+                "gbs_records": 2 * n / best / 1e9, "gbs_file": size / best / 1e9, "verified": bool(ok),
+                "cpu_reference": ({k: v for k, v in ref.items() if k != "counters"} if ref else None),
+                "speedup_vs_reference_1thread": (n / best / 1e9 / ref["grec_s_1thread"]) if ref else None,
+                "speedup_vs_reference_all_cores": (n / best / 1e9 / ref["grec_s_all_cores"]) if ref else None,
+            }
+            os.remove(path)
+    finally:
+        try:
+            os.rmdir(tmp)
+        except OSError:
+            pass
+    return res
+
+
 def ours(args) -> int:
     import numpy as np
     import torch
@@ -255,11 +528,21 @@ def ours(args) -> int:
         fs.flagstat_device(data, out=counters, stream=stream)
         sharded.allreduce_counters(counters)
 
+    deferred = xchg is not None and overlap and not args.no_deferred
+
     def step_fused():
         # ONE kernel launch per rank: count the shard, push the 32 totals into every
-        # peer's exchange buffer over NVLink, wait for the peers', write the global
-        # counters (overwrite mode: no memset either)
-        xchg.flagstat(data, out=counters, accumulate=False, stream=stream)
+        # peer's exchange buffer over NVLink, write the global counters (overwrite mode: no
+        # memset either).  Deferred collection (default): the launch does not wait for the
+        # peers' totals of THIS step -- the next step's launch first collects them (and the
+        # last step's are collected by xchg.collect() inside the timed region), so a rank only
+        # ever waits for its peers' PREVIOUS step and per-step jitter between GPUs stays off
+        # the critical path.
+        xchg.flagstat(data, out=counters, accumulate=False, stream=stream, deferred=deferred)
+
+    def finish_steps():
+        if deferred:
+            xchg.collect(stream=stream)
 
     step = step_fused if xchg is not None else step_nccl
 
@@ -307,6 +590,7 @@ def ours(args) -> int:
             xchg.close()
             xchg = sharded.FusedExchange(device=dev, overlap=False)
             overlap = False
+            deferred = False
             for _ in range(max(args.warmup, 3)):
                 step()
             fence()
@@ -323,6 +607,8 @@ def ours(args) -> int:
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    if xchg is not None:
+        finish_steps()  # the last step's counters (deferred collection): inside the timed region
     e1.record(stream)
     fence()
     t1 = time.perf_counter()
@@ -337,8 +623,11 @@ def ours(args) -> int:
 
     # the same K steps with launches strictly serialised (no overlap of consecutive steps), for the record
     serial_ms = None
+    serial_ok = None
     if xchg is not None and overlap:
+        finish_steps()
         xchg.set_overlap(False)
+        was_deferred, deferred = deferred, False  # one call = count + exchange + wait, strictly in order
         for _ in range(3):
             step()
         fence()
@@ -354,6 +643,25 @@ def ours(args) -> int:
         serial_ms = float(t.item()) / args.steps
         serial_ok = counters.cpu().numpy().view(np.uint64).tolist() == result.tolist()
         xchg.set_overlap(True)
+        deferred = was_deferred
+
+    # overlapped steps with the wait in the same launch (round-1 behaviour), for the record
+    immediate_ms = None
+    if xchg is not None and overlap and deferred and world > 1:
+        deferred = False
+        for _ in range(3):
+            step()
+        fence()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record(stream)
+        for _ in range(args.steps):
+            step()
+        i1.record(stream)
+        fence()
+        t = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        immediate_ms = float(t.item()) / args.steps
+        deferred = True
 
     # the same K steps with the other exchange (kernel + separate NCCL all-reduce), for the record
     alt_ms = None
@@ -371,6 +679,16 @@ def ours(args) -> int:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         alt_ms = float(t.item()) / args.steps
         alt_ok = counters.cpu().numpy().view(np.uint64).tolist() == result.tolist()
+
+    # ---- BASELINE configs[3]: 2^34 records range-sharded over the ranks (STRONG scaling) ----------
+    # rank r holds shard_range(2^34, world, r) of the same generator (34.4 GB at N = 1); K overlapped
+    # steps and K serialised ones, checked against the reference-made answer in the golden fixture
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_scaling_leg(args, fs, sharded, synth, xchg, overlap, dev, stream, world, rank, fence, dist, torch, np)
+        except Exception as exc:  # the headline numbers must survive a failure of this leg
+            strong = {"error": repr(exc)}
 
     # ---- the kernel alone (roofline): same stream, CUDA events -------------
     # Long enough (>= ~0.4 s) for nvidia-smi to see clocks and throttle reasons
@@ -498,6 +816,18 @@ def ours(args) -> int:
     except Exception as exc:  # the headline numbers must survive a failure of this extra leg
         stream_info = {"error": repr(exc)}
 
+    # ---- N = 1 extras: configs[0] on the GPU and the FLAG-file readers ------------------
+    inmemory_info = file_info = None
+    if world == 1 and not args.no_extras:
+        try:
+            inmemory_info = inmemory_leg(fs, synth, torch, dev, load_peaks()[0])
+        except Exception as exc:
+            inmemory_info = {"error": repr(exc)}
+        try:
+            file_info = file_leg(fs, torch, dev, len(os.sched_getaffinity(0)), pcie_gbs)
+        except Exception as exc:
+            file_info = {"error": repr(exc)}
+
     # ---- verification: N x KAT-E, from the committed golden fixture ---------
     verified = None
     try:
@@ -542,17 +872,31 @@ def ours(args) -> int:
             "one_thread_value": sample / r["one_thread_s"], "cpu": cpu_model(),
             "verified": r["verified"],
         }
+        if not args.no_extras:
+            # scalar / avx2 / avx512 / avx512_improved3 / STORM_pospopcnt_u16 on the
+            # 100 M-record U(0,4095) buffer, 1 thread and all cores; and the drop-in block loop
+            try:
+                cpu["inmemory_100m_kernel_set"] = cpu_baseline_set(threads)
+            except Exception as exc:
+                cpu["inmemory_100m_kernel_set"] = {"error": repr(exc)}
+            try:
+                cpu["dropin_block_loop"] = cpu_dropin_loop()
+            except Exception as exc:
+                cpu["dropin_block_loop"] = {"error": repr(exc)}
 
     peak, peak_src = load_peaks()
     step_ms = ms_total / args.steps
     value = world * n / (step_ms * 1e-3)
+    # one call at a time (every launch waits for the previous one): what a single FLAGSTAT_cuda_device*
+    # call costs; `value` pipelines consecutive calls (ms_per_step < roofline.kernel_ms is that overlap)
+    value_serialised = (world * n / (serial_ms * 1e-3)) if serial_ms else None
     achieved = 2.0 * n / (kernel_ms * 1e-3) / 1e9
     traffic = load_traffic()
     kernel_name = fs.lib().FLAGSTAT_cuda_kernel_name(0).decode()
     if traffic and "fsb200::" + traffic.get("kernel", "") != kernel_name:
         traffic = None  # the committed ncu capture is of another kernel: no traffic claim
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": value, "value_serialised": value_serialised, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
@@ -581,15 +925,22 @@ def ours(args) -> int:
         },
         "e2e_pageable": pageable_info,
         "stream_e2e": stream_info,
+        "strong_2p34": strong,
+        "inmemory_100m": inmemory_info,
+        "file_e2e": file_info,
         "gpu_launches": int(launches),
         "exchange": ("fused: counters exchanged by the counting kernel itself through peer-mapped "
                      "memory (FLAGSTAT_cuda_device_allreduce), 1 launch/step"
                      + ("; consecutive steps overlap (programmatic dependent launch: the next step "
                         "streams its shard while this step's last CTA exchanges counters)" if overlap else "")
+                     + ("; deferred collection: a step pushes its totals, the next step's launch (the last "
+                        "one: FLAGSTAT_cuda_xchg_collect, inside the timed region) waits for the peers' and "
+                        "writes the counters" if deferred and world > 1 else "")
                      if xchg is not None else "kernel + memset + NCCL all-reduce of 32 x u64"),
         "overlap_fallback": overlap_fallback,
         "ms_per_step_serialised_launches": serial_ms,
-        "serialised_same_result": (serial_ok if serial_ms is not None else None),
+        "ms_per_step_overlapped_wait_in_launch": immediate_ms,
+        "serialised_same_result": serial_ok,
         "ms_per_step_with_nccl_allreduce": alt_ms,
         "nccl_path_same_result": (alt_ok if alt_ms is not None else None),
         "clocks": clocks,
@@ -616,6 +967,11 @@ def main() -> int:
                     help="extra warm-up under load before the timed steps (seconds)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="launch consecutive fused steps strictly serialised (no programmatic dependent launch)")
+    ap.add_argument("--no-deferred", action="store_true",
+                    help="fused steps wait for the peers' totals in the same launch (round-1 behaviour)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 2^34-record strong-scaling leg (configs[3])")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the N=1 extra legs (100 M in-memory config, FLAG files, drop-in block loop, CPU kernel set)")
     ap.add_argument("--exchange", choices=["fused", "nccl"], default="fused",
                     help="how the 32 counters are summed across ranks")
     args = ap.parse_args()

@@ -303,7 +303,10 @@ const char* FLAGSTAT_cuda_strerror(int code);
 const char* FLAGSTAT_cuda_version(void);
 /* Kernels this library has launched in this process (all threads). */
 uint64_t FLAGSTAT_cuda_launch_count(void);
-/* Select a kernel variant for A/B tests (0 = default).  Returns the previous. */
+/* Select a kernel variant for A/B tests (0 = default).  Returns the previous, or
+ * FLAGSTAT_CUDA_EINVAL for a variant this build does not contain: the product library carries
+ * 0 (default), 1 (integer-only mask select), 3 (TMA-staged) and 8 (compare-mask forms); the
+ * other measured-and-superseded variants need a -DFSB_ALL_VARIANTS build. */
 int FLAGSTAT_cuda_set_variant(int variant);
 /* LZ4 block decoder for A/B tests: 1 = 32 sequences per warp step (default), 0 = one
  * sequence per warp step.  Returns the previous.  Env FLAGSTAT_CUDA_LZ4_VARIANT sets the
@@ -314,6 +317,12 @@ int FLAGSTAT_cuda_set_lz4_variant(int variant);
 const char* FLAGSTAT_cuda_kernel_name(int mode);
 /* Persistent-grid size override: CTAs per SM (0 = default). */
 int FLAGSTAT_cuda_set_ctas_per_sm(int n);
+/* Work distribution of the default kernel.  Long columns are handed out dynamically (every warp
+ * claims 8 KiB chunks from a shared counter, so slow SMs simply take fewer); short ones are split
+ * statically.  min_chunks: -1 = always static, 0 = default threshold (6 chunks per resident
+ * warp, ~58 M records on a B200), > 0 = dynamic from that many chunks on (tests force 1).
+ * groups_per_chunk: 1 or 2 (8 / 16 KiB per claim), 0 = leave unchanged. */
+int FLAGSTAT_cuda_set_dynamic(long long min_chunks, int groups_per_chunk);
 
 /* Deterministic synthetic FLAG columns, pure functions of the GLOBAL record
  * index.  Device twins of oracle_synth_uniform/_hiseqx; d_out is
@@ -339,7 +348,8 @@ int FLAGSTAT_cuda_time_device(const uint16_t* d_array, uint64_t len, uint64_t* d
                               int pospopcnt_mode, float* ms_per_launch);
 /* The same over n_rot copies of the column laid out stride_records apart (launch i reads copy
  * i % n_rot): columns smaller than the 126 MB L2 are then timed from HBM rather than from the
- * cache a back-to-back loop over ONE copy would hit.  mode as pospopcnt_mode above. */
+ * cache a back-to-back loop over ONE copy would hit.  mode as pospopcnt_mode above; + 4: the
+ * launches are overlapped ones (FLAGSTAT_cuda_device_overlapped). */
 int FLAGSTAT_cuda_time_device_rot(const uint16_t* d_base, uint64_t len, uint64_t stride_records,
                                   uint32_t n_rot, uint64_t* d_flags, int iters, int mode,
                                   float* ms_per_launch);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "FLAGSTAT_cuda_kernel_name": (C.c_char_p, [C.c_int]),
     "FLAGSTAT_cuda_set_lz4_variant": (C.c_int, [C.c_int]),
     "FLAGSTAT_cuda_set_ctas_per_sm": (C.c_int, [C.c_int]),
+    "FLAGSTAT_cuda_set_dynamic": (C.c_int, [C.c_longlong, C.c_int]),
     "FLAGSTAT_cuda_synth_uniform": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.c_uint16, C.c_void_p]),
     "FLAGSTAT_cuda_synth_hiseqx": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,

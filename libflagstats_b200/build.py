@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libflagstats_cuda.so")
 
 SOURCES = ["flagstat_capi.cu"]
-HEADERS = ["flagstat_kernels.cuh", "flagstat_kernel_tma.cuh", "flagstat_kernel_group.cuh", "lz4_block.cuh", "lz4_block_group.cuh", "zstd_frame.cuh", "zstd_block.cuh", "ingest_text.cuh", "flagstat_blockfile.inl", "bitcounter.cuh", "synth.cuh",
+HEADERS = ["flagstat_kernels.cuh", "flagstat_kernel_tma.cuh", "flagstat_kernel_group.cuh", "flagstat_kernel_dyn.cuh", "lz4_block.cuh", "lz4_block_group.cuh", "zstd_frame.cuh", "zstd_block.cuh", "ingest_text.cuh", "flagstat_blockfile.inl", "bitcounter.cuh", "synth.cuh",
            os.path.join("..", "..", "include", "flagstats_cuda.h")]
 
 NVCC_FLAGS = [
@@ -44,19 +44,26 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+VARIANTS_SO = os.path.join(os.path.dirname(HERE), "tools", "bin", "libflagstats_cuda_variants.so")
+
+
+def build(force: bool = False, verbose: bool = False, all_variants: bool = False) -> str:
+    """all_variants: the A/B build with every measured-and-superseded kernel variant compiled in
+    (-DFSB_ALL_VARIANTS), written to tools/bin/ -- never the product library."""
+    out = VARIANTS_SO if all_variants else SO
+    if not all_variants and not force and not stale():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc()] + NVCC_FLAGS + (["-DFSB_ALL_VARIANTS"] if all_variants else [])
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
-    print(SO)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv,
+                all_variants="--all-variants" in sys.argv))

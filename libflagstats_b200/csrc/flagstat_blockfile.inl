@@ -124,16 +124,13 @@ int lz4_variant()
 int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status,
                uint32_t n_blocks, cudaStream_t st)
 {
-    static std::once_flag once;
-    static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [] {
-        attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem);
-        if (attr_rc == cudaSuccess)
-            attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem);
-    });
-    if (attr_rc != cudaSuccess) return (int)attr_rc;
+    // both decoders need more than 48 KiB of dynamic shared memory: that opt-in is a PER-DEVICE
+    // function attribute, set for every device in device_info()
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    DeviceInfo* di = nullptr;
+    const int rc = device_info(dev, &di);
+    if (rc) return rc;
     const unsigned grid = (n_blocks + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
     if (lz4_variant() == 0)
         lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4Smem, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
@@ -260,25 +257,23 @@ int lz4_lane_ship(int mode, int codec, Lz4Lane& l, size_t comp_bytes, size_t raw
     if (l.n == 0) return 0;
     CK(cudaMemcpyAsync(l.d_comp, l.h_comp, comp_bytes, cudaMemcpyHostToDevice, l.st));
     CK(cudaMemcpyAsync(l.d_desc, l.h_desc, l.n * sizeof(Lz4BlockDesc), cudaMemcpyHostToDevice, l.st));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    TimerPair dbg;  // FLAGSTAT_CUDA_DEBUG: decode kernel time on stderr (events freed on every path)
     if (file_debug()) {
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        CK(cudaEventRecord(e0, l.st));
+        CK(cudaEventCreate(&dbg.e0));
+        CK(cudaEventCreate(&dbg.e1));
+        CK(cudaEventRecord(dbg.e0, l.st));
     }
     int rc = codec == kCodecZstd
                  ? zstd_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.d_work, l.st)
                  : lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st);
     if (rc) return rc;
     if (file_debug()) {
-        CK(cudaEventRecord(e1, l.st));
-        CK(cudaEventSynchronize(e1));
+        CK(cudaEventRecord(dbg.e1, l.st));
+        CK(cudaEventSynchronize(dbg.e1));
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventElapsedTime(&ms, dbg.e0, dbg.e1);
         std::fprintf(stderr, "[flagstat_cuda] block decode: %d blocks, %zu -> %zu bytes, %.3f ms (%.1f GB/s out)\n",
                      l.n, comp_bytes, raw_bytes, ms, raw_bytes / (ms * 1e6));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
     if (all_even) {  // the decoded blocks are one contiguous run of whole records
         rc = launch(mode, reinterpret_cast<const uint16_t*>(l.d_raw), raw_bytes / 2, d_flags, l.st);
@@ -614,6 +609,10 @@ int consume_raw_fd(int mode, int fd, uint64_t size, uint64_t* totals, uint64_t* 
 // cudaMemcpyAsync from such memory is staged by the driver through its own bounce buffer on
 // the calling thread; here T threads memcpy their slices into pinned slots and every slice is
 // its own DMA + launch, so the page-in copy of one slice overlaps the DMA of the others.
+// (Pinning the caller's pages in place instead -- cudaHostRegister per 32 MiB granule, DMA straight
+// from user memory, unregister behind it -- was built and measured: 8.6-9.6 GB/s whatever the
+// thread count, the per-granule pin / unpin calls serialise in the driver; one whole-array
+// cudaHostRegister costs 36-55 ms + 27-40 ms to undo per 1.65 GB.  profiles/r4e_pageable.jsonl.)
 int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals)
 {
     const uint64_t size = len * sizeof(uint16_t);
@@ -690,15 +689,7 @@ int FLAGSTAT_cuda_file_u64(const char* path, int format, uint64_t* flags, uint64
     ByteSource src;
     src.fp = std::fopen(path, "rb");
     if (!src.fp) return FLAGSTAT_CUDA_EIO;
-    static thread_local std::vector<char> iobuf;
-    int rc = guarded([&] {
-        iobuf.resize(4u << 20);
-        return 0;
-    });
-    if (rc == 0) {
-        std::setvbuf(src.fp, iobuf.data(), _IOFBF, iobuf.size());
-        rc = consume(src, format, flags, n_records);
-    }
+    const int rc = consume(src, format, flags, n_records);  // every reader pread()s the descriptor
     std::fclose(src.fp);
     return rc;
 }
@@ -721,11 +712,13 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
 {
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
     if (n_blocks == 0) return 0;
-    if (!comp || !raw || !status) return FLAGSTAT_CUDA_EINVAL;
+    if (!comp || !raw || !status || !comp_off || !comp_size || !raw_off || !raw_size) return FLAGSTAT_CUDA_EINVAL;
     return guarded([&]() -> int {
     std::vector<Lz4BlockDesc> desc(n_blocks);
     for (uint32_t b = 0; b < n_blocks; ++b) {
-        if (comp_off[b] + comp_size[b] > comp_bytes || raw_off[b] + raw_size[b] > raw_total)
+        // written so that an offset near 2^64 cannot wrap the sum past the bound
+        if (comp_off[b] > comp_bytes || comp_size[b] > comp_bytes - comp_off[b] || raw_off[b] > raw_total ||
+            raw_size[b] > raw_total - raw_off[b])
             return FLAGSTAT_CUDA_EINVAL;
         desc[b] = Lz4BlockDesc{comp_off[b], raw_off[b], comp_size[b], raw_size[b]};
     }

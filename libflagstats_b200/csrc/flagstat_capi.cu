@@ -13,6 +13,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <emmintrin.h>
@@ -26,6 +27,7 @@
 #include "flagstat_kernels.cuh"
 #include "flagstat_kernel_tma.cuh"
 #include "flagstat_kernel_group.cuh"
+#include "flagstat_kernel_dyn.cuh"
 #include "synth.cuh"
 #include "lz4_block.cuh"
 #include "lz4_block_group.cuh"
@@ -124,25 +126,36 @@ struct KernelCfg {
 
 constexpr size_t tma_smem(int stages) { return (size_t)stages * kStageBytes + 2u * stages * 8u; }
 
+// The product library ships the default (0), the integer-only cross-check (1), one TMA variant (3)
+// and the compare-mask forms (8, the cross-check of the FMA-pipe mask arithmetic).  The others are
+// measured A/B history (profiles/README.md): compiled only with -DFSB_ALL_VARIANTS
+// (python -m libflagstats_b200.build --all-variants -> tools/bin/libflagstats_cuda_variants.so).
+#ifdef FSB_ALL_VARIANTS
+#define FSB_AB(...) __VA_ARGS__
+#else
+#define FSB_AB(...) {{nullptr, nullptr}, 0, 0}
+#endif
 const KernelCfg kKernels[kNumVariants] = {
     {{flagstat_kernel_group<kFlagstat, 3, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
     {{flagstat_kernel_group<kFlagstat, 1, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
-    {{flagstat_kernel<kFlagstat, 0>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0},
+    FSB_AB({{flagstat_kernel<kFlagstat, 0>, flagstat_kernel<kPospopcnt, 0>}, kThreads, 0}),
     {{flagstat_kernel_tma<kFlagstat, 0, 4, 2>, flagstat_kernel_tma<kPospopcnt, 0, 4, 2>},
      kThreads + 32, tma_smem(4)},
-    {{flagstat_kernel_tma<kFlagstat, 0, 6, 2>, flagstat_kernel_tma<kPospopcnt, 0, 6, 2>},
-     kThreads + 32, tma_smem(6)},
-    {{flagstat_kernel_ring<kFlagstat, 0, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
-     kThreads, (size_t)4 * kStageBytes},
-    {{flagstat_kernel_ring<kFlagstat, 0, 2, 2>, flagstat_kernel_ring<kPospopcnt, 0, 2, 2>},
-     kThreads, (size_t)2 * kStageBytes},
-    {{flagstat_kernel_ring<kFlagstat, 2, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
-     kThreads, (size_t)4 * kStageBytes},
+    FSB_AB({{flagstat_kernel_tma<kFlagstat, 0, 6, 2>, flagstat_kernel_tma<kPospopcnt, 0, 6, 2>},
+            kThreads + 32, tma_smem(6)}),
+    FSB_AB({{flagstat_kernel_ring<kFlagstat, 0, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+            kThreads, (size_t)4 * kStageBytes}),
+    FSB_AB({{flagstat_kernel_ring<kFlagstat, 0, 2, 2>, flagstat_kernel_ring<kPospopcnt, 0, 2, 2>},
+            kThreads, (size_t)2 * kStageBytes}),
+    FSB_AB({{flagstat_kernel_ring<kFlagstat, 2, 4, 2>, flagstat_kernel_ring<kPospopcnt, 0, 4, 2>},
+            kThreads, (size_t)4 * kStageBytes}),
     {{flagstat_kernel_group<kFlagstat, 0, 2>, flagstat_kernel_group<kPospopcnt, 0, 2>},
      kThreads, (size_t)4 * kStageBytes},
 };
+
+inline bool variant_built(int v) { return v >= 0 && v < kNumVariants && kKernels[v].fn[0] != nullptr; }
 
 // kSamtools (exact n_pair_all in slots 0 / 16) has one instantiation whatever variant is
 // selected: the group kernel with the FMA-pipe mask forms (flagstat_kernels.cuh: mask_select_fx)
@@ -150,10 +163,31 @@ const KernelCfg kSamtoolsKernel = {
     {flagstat_kernel_group<kSamtools, 3, 2>, flagstat_kernel_group<kSamtools, 3, 2>},
     kThreads, (size_t)4 * kStageBytes};
 
+// The default variant's dynamically scheduled twin (flagstat_kernel_dyn.cuh), by mode.  CG = 8 KiB
+// groups per claimed chunk: kDynCG (A/B: FLAGSTAT_CUDA_DYN_CG=2 selects the 16 KiB instantiation).
+constexpr int kDynCG = 1;
+const KernelFn kDynKernels[2][3] = {
+    {flagstat_kernel_dyn<kFlagstat, 3, 2, 1>, flagstat_kernel_dyn<kPospopcnt, 0, 2, 1>,
+     flagstat_kernel_dyn<kSamtools, 3, 2, 1>},
+    {flagstat_kernel_dyn<kFlagstat, 3, 2, 2>, flagstat_kernel_dyn<kPospopcnt, 0, 2, 2>,
+     flagstat_kernel_dyn<kSamtools, 3, 2, 2>},
+};
+constexpr int kDynStreams = 1024;  // streams per device that can hold a private pair of counter slots
+
+struct DynStream {
+    int base;        // slot pair index
+    uint64_t count;  // launches of the dynamic kernel on this stream so far: parity picks the slot
+};
+
 struct DeviceInfo {
     int sms = 0;
     int occ[kNumVariants][2];  // resident CTAs per SM
     int occ_samtools = 2;
+    int occ_dyn[3] = {2, 2, 2};
+    unsigned char* dyn = nullptr;  // kDynStreams x 2 slots of kDynSlotBytes (device memory, zeroed)
+    std::unordered_map<cudaStream_t, DynStream> dyn_map;
+    std::mutex dyn_mu;
+    std::atomic<uint32_t> dyn_tag{0};
     bool ok = false;
 };
 
@@ -189,6 +223,10 @@ int device_info(int dev, DeviceInfo** out)
         for (int v = 0; v < kNumVariants; ++v)
             for (int m = 0; m < 2; ++m) {
                 const KernelCfg& k = kKernels[v];
+                if (!variant_built(v)) {
+                    d.occ[v][m] = 1;
+                    continue;
+                }
                 if (k.smem > 48u * 1024u)
                     CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(k.fn[m]),
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -214,11 +252,89 @@ int device_info(int dev, DeviceInfo** out)
             }
             d.occ_samtools = nb < 1 ? 1 : nb;
         }
+        for (int c = 0; c < 2; ++c)
+            for (int m = 0; m < 3; ++m) {
+                const void* fn = reinterpret_cast<const void*>(kDynKernels[c][m]);
+                CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kStageBytes));
+                int nb = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, (size_t)4 * kStageBytes) !=
+                    cudaSuccess) {
+                    cudaGetLastError();
+                    nb = 2;
+                }
+                if (c == 0) d.occ_dyn[m] = nb < 1 ? 1 : nb;
+            }
+        // the LZ4 block decoders of flagstat_blockfile.inl (> 48 KiB of dynamic shared memory)
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem));
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem));
+        CK(cudaMalloc(&d.dyn, (size_t)kDynStreams * 2 * kDynSlotBytes));
+        CK(cudaMemset(d.dyn, 0, (size_t)kDynStreams * 2 * kDynSlotBytes));
         if (cur != dev && cur >= 0) CK(cudaSetDevice(cur));
         d.ok = true;
     }
     *out = &d;
     return 0;
+}
+
+// Dynamic scheduling knobs (FLAGSTAT_cuda_set_dynamic; env FLAGSTAT_CUDA_DYNAMIC=0 switches it off,
+// FLAGSTAT_CUDA_DYN_MIN_CHUNKS / FLAGSTAT_CUDA_DYN_CG preset the other two):
+//   g_dyn_min_chunks  -1 off; 0 default = 6 chunks per resident warp (~58 M records on a B200);
+//                     > 0: use the dynamic kernel from that many chunks on (tests force 1)
+//   g_dyn_cg          8 KiB groups per claimed chunk: 1 or 2
+std::atomic<long long> g_dyn_min_chunks{-2};  // -2 = read the environment first
+std::atomic<int> g_dyn_cg{0};
+
+long long dyn_min_chunks()
+{
+    long long v = g_dyn_min_chunks.load(std::memory_order_relaxed);
+    if (v == -2) {
+        v = 0;
+        if (const char* e = std::getenv("FLAGSTAT_CUDA_DYNAMIC"))
+            if (std::atoi(e) == 0) v = -1;
+        if (v == 0)
+            if (const char* e = std::getenv("FLAGSTAT_CUDA_DYN_MIN_CHUNKS")) v = std::atoll(e) > 0 ? std::atoll(e) : 0;
+        g_dyn_min_chunks.store(v);
+    }
+    return v;
+}
+
+int dyn_cg()
+{
+    int v = g_dyn_cg.load(std::memory_order_relaxed);
+    if (v == 0) {
+        const char* e = std::getenv("FLAGSTAT_CUDA_DYN_CG");
+        v = (e && std::atoi(e) == 2) ? 2 : kDynCG;
+        g_dyn_cg.store(v);
+    }
+    return v;
+}
+
+// The counter slot of this launch and its owner tag (flagstat_kernel_dyn.cuh explains why a pair
+// of slots per stream, used alternately, is private to each launch), or nullptr when the launch
+// has to run the static kernel: stream capture, cudaStreamPerThread, more than kDynStreams streams.
+unsigned long long* dyn_slot(DeviceInfo* di, cudaStream_t st, unsigned int* tag)
+{
+    if (st == cudaStreamPerThread) return nullptr;
+    if (st == nullptr) st = cudaStreamLegacy;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (cap != cudaStreamCaptureStatusNone) return nullptr;
+    uint32_t t = di->dyn_tag.fetch_add(1, std::memory_order_relaxed) + 1u;
+    if (t == 0u) t = di->dyn_tag.fetch_add(1, std::memory_order_relaxed) + 1u;  // 0 means "free"
+    *tag = t;
+    std::lock_guard<std::mutex> lk(di->dyn_mu);
+    auto it = di->dyn_map.find(st);
+    if (it == di->dyn_map.end()) {
+        if ((int)di->dyn_map.size() >= kDynStreams) return nullptr;
+        it = di->dyn_map.emplace(st, DynStream{(int)di->dyn_map.size(), 0}).first;
+    }
+    const uint64_t k = it->second.count++;
+    return reinterpret_cast<unsigned long long*>(di->dyn + ((size_t)it->second.base * 2 + (size_t)(k & 1u)) * kDynSlotBytes);
 }
 
 // Enqueue one kernel on the current device.
@@ -242,23 +358,47 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
         if (const char* e = std::getenv("FLAGSTAT_CUDA_VARIANT")) variant = std::atoi(e);
         g_variant.store(variant);
     }
-    if (variant < 0 || variant >= kNumVariants) variant = 0;
+    if (!variant_built(variant)) variant = 0;
     const bool sam = mode == kSamtools;
     const KernelCfg& k = sam ? kSamtoolsKernel : kKernels[variant];
-    const KernelFn fn = sam ? k.fn[0] : k.fn[mode];
+    KernelFn fn = sam ? k.fn[0] : k.fn[mode];
 
     const uint64_t addr = reinterpret_cast<uintptr_t>(d_array);
     uint64_t head = ((16u - (addr & 15u)) & 15u) >> 1;
     if (head > n) head = n;
-    const uint64_t nb = ((n - head) >> 3) / kVecPerBatch;
+    const uint64_t nvec = (n - head) >> 3;
+    const uint64_t nb = nvec / kVecPerBatch;
     int per_sm = g_ctas_per_sm.load();
+    const bool default_grid = per_sm <= 0;
     if (per_sm <= 0) per_sm = sam ? di->occ_samtools : di->occ[variant][mode];
     uint64_t grid = (uint64_t)per_sm * (uint64_t)di->sms;
     if (grid > nb + 1) grid = nb + 1;
 
-    XchgArgs none;
-    std::memset(&none, 0, sizeof(none));
+    XchgArgs args;
+    if (xa) args = *xa;
+    else std::memset(&args, 0, sizeof(args));
+    args.nb_q = nb / grid;
+    args.nb_r = (unsigned)(nb % grid);
+    args.pdl = 0;
+    args.dyn = nullptr;
+    // Columns long enough to keep every resident warp busy for several chunks take the dynamically
+    // scheduled twin of the default kernel (same arithmetic, work claimed per warp from a counter).
+    if ((variant == 0 || sam) && default_grid && dyn_min_chunks() >= 0) {
+        const int cg = dyn_cg();
+        const uint64_t chunk_vec = (uint64_t)cg * kDynWarpVecPerGroup;
+        const uint64_t full = (uint64_t)di->occ_dyn[mode] * (uint64_t)di->sms;
+        const uint64_t chunks = nvec / chunk_vec;
+        const uint64_t need = dyn_min_chunks() > 0 ? (uint64_t)dyn_min_chunks() : 6ull * full * kWarps;
+        if (chunks >= need && chunks < 0xFFFFFFF0ull) {
+            if (unsigned long long* slot = dyn_slot(di, st, &args.dyn_tag)) {
+                args.dyn = slot;
+                fn = kDynKernels[cg - 1][mode];
+                grid = full;
+            }
+        }
+    }
     if (overlap && !g_pdl_unsupported.load(std::memory_order_relaxed)) {
+        args.pdl = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(k.threads);
@@ -270,17 +410,17 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
         cfg.attrs = at;
         cfg.numAttrs = 1;
         const cudaError_t e = cudaLaunchKernelEx(&cfg, fn, d_array, (uint64_t)n,
-                                                 reinterpret_cast<unsigned long long*>(d_out),
-                                                 xa ? *xa : none);
+                                                 reinterpret_cast<unsigned long long*>(d_out), args);
         if (e == cudaSuccess) {
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return 0;
         }
         cudaGetLastError();  // e.g. a stream kind that cannot take the attribute: plain launch from now on
         g_pdl_unsupported.store(1, std::memory_order_relaxed);
+        args.pdl = 0;
     }
     fn<<<dim3((unsigned)grid), dim3(k.threads), k.smem, st>>>(
-        d_array, n, reinterpret_cast<unsigned long long*>(d_out), xa ? *xa : none);
+        d_array, n, reinterpret_cast<unsigned long long*>(d_out), args);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
     return 0;
@@ -379,7 +519,6 @@ void lane_release(Lane* l)
 
 // flagstat_blockfile.inl: T threads copy slices of a PAGEABLE host array into pinned slots
 int run_pageable(int mode, const uint16_t* array, uint64_t len, uint64_t* totals);
-
 // host arrays of at least this many bytes that are not page-locked take run_pageable()
 uint64_t pageable_min_bytes()
 {
@@ -1171,10 +1310,20 @@ uint64_t FLAGSTAT_cuda_launch_count(void) { return g_launches.load(); }
 
 int FLAGSTAT_cuda_set_variant(int v)
 {
-    const int prev = g_variant.exchange(v < 0 ? 0 : v);
+    if (!variant_built(v)) return FLAGSTAT_CUDA_EINVAL;  // not compiled into this build (see kKernels)
+    const int prev = g_variant.exchange(v);
     return prev < 0 ? 0 : prev;
 }
 int FLAGSTAT_cuda_set_ctas_per_sm(int n) { return g_ctas_per_sm.exchange(n); }
+
+int FLAGSTAT_cuda_set_dynamic(long long min_chunks, int groups_per_chunk)
+{
+    if (min_chunks < -1 || (groups_per_chunk != 0 && groups_per_chunk != 1 && groups_per_chunk != 2))
+        return FLAGSTAT_CUDA_EINVAL;
+    g_dyn_min_chunks.store(min_chunks);
+    if (groups_per_chunk) g_dyn_cg.store(groups_per_chunk);
+    return 0;
+}
 
 const char* FLAGSTAT_cuda_kernel_name(int mode)
 {
@@ -1196,7 +1345,17 @@ const char* FLAGSTAT_cuda_kernel_name(int mode)
         v = 0;
         if (const char* e = std::getenv("FLAGSTAT_CUDA_VARIANT")) v = std::atoi(e);
     }
-    if (v < 0 || v >= kNumVariants) v = 0;
+    if (!variant_built(v)) v = 0;
+    // long columns (>= 6 chunks per resident warp) of the default variant run its dynamically
+    // scheduled twin; that is the instantiation the bench workloads launch
+    if ((v == 0 || mode == kSamtools) && dyn_min_chunks() >= 0) {
+        static const char* const kDyn[2][3] = {
+            {"fsb200::flagstat_kernel_dyn<0, 3, 2, 1>", "fsb200::flagstat_kernel_dyn<1, 0, 2, 1>",
+             "fsb200::flagstat_kernel_dyn<2, 3, 2, 1>"},
+            {"fsb200::flagstat_kernel_dyn<0, 3, 2, 2>", "fsb200::flagstat_kernel_dyn<1, 0, 2, 2>",
+             "fsb200::flagstat_kernel_dyn<2, 3, 2, 2>"}};
+        return kDyn[dyn_cg() - 1][mode == kSamtools ? 2 : mode == kPospopcnt ? 1 : 0];
+    }
     if (mode == kSamtools) return "fsb200::flagstat_kernel_group<2, 3, 2>";
     return kNames[v][mode == kPospopcnt ? 1 : 0];
 }
@@ -1278,7 +1437,8 @@ int FLAGSTAT_cuda_time_device_rot(const uint16_t* d_base, uint64_t len, uint64_t
 {
     if (!d_flags || !ms_per_launch || iters <= 0 || n_rot == 0) return FLAGSTAT_CUDA_EINVAL;
     if (probe_devices() <= 0) return FLAGSTAT_CUDA_ENODEV;
-    const int m = mode == 2 ? kSamtools : mode ? kPospopcnt : kFlagstat;
+    const bool overlapped = (mode & 4) != 0;  // launches carry the programmatic-serialization attribute
+    const int m = (mode & 3) == 2 ? kSamtools : (mode & 3) ? kPospopcnt : kFlagstat;
     TimerPair t;
     CK(cudaStreamCreateWithFlags(&t.st, cudaStreamNonBlocking));
     t.own_stream = true;
@@ -1288,7 +1448,8 @@ int FLAGSTAT_cuda_time_device_rot(const uint16_t* d_base, uint64_t len, uint64_t
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(t.e0, t.st));
     for (int i = 0; i < iters && rc == 0; ++i)
-        rc = launch(m, d_base + (uint64_t)((uint32_t)i % n_rot) * stride_records, len, d_flags, t.st);
+        rc = launch(m, d_base + (uint64_t)((uint32_t)i % n_rot) * stride_records, len, d_flags, t.st, nullptr,
+                    overlapped);
     CK(cudaEventRecord(t.e1, t.st));
     CK(cudaStreamSynchronize(t.st));
     float ms = 0.f;
@@ -1413,8 +1574,15 @@ extern "C" int FLAGSTAT_cuda_ingest_text(const char* text, uint64_t n_bytes, uin
             if ((rc = (int)cudaGetLastError())) break;
         }
         if (has_tail) {
-            const std::string last(text + tail_lo, text + n_bytes);
-            const uint16_t v = (uint16_t)std::atoi(last.c_str());
+            // atoi stops at the first non-digit after optional white space and sign: 32 characters
+            // are more than it can consume of a value that is then truncated to 16 bits
+            char last[40];
+            uint64_t ws = tail_lo;  // (leading white space of any length is skipped here, as atoi would)
+            while (ws < n_bytes && (text[ws] == ' ' || (text[ws] >= '\t' && text[ws] <= '\r'))) ++ws;
+            const uint64_t tl = n_bytes - ws < sizeof(last) - 1 ? n_bytes - ws : sizeof(last) - 1;
+            std::memcpy(last, text + ws, tl);
+            last[tl] = '\0';
+            const uint16_t v = (uint16_t)std::atoi(last);
             if ((rc = (int)cudaMemcpy(d_out + total, &v, sizeof(v), cudaMemcpyHostToDevice))) break;
         }
         if (flags) {  // count straight from the device column: the text never becomes a host uint16 array

@@ -274,7 +274,14 @@ __device__ __forceinline__ void lds128_imm(uint32_t smem, uint32_t& a, uint32_t&
 __device__ unsigned long long g_timeline[8 * 2048];
 #define FSB_TL(k)                                                                      \
     do {                                                                               \
-        if (threadIdx.x == 0 && blockIdx.x < 2048u) g_timeline[blockIdx.x * 8u + (k)] = global_timer_ns(); \
+        if (threadIdx.x == 0 && blockIdx.x < 2048u) {                                  \
+            g_timeline[blockIdx.x * 8u + (k)] = global_timer_ns();                     \
+            if ((k) == 0) {                                                            \
+                uint32_t sm_;                                                          \
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                       \
+                g_timeline[blockIdx.x * 8u + 6u] = sm_ + 1u;                           \
+            }                                                                          \
+        }                                                                              \
     } while (0)
 #else
 #define FSB_TL(k) do { } while (0)
@@ -287,7 +294,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
 {
     constexpr int DEPTH = 4;  // ring depth == group size
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    pdl_launch_dependents();  // overlapped launches: the next kernel may take SM slots as they free up
+    if (xa.pdl) pdl_launch_dependents();  // overlapped launches: the next kernel may take SM slots as they free up
     FSB_TL(0);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -300,7 +307,8 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
     const uint64_t ntail = n - tail_start;
     const uint64_t NB = V / kVecPerBatch;
     const uint64_t G = gridDim.x;
-    const uint32_t my = (NB > blockIdx.x) ? (uint32_t)((NB - blockIdx.x + G - 1) / G) : 0u;
+    // batches blockIdx.x, blockIdx.x + G, ... < NB = nb_q * G + nb_r (quotient and remainder from the host)
+    const uint32_t my = (uint32_t)xa.nb_q + (blockIdx.x < xa.nb_r ? 1u : 0u);
     const uint64_t stride_bytes = G * (uint64_t)kVecPerBatch * 16u;
 
     GroupLanes<MODE, VARIANT> st;
@@ -310,7 +318,7 @@ flagstat_kernel_group(const uint16_t* __restrict__ base, uint64_t n,
 
     // the CTA that would own batch NB takes the left-over vectors and the ragged
     // records as a partial group of two batches
-    if (blockIdx.x == (uint32_t)(NB % G)) {
+    if (blockIdx.x == xa.nb_r) {
         uint32_t w[16];
         {
             uint4 v[kU];

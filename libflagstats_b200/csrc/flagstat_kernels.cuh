@@ -464,6 +464,13 @@ struct XchgArgs {
     unsigned long long prev_epoch;       // != 0: collect this epoch into prev_out first
     unsigned long long* prev_out;
     unsigned long long* host_err;        // mapped host word, receives the epoch of a timeout (may be null)
+    // launch geometry worked out on the host (64-bit divisions cost a CTA ~0.3 us at its start):
+    // NB full CTA batches = nb_q * gridDim.x + nb_r
+    unsigned long long nb_q;
+    unsigned int nb_r;
+    int pdl;                             // launched with programmatic stream serialization
+    unsigned long long* dyn;             // flagstat_kernel_dyn: this launch's {counter, done tickets, owner} slot
+    unsigned int dyn_tag;                //   ... and the tag that marks the slot as this launch's
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
@@ -484,6 +491,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // Programmatic dependent launch; both are no-ops in a launch without the attribute.
@@ -608,8 +621,8 @@ __device__ __forceinline__ void cta_epilogue(unsigned long long* __restrict__ ou
     __syncthreads();
     if (warp != 0) return;
     // nothing is published before the previous kernel of the stream has completed
-    // (overlapped launches only; returns at once otherwise)
-    pdl_wait_prior_grids();
+    // (overlapped launches only)
+    if (xa.pdl) pdl_wait_prior_grids();
     unsigned long long a = 0ull, f = 0ull;
 #pragma unroll
     for (int i = 0; i < kWarps; ++i) {

@@ -121,11 +121,16 @@ def test_product_never_touches_the_oracle():
     # the library links nothing from oracle/ either
     from libflagstats_b200 import build as b
     assert not any("oracle" in x for x in b.SOURCES + b.HEADERS + b.NVCC_FLAGS)
-    # bench.py: the oracle is imported inside cpu_reference_run() only (cpu_baseline / --impl reference)
+    # bench.py: the oracle is imported inside the cpu_* functions only (cpu_baseline legs / --impl
+    # reference); the GPU legs build their inputs without it (tools/containers.py)
     bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
-    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
-    assert len(uses) == 1
-    assert bench.rfind("def ", 0, uses[0]) == bench.find("def cpu_reference_run")
+    uses = [m.start() for m in re.finditer(r"from oracle import|import oracle", bench)]
+    assert uses
+    for u in uses:
+        d = bench.rfind("\ndef ", 0, u)
+        assert bench[d + 1:].startswith("def cpu_"), bench[d + 1:d + 60]
+    containers = open(os.path.join(ROOT, "tools", "containers.py"), encoding="utf-8").read()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", containers, re.M)
 
 
 def test_header_is_plain_c99_and_cxx11(tmp_path):

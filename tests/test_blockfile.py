@@ -2,6 +2,7 @@
 [int32 raw][int32 comp][LZ4 block] containers (benchmark/flagstats.cpp:110-186,
 288-358, 415-468).  The GPU LZ4 decoder is checked against blocks written by a
 real liblz4 (pyarrow lz4_raw) and by the oracle's own encoder."""
+import ctypes as C
 import struct
 
 import numpy as np
@@ -311,3 +312,64 @@ def test_zstd_container_counts_match_the_column(cuda_lib, level, batch, monkeypa
     with pytest.raises(cuda_lib.FlagstatCudaError):
         blockfile.flagstat_container(bytes(bad), blockfile.ZSTD, flags=f)
     assert f.tolist() == [7] * 32
+
+
+def test_lz4_container_on_a_second_device_after_the_first(cuda_lib):
+    """The > 48 KiB dynamic shared memory opt-in of the decoders is a per-DEVICE function attribute
+    (round-1 advisor finding: it used to be set once per process, so every device but the first one
+    used failed with cudaErrorInvalidValue).  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    fs = cuda_lib
+    a = O.synth_hiseqx(0, 3 * fs.BLOCK_RECORDS + 777, 1, 1000)
+    blob = O.write_lz4_container(a, compressor=O.liblz4_compress)
+    want = O.numpy_flagstat(a).tolist()
+    for variant in (1, 0):
+        prev = fs.lib().FLAGSTAT_cuda_set_lz4_variant(variant)
+        try:
+            for dev in (0, 1, 0, 1):
+                with torch.cuda.device(dev):
+                    f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
+                    assert n == a.size and f.tolist() == want, (variant, dev)
+        finally:
+            fs.lib().FLAGSTAT_cuda_set_lz4_variant(prev)
+
+
+def test_decode_entries_reject_wrapping_descriptors_and_null_arrays(cuda_lib):
+    """comp_off + comp_size (raw_off + raw_size) must not be allowed to wrap past 2^64 (advisor
+    finding), and NULL descriptor arrays are an argument error, not a crash."""
+    fs = cuda_lib
+    lib = fs.lib()
+    raw = O.synth_hiseqx(0, 5000).tobytes()
+    comp = np.frombuffer(O.liblz4_compress(raw), dtype=np.uint8).copy()
+    out = np.zeros(len(raw), np.uint8)
+    status = np.zeros(1, np.int32)
+    u64, u32 = np.uint64, np.uint32
+    ok_args = dict(comp_off=np.array([0], u64), comp_size=np.array([comp.size], u32),
+                   raw_off=np.array([0], u64), raw_size=np.array([len(raw)], u32))
+
+    def call(entry, **kw):
+        a = dict(ok_args, **kw)
+        ptr = lambda x, t: None if x is None else x.ctypes.data_as(t)  # noqa: E731
+        return getattr(lib, entry)(comp.ctypes.data, comp.size, ptr(a["comp_off"], _capi_u64p()), ptr(a["comp_size"], _capi_u32p()),
+                                   ptr(a["raw_off"], _capi_u64p()), ptr(a["raw_size"], _capi_u32p()), 1, out.ctypes.data,
+                                   out.size, status.ctypes.data_as(C.POINTER(C.c_int)))
+
+    for entry in ("FLAGSTAT_cuda_lz4_decode", "FLAGSTAT_cuda_zstd_decode"):
+        assert call(entry, comp_off=np.array([2**64 - 8], u64)) == -2, entry
+        assert call(entry, raw_off=np.array([2**64 - 100], u64)) == -2, entry
+        assert call(entry, comp_size=np.array([comp.size + 1], u32)) == -2, entry
+        for k in ("comp_off", "comp_size", "raw_off", "raw_size"):
+            assert call(entry, **{k: None}) == -2, (entry, k)
+    assert call("FLAGSTAT_cuda_lz4_decode") == 0 and status[0] == len(raw) and out.tobytes() == raw
+
+
+def _capi_u64p():
+    from libflagstats_b200 import _capi
+    return _capi.u64p
+
+
+def _capi_u32p():
+    from libflagstats_b200 import _capi
+    return _capi.u32p

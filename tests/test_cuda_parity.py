@@ -31,10 +31,20 @@ def _dev(a, off=0):
     return v
 
 
+def _select_variant(fs, variant):
+    """Returns the previous variant; skips the test when this build does not contain `variant`
+    (the product library ships 0, 1, 3 and 8; the rest need -DFSB_ALL_VARIANTS)."""
+    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    if prev < 0:
+        assert variant not in (0, 1, 3, 8), "a product variant is missing from the build"
+        pytest.skip(f"kernel variant {variant} is an A/B variant, not compiled into the product library")
+    return prev
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_golden_cases_host_and_device_pointers(cuda_lib, golden, variant):
     fs = cuda_lib
-    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    prev = _select_variant(fs, variant)
     try:
         for c in golden["cases"]:
             a = make_input(c["spec"])
@@ -55,7 +65,7 @@ def test_every_record_value_in_both_register_halves(cuda_lib, variant):
     ar = np.arange(65536, dtype=np.uint32).astype(np.uint16)
     a = np.concatenate([ar, np.zeros(1, np.uint16), ar, ar[::-1], np.full(3, 0x0FFF, np.uint16), ar[::-1]])
     want = O.flagstat_simd(a).tolist()
-    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    prev = _select_variant(fs, variant)
     try:
         assert fs.flagstat_u64(_dev(a)).tolist() == want
         assert fs.flagstat_u64(_dev(a, 1)).tolist() == want
@@ -184,7 +194,7 @@ def test_dense_mode_transitions(cuda_lib, variant):
     host = d.cpu().numpy().view(np.uint16)
     want = O.flagstat_simd(host)
     head = O.flagstat_simd(host[:3])
-    prev = fs.lib().FLAGSTAT_cuda_set_variant(variant)
+    prev = _select_variant(fs, variant)
     try:
         assert fs.flagstat_u64(d).tolist() == want.tolist()
         assert fs.flagstat_u64(d[3:]).tolist() == (want - head).tolist()  # unaligned base

@@ -36,7 +36,7 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def timed(region, n, base, mode, rotate=True, target_ms=60.0):
+def timed(region, n, base, mode, rotate=True, target_ms=60.0, overlapped=False):
     """ms per launch over `region` (a device tensor of 16-bit words)."""
     lib = fs.lib()
     out = torch.zeros(32, dtype=torch.int64, device=region.device)
@@ -48,6 +48,7 @@ def timed(region, n, base, mode, rotate=True, target_ms=60.0):
     else:
         n_rot = 1
     ms = C.c_float(0)
+    mode = mode | (4 if overlapped else 0)
     ptr = region.data_ptr() + 2 * base
     fs.check(lib.FLAGSTAT_cuda_time_device_rot(ptr, n, stride, n_rot, out.data_ptr(), max(3, min(n_rot, 50)),
                                                mode, C.byref(ms)), "time")
@@ -61,12 +62,13 @@ def timed(region, n, base, mode, rotate=True, target_ms=60.0):
     return best, n_rot, iters
 
 
-def row(case, region, n, base=0, mode="flagstat", rotate=True):
-    ms, n_rot, iters = timed(region, n, base, MODES[mode], rotate)
+def row(case, region, n, base=0, mode="flagstat", rotate=True, overlapped=False):
+    ms, n_rot, iters = timed(region, n, base, MODES[mode], rotate, overlapped=overlapped)
     gbs = 2 * n / (ms * 1e-3) / 1e9
     emit(case=case, mode=mode, records=n, base_offset_records=base, ms=round(ms, 6), us=round(ms * 1e3, 3),
          gbs=round(gbs, 1), frac_of_measured_peak=round(gbs / PEAK, 4), grec_s=round(n / (ms * 1e-3) / 1e9, 3),
          copies_rotated=n_rot, distinct_bytes=2 * n * n_rot, from_hbm=bool(2 * n * n_rot > (256 << 20)),
+         launches="overlapped (programmatic dependent launch)" if overlapped else "serialised in one stream",
          iters=iters)
 
 
@@ -86,6 +88,7 @@ def main():
     for e in exps:
         n = 1 << e
         row("sweep hiseqx", hiseqx, n)
+        row("sweep hiseqx, overlapped launches", hiseqx, n, overlapped=True)
         if n <= (1 << 25):
             row("sweep hiseqx hot (one copy, L2-resident)", hiseqx, n, rotate=False)
         if not quick or e % 4 == 0:
@@ -102,9 +105,20 @@ def main():
                 row("sweep samtools uniform12", uniform, n, mode="samtools")
     # BASELINE configs[0]: 100 M records U(0,4095); and the same length HiSeqX-shaped
     for n in (100_000_000, 16_777_216, 50_000_000):
-        row(f"inmemory {n} uniform12 (configs[0] shape)", uniform, n)
-        row(f"inmemory {n} hiseqx", hiseqx, n)
-        row(f"inmemory {n} pospopcnt uniform16", uniform16, n, mode="pospopcnt")
+        for ov in (False, True):
+            tag = ", overlapped launches" if ov else ""
+            row(f"inmemory {n} uniform12 (configs[0] shape){tag}", uniform, n, overlapped=ov)
+            row(f"inmemory {n} hiseqx{tag}", hiseqx, n, overlapped=ov)
+            row(f"inmemory {n} pospopcnt uniform16{tag}", uniform16, n, mode="pospopcnt", overlapped=ov)
+    # static split vs dynamic claims (8 / 16 KiB chunks), and where the default threshold should sit
+    for label, minc, cg in (("static", -1, 1), ("dynamic 8 KiB", 1, 1), ("dynamic 16 KiB", 1, 2)):
+        fs.lib().FLAGSTAT_cuda_set_dynamic(minc, cg)
+        for n in (1 << 22, 1 << 23, 1 << 24, 1 << 25, 50_000_000, 100_000_000, 1 << 28, 824_541_892, 1 << 31):
+            row(f"split={label} hiseqx", hiseqx, n)
+            if n in (100_000_000, 824_541_892):
+                row(f"split={label} uniform12", uniform, n)
+                row(f"split={label} hiseqx, overlapped launches", hiseqx, n, overlapped=True)
+    fs.lib().FLAGSTAT_cuda_set_dynamic(0, 1)
     # grid-size sensitivity in the mid-size regime
     for per_sm in (1, 2):
         fs.lib().FLAGSTAT_cuda_set_ctas_per_sm(per_sm)

@@ -31,7 +31,7 @@ def main():
     pinned_s = (time.perf_counter() - t0) / 3
     print(json.dumps({"case": "pinned", "records": n, "gbs": 2 * n / pinned_s / 1e9, "cpus": len(os.sched_getaffinity(0))}), flush=True)
     for T in (1, 2, 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32):
-        if T > len(os.sched_getaffinity(0)):
+        if T > len(os.sched_getaffinity(0)) or T > 24:
             break
         os.environ["FLAGSTAT_CUDA_IO_THREADS"] = str(T)
         f = fs.flagstat_u64(page)

@@ -62,7 +62,8 @@ def main():
              grec_s=t.numel() / (ms * 1e-3) / 1e9, **{k: v for k, v in kw.items() if k != "iters"})
 
     for variant in (0, 1, 2, 3, 5, 6):
-        lib.FLAGSTAT_cuda_set_variant(variant)
+        if lib.FLAGSTAT_cuda_set_variant(variant) < 0:
+            continue  # A/B variant not compiled into this build (python -m libflagstats_b200.build --all-variants)
         row(f"hiseqx v{variant}", hiseqx)
         row(f"uniform12 (50% QC-fail) v{variant}", uniform)
         row(f"hiseqx 1% QC-fail v{variant}", fail1pct)

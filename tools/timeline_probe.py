@@ -48,36 +48,72 @@ def main():
     out = torch.zeros(32, dtype=torch.int64, device="cuda")
     st = torch.cuda.Stream()
     names = ["entry", "ring_primed", "first_stage_landed", "loop_done", "flush_done", "epilogue_done"]
-    for per_sm in (0, 1):
+
+    def fetch():
+        tl = np.zeros(8 * 2048, np.uint64)
+        assert lib.FLAGSTAT_cuda_timeline_fetch(tl.ctypes.data, tl.size) == 0
+        tl = tl.reshape(2048, 8)
+        return tl[tl[:, 0] != 0].astype(np.int64)
+
+    def summarize(t, rec):
+        t0 = t[:, 0].min()
+        for k, nm in enumerate(names):
+            col = t[:, k][t[:, k] != 0] - t0
+            if col.size:
+                rec[nm] = {"min_us": round(col.min() / 1e3, 2), "median_us": round(float(np.median(col)) / 1e3, 2),
+                           "max_us": round(col.max() / 1e3, 2)}
+        # is the spread of loop_done systematic by SM?  mean loop_done per SM id, slowest / fastest five
+        sm = t[:, 6] - 1
+        done = (t[:, 3] - t0) / 1e3
+        per = {}
+        for a, b in zip(sm.tolist(), done.tolist()):
+            per.setdefault(a, []).append(b)
+        means = sorted((float(np.mean(v)), k) for k, v in per.items())
+        rec["sms_used"] = len(per)
+        rec["fastest_sms"] = [(k, round(m, 1)) for m, k in means[:5]]
+        rec["slowest_sms"] = [(k, round(m, 1)) for m, k in means[-5:]]
+        return rec
+
+    lib.FLAGSTAT_cuda_set_dynamic.argtypes = [C.c_longlong, C.c_int]
+    for per_sm, dyn in ((0, -1), (0, 1), (1, -1)):  # static split, dynamic claims (8 KiB chunks), static at 1 CTA / SM
         lib.FLAGSTAT_cuda_set_ctas_per_sm(per_sm)
+        lib.FLAGSTAT_cuda_set_dynamic(dyn, 1)
         for n in (1 << 10, 1 << 20, 1 << 22, 1 << 24, 100_000_000, 1 << 28, big):
-            rows = []
-            for rep in range(4):
-                flush.fill_(rep)  # evict the column from L2
+            if dyn == 1 and n < (1 << 22):
+                continue
+            # (a) one launch alone, column not in L2
+            for rep in range(3):
+                flush.fill_(rep)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 lib.FLAGSTAT_cuda_timeline_clear()
-                with torch.cuda.stream(st):
-                    e0.record(st)
-                    assert lib.FLAGSTAT_cuda_device(data.data_ptr(), n, out.data_ptr(), C.c_void_p(st.cuda_stream)) == 0
-                    e1.record(st)
+                e0.record(st)
+                assert lib.FLAGSTAT_cuda_device(data.data_ptr(), n, out.data_ptr(), C.c_void_p(st.cuda_stream)) == 0
+                e1.record(st)
                 st.synchronize()
-                tl = np.zeros(8 * 2048, np.uint64)
-                assert lib.FLAGSTAT_cuda_timeline_fetch(tl.ctypes.data, tl.size) == 0
-                tl = tl.reshape(2048, 8)
-                live = tl[:, 0] != 0
-                t = tl[live].astype(np.int64)
-                t0 = t[:, 0].min()
-                rec = {"records": n, "ctas_per_sm": per_sm or "default", "ctas": int(live.sum()), "rep": rep,
-                       "event_us": round(e0.elapsed_time(e1) * 1e3, 2),
-                       "ideal_us_at_7TBs": round(2 * n / 7.0e6, 2)}
-                for k, nm in enumerate(names):
-                    col = t[:, k][t[:, k] != 0] - t0
-                    if col.size:
-                        rec[nm] = {"min_us": round(col.min() / 1e3, 2), "median_us": round(float(np.median(col)) / 1e3, 2),
-                                   "max_us": round(col.max() / 1e3, 2)}
-                rows.append(rec)
-            print(json.dumps(rows[-1]), flush=True)  # the last repetition (clocks settled)
+            rec = {"how": "alone", "split": "dynamic" if dyn == 1 else "static", "records": n, "ctas_per_sm": per_sm or "default",
+                   "event_us": round(e0.elapsed_time(e1) * 1e3, 2), "ideal_us_at_7TBs": round(2 * n / 7.0e6, 2)}
+            t = fetch()
+            rec["ctas"] = int(t.shape[0])
+            print(json.dumps(summarize(t, rec)), flush=True)
+            # (b) the last of 8 back-to-back launches over rotating copies (steady state, from HBM)
+            stride = (n + 15) // 8 * 8
+            copies = max(1, min(8, (big - 8) // stride))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lib.FLAGSTAT_cuda_timeline_clear()
+            e0.record(st)
+            for i in range(8):
+                assert lib.FLAGSTAT_cuda_device(data.data_ptr() + 2 * stride * (i % copies), n, out.data_ptr(),
+                                                C.c_void_p(st.cuda_stream)) == 0
+            e1.record(st)
+            st.synchronize()
+            rec = {"how": "last of 8 back-to-back", "split": "dynamic" if dyn == 1 else "static", "records": n, "ctas_per_sm": per_sm or "default",
+                   "event_us_per_launch": round(e0.elapsed_time(e1) * 1e3 / 8, 2), "copies": copies,
+                   "ideal_us_at_7TBs": round(2 * n / 7.0e6, 2)}
+            t = fetch()
+            rec["ctas"] = int(t.shape[0])
+            print(json.dumps(summarize(t, rec)), flush=True)
 
 
 if __name__ == "__main__":
