@@ -82,8 +82,12 @@ int FLAGSTAT_cuda_available(void);
 
 /* Length at or above which FLAGSTATS_get_function should pick FLAGSTAT_cuda for
  * HOST data (the analogue of the 1024/512/256 thresholds, :3000,3006,3016).
- * Defaults to 262144 (where one PCIe round trip starts to beat one AVX-512 core);
- * env FLAGSTAT_CUDA_MIN_LEN or the setter override it. */
+ * Default 1,048,576 records: the measured crossover of one synchronous call on PAGEABLE host
+ * memory against FLAGSTAT_avx512 on one core of a B200 host (227 vs 253 us; at the reference's
+ * 512,000-record block it is a tie, 129 vs 126 us, because staging pageable memory costs one
+ * core about what the AVX-512 kernel costs -- so the reference's own block loop stays on the
+ * CPU by default).  Callers with PINNED buffers win from 131,072 records (24.7 vs 31.7 us) and
+ * lower it through env FLAGSTAT_CUDA_MIN_LEN or the setter.  profiles/r4c_dropin_time.jsonl. */
 uint32_t FLAGSTAT_cuda_min_len(void);
 void FLAGSTAT_cuda_set_min_len(uint32_t n);
 
@@ -317,11 +321,12 @@ int FLAGSTAT_cuda_set_lz4_variant(int variant);
 const char* FLAGSTAT_cuda_kernel_name(int mode);
 /* Persistent-grid size override: CTAs per SM (0 = default). */
 int FLAGSTAT_cuda_set_ctas_per_sm(int n);
-/* Work distribution of the default kernel.  Long columns are handed out dynamically (every warp
- * claims 8 KiB chunks from a shared counter, so slow SMs simply take fewer); short ones are split
- * statically.  min_chunks: -1 = always static, 0 = default threshold (6 chunks per resident
- * warp, ~58 M records on a B200), > 0 = dynamic from that many chunks on (tests force 1).
- * groups_per_chunk: 1 or 2 (8 / 16 KiB per claim), 0 = leave unchanged. */
+/* A/B builds (-DFSB_ALL_VARIANTS) only: hand the work of the default kernel out dynamically (every
+ * warp claims 8 KiB chunks from per-launch counters) instead of splitting it statically.
+ * min_chunks: -1 = static (the only value the product library accepts), 0 = dynamic from 6
+ * chunks per resident warp on, > 0 = dynamic from that many chunks on.  groups_per_chunk: 1 or
+ * 2 (8 / 16 KiB per claim), 0 = leave unchanged.  Measured: balances the CTAs, does not shorten
+ * the launch (profiles/r4h_*). */
 int FLAGSTAT_cuda_set_dynamic(long long min_chunks, int groups_per_chunk);
 
 /* Deterministic synthetic FLAG columns, pure functions of the GLOBAL record

@@ -229,6 +229,29 @@ int main(int argc, char** argv)
         bad += compare(want, counters, total, "block loop");
     }
 
+    // the same block loop with the threshold lowered the way a caller with short blocks would
+    // (FLAGSTAT_cuda_set_min_len): every 512,000-record block must now go to the device
+    if (have_gpu) {
+        FLAGSTAT_cuda_set_min_len(4096);
+        uint32_t counters[32] = {0}, want[32] = {0};
+        const uint32_t block = 512000;
+        int on_device = 0;
+        for (uint32_t lo = 0; lo < total; lo += block) {
+            const uint32_t N = (total - lo < block) ? (total - lo) : block;
+            FLAGSTATS_func func = FLAGSTATS_get_function(N);
+            on_device += func == &FLAGSTAT_cuda;
+            (*func)(flags.data() + lo, N, counters);
+        }
+        FLAGSTAT_scalar(flags.data(), total, want);
+        bad += compare(want, counters, total, "block loop on the device");
+        if (on_device != (int)((total + block - 1) / block)) {
+            std::printf("FAIL: min_len = 4096 but only %d blocks went to FLAGSTAT_cuda\n", on_device);
+            ++bad;
+        }
+        cuda_selected += on_device;
+        FLAGSTAT_cuda_set_min_len(thr);
+    }
+
     if (have_gpu && cuda_selected == 0) {
         std::printf("FAIL: a device is present but FLAGSTAT_cuda was never selected\n");
         ++bad;

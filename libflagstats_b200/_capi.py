@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libflagstats_cuda.so")
+# LIBFLAGSTATS_CUDA_SO: load another build of the same ABI instead (the -DFSB_ALL_VARIANTS A/B
+# build in tools/bin/, for the variant tests and tools); the product path is the in-tree library
+SO_PATH = os.environ.get("LIBFLAGSTATS_CUDA_SO") or os.path.join(HERE, "libflagstats_cuda.so")
 
 u16p = C.POINTER(C.c_uint16)
 u32p = C.POINTER(C.c_uint32)

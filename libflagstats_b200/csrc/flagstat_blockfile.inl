@@ -586,10 +586,30 @@ int consume_staged(int mode, uint64_t size, size_t slot_bytes, Fill fill, uint64
     return 0;
 }
 
+// Slot size of the raw-file reader: 8 MB DMAs reach the link rate when ONE producer feeds them
+// (block stream, section 8 of DESIGN.md), but T readers that all start with an 8 MB pread leave
+// the link idle for the first ~0.8 ms and drain as long at the end -- a tenth of a 410 MB file.
+// Smaller slots start the first DMA earlier; the per-DMA fixed cost overlaps across the T
+// streams.  FLAGSTAT_CUDA_RAW_SLOT_KB overrides (A/B: tools/file_bench.py).
+size_t raw_slot_bytes(uint64_t file_size, int threads)
+{
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_RAW_SLOT_KB")) {
+        size_t v = (size_t)std::strtoull(e, nullptr, 10) << 10;
+        v &= ~(size_t)65535u;
+        if (v >= (64u << 10) && v <= kRawSlotBytes) return v;
+    }
+    // at least ~8 slots per thread, between 1 MiB and the ring slot
+    size_t v = (size_t)(file_size / ((uint64_t)threads * 8u));
+    v = (v + 65535u) & ~(size_t)65535u;
+    if (v < (1u << 20)) v = 1u << 20;
+    if (v > (kRawSlotBytes & ~(size_t)65535u)) v = kRawSlotBytes & ~(size_t)65535u;
+    return v;
+}
+
 int consume_raw_fd(int mode, int fd, uint64_t size, uint64_t* totals, uint64_t* n_records)
 {
     const int rc = consume_staged(
-        mode, size, kRawSlotBytes,
+        mode, size, raw_slot_bytes(size, io_threads()),
         [fd](unsigned char* h, uint64_t off, size_t len) {
             size_t got = 0;
             while (got < len) {

@@ -27,7 +27,9 @@
 #include "flagstat_kernels.cuh"
 #include "flagstat_kernel_tma.cuh"
 #include "flagstat_kernel_group.cuh"
-#include "flagstat_kernel_dyn.cuh"
+#ifdef FSB_ALL_VARIANTS
+#include "flagstat_kernel_dyn.cuh"  // dynamically scheduled twin of the default kernel: a measured non-gain, A/B builds only
+#endif
 #include "synth.cuh"
 #include "lz4_block.cuh"
 #include "lz4_block_group.cuh"
@@ -163,8 +165,15 @@ const KernelCfg kSamtoolsKernel = {
     {flagstat_kernel_group<kSamtools, 3, 2>, flagstat_kernel_group<kSamtools, 3, 2>},
     kThreads, (size_t)4 * kStageBytes};
 
-// The default variant's dynamically scheduled twin (flagstat_kernel_dyn.cuh), by mode.  CG = 8 KiB
-// groups per claimed chunk: kDynCG (A/B: FLAGSTAT_CUDA_DYN_CG=2 selects the 16 KiB instantiation).
+// The default variant's dynamically scheduled twin (flagstat_kernel_dyn.cuh), by mode: every warp
+// claims 8 / 16 KiB chunks from per-launch counters instead of taking a static share.  It does
+// what it was built for -- the CTAs of a launch leave the loop within 2 % of each other instead
+// of 194 ... 232 us apart on the 1.65 GB column -- and the launch is no faster for it
+// (244 vs 243 us sustained, 41.6 vs 40.6 us at 100 M records; profiles/r4h_*): the CTAs that a
+// static split lets finish early leave their share of the HBM to the others, the machine is
+// limited by its aggregate rate either way.  Kept for A/B builds (-DFSB_ALL_VARIANTS) with its
+// tests; the product library does not contain it.
+#ifdef FSB_ALL_VARIANTS
 constexpr int kDynCG = 1;
 const KernelFn kDynKernels[2][3] = {
     {flagstat_kernel_dyn<kFlagstat, 3, 2, 1>, flagstat_kernel_dyn<kPospopcnt, 0, 2, 1>,
@@ -178,16 +187,19 @@ struct DynStream {
     int base;        // slot pair index
     uint64_t count;  // launches of the dynamic kernel on this stream so far: parity picks the slot
 };
+#endif
 
 struct DeviceInfo {
     int sms = 0;
     int occ[kNumVariants][2];  // resident CTAs per SM
     int occ_samtools = 2;
+#ifdef FSB_ALL_VARIANTS
     int occ_dyn[3] = {2, 2, 2};
     unsigned char* dyn = nullptr;  // kDynStreams x 2 slots of kDynSlotBytes (device memory, zeroed)
     std::unordered_map<cudaStream_t, DynStream> dyn_map;
     std::mutex dyn_mu;
     std::atomic<uint32_t> dyn_tag{0};
+#endif
     bool ok = false;
 };
 
@@ -252,6 +264,12 @@ int device_info(int dev, DeviceInfo** out)
             }
             d.occ_samtools = nb < 1 ? 1 : nb;
         }
+        // the LZ4 block decoders of flagstat_blockfile.inl (> 48 KiB of dynamic shared memory)
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem));
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem));
+#ifdef FSB_ALL_VARIANTS
         for (int c = 0; c < 2; ++c)
             for (int m = 0; m < 3; ++m) {
                 const void* fn = reinterpret_cast<const void*>(kDynKernels[c][m]);
@@ -264,13 +282,9 @@ int device_info(int dev, DeviceInfo** out)
                 }
                 if (c == 0) d.occ_dyn[m] = nb < 1 ? 1 : nb;
             }
-        // the LZ4 block decoders of flagstat_blockfile.inl (> 48 KiB of dynamic shared memory)
-        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_kernel),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem));
-        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem));
         CK(cudaMalloc(&d.dyn, (size_t)kDynStreams * 2 * kDynSlotBytes));
         CK(cudaMemset(d.dyn, 0, (size_t)kDynStreams * 2 * kDynSlotBytes));
+#endif
         if (cur != dev && cur >= 0) CK(cudaSetDevice(cur));
         d.ok = true;
     }
@@ -278,9 +292,10 @@ int device_info(int dev, DeviceInfo** out)
     return 0;
 }
 
-// Dynamic scheduling knobs (FLAGSTAT_cuda_set_dynamic; env FLAGSTAT_CUDA_DYNAMIC=0 switches it off,
+#ifdef FSB_ALL_VARIANTS
+// Dynamic scheduling knobs (FLAGSTAT_cuda_set_dynamic; env FLAGSTAT_CUDA_DYNAMIC=1 switches it on,
 // FLAGSTAT_CUDA_DYN_MIN_CHUNKS / FLAGSTAT_CUDA_DYN_CG preset the other two):
-//   g_dyn_min_chunks  -1 off; 0 default = 6 chunks per resident warp (~58 M records on a B200);
+//   g_dyn_min_chunks  -1 off (default); 0 = from 6 chunks per resident warp (~58 M records on a B200);
 //                     > 0: use the dynamic kernel from that many chunks on (tests force 1)
 //   g_dyn_cg          8 KiB groups per claimed chunk: 1 or 2
 std::atomic<long long> g_dyn_min_chunks{-2};  // -2 = read the environment first
@@ -290,11 +305,11 @@ long long dyn_min_chunks()
 {
     long long v = g_dyn_min_chunks.load(std::memory_order_relaxed);
     if (v == -2) {
-        v = 0;
+        v = -1;  // off unless asked for: it is an A/B kernel
         if (const char* e = std::getenv("FLAGSTAT_CUDA_DYNAMIC"))
-            if (std::atoi(e) == 0) v = -1;
-        if (v == 0)
-            if (const char* e = std::getenv("FLAGSTAT_CUDA_DYN_MIN_CHUNKS")) v = std::atoll(e) > 0 ? std::atoll(e) : 0;
+            if (std::atoi(e) != 0) v = 0;
+        if (const char* e = std::getenv("FLAGSTAT_CUDA_DYN_MIN_CHUNKS"))
+            if (std::atoll(e) > 0) v = std::atoll(e);
         g_dyn_min_chunks.store(v);
     }
     return v;
@@ -336,6 +351,8 @@ unsigned long long* dyn_slot(DeviceInfo* di, cudaStream_t st, unsigned int* tag)
     const uint64_t k = it->second.count++;
     return reinterpret_cast<unsigned long long*>(di->dyn + ((size_t)it->second.base * 2 + (size_t)(k & 1u)) * kDynSlotBytes);
 }
+
+#endif  // FSB_ALL_VARIANTS
 
 // Enqueue one kernel on the current device.
 // overlap: launch with the programmatic-stream-serialization attribute, so that this kernel's
@@ -383,6 +400,7 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
     args.dyn = nullptr;
     // Columns long enough to keep every resident warp busy for several chunks take the dynamically
     // scheduled twin of the default kernel (same arithmetic, work claimed per warp from a counter).
+#ifdef FSB_ALL_VARIANTS
     if ((variant == 0 || sam) && default_grid && dyn_min_chunks() >= 0) {
         const int cg = dyn_cg();
         const uint64_t chunk_vec = (uint64_t)cg * kDynWarpVecPerGroup;
@@ -397,6 +415,9 @@ int launch(int mode, const uint16_t* d_array, uint64_t n, uint64_t* d_out, cudaS
             }
         }
     }
+#else
+    (void)default_grid;
+#endif
     if (overlap && !g_pdl_unsupported.load(std::memory_order_relaxed)) {
         args.pdl = 1;
         cudaLaunchConfig_t cfg = {};
@@ -524,7 +545,9 @@ uint64_t pageable_min_bytes()
 {
     static const uint64_t v = [] {
         if (const char* e = std::getenv("FLAGSTAT_CUDA_PAGEABLE_MIN")) return (uint64_t)std::strtoull(e, nullptr, 10);
-        return (uint64_t)(8u << 20);
+        // spawning the staging threads costs ~0.5 ms: below ~16 MB the plain cudaMemcpyAsync of
+        // pageable memory is faster (4 M records: 1.11 ms threaded vs ~0.83 ms plain, r4c_dropin_time.jsonl)
+        return (uint64_t)(16u << 20);
     }();
     return v;
 }
@@ -641,7 +664,15 @@ uint32_t min_len_init()
 {
     uint32_t v = g_min_len.load();
     if (v) return v;
-    v = 262144u;
+    // Measured, not guessed (profiles/r4c_dropin_time.jsonl, r4e_dropin_time.jsonl: one synchronous
+    // FLAGSTAT_cuda call per n records of PAGEABLE host memory -- what the reference's callers hand
+    // over -- against FLAGSTAT_avx512 on one core of the same host): 524,288 records 129 vs 126 us
+    // (a tie: the driver's single-threaded staging copy of pageable memory costs as much as the
+    // AVX-512 kernel), 1,048,576 records 227 vs 253 us, 2,097,152 418 vs 506 us, and from 8 M records
+    // on the threaded staging path pulls away (16.7 M: 1.85 vs 4.07 ms).  From PINNED memory the
+    // call wins from 131,072 records (24.7 vs 31.7 us): callers that own pinned buffers lower the
+    // threshold with FLAGSTAT_CUDA_MIN_LEN / FLAGSTAT_cuda_set_min_len.
+    v = 1048576u;
     if (const char* e = std::getenv("FLAGSTAT_CUDA_MIN_LEN")) {
         const unsigned long long t = std::strtoull(e, nullptr, 10);
         if (t > 0 && t <= 0xFFFFFFFFull) v = (uint32_t)t;
@@ -1318,11 +1349,16 @@ int FLAGSTAT_cuda_set_ctas_per_sm(int n) { return g_ctas_per_sm.exchange(n); }
 
 int FLAGSTAT_cuda_set_dynamic(long long min_chunks, int groups_per_chunk)
 {
+#ifndef FSB_ALL_VARIANTS
+    (void)groups_per_chunk;
+    return min_chunks == -1 ? 0 : FLAGSTAT_CUDA_EINVAL;  // the product library has the static split only
+#else
     if (min_chunks < -1 || (groups_per_chunk != 0 && groups_per_chunk != 1 && groups_per_chunk != 2))
         return FLAGSTAT_CUDA_EINVAL;
     g_dyn_min_chunks.store(min_chunks);
     if (groups_per_chunk) g_dyn_cg.store(groups_per_chunk);
     return 0;
+#endif
 }
 
 const char* FLAGSTAT_cuda_kernel_name(int mode)
@@ -1348,6 +1384,7 @@ const char* FLAGSTAT_cuda_kernel_name(int mode)
     if (!variant_built(v)) v = 0;
     // long columns (>= 6 chunks per resident warp) of the default variant run its dynamically
     // scheduled twin; that is the instantiation the bench workloads launch
+#ifdef FSB_ALL_VARIANTS
     if ((v == 0 || mode == kSamtools) && dyn_min_chunks() >= 0) {
         static const char* const kDyn[2][3] = {
             {"fsb200::flagstat_kernel_dyn<0, 3, 2, 1>", "fsb200::flagstat_kernel_dyn<1, 0, 2, 1>",
@@ -1356,6 +1393,7 @@ const char* FLAGSTAT_cuda_kernel_name(int mode)
              "fsb200::flagstat_kernel_dyn<2, 3, 2, 2>"}};
         return kDyn[dyn_cg() - 1][mode == kSamtools ? 2 : mode == kPospopcnt ? 1 : 0];
     }
+#endif
     if (mode == kSamtools) return "fsb200::flagstat_kernel_group<2, 3, 2>";
     return kNames[v][mode == kPospopcnt ? 1 : 0];
 }
@@ -1502,6 +1540,21 @@ int FLAGSTAT_cuda_read_probe(const void* d_bytes, uint64_t n_bytes, int iters, f
     *ms_per_launch = ms / (float)iters;
     return 0;
 }
+
+#ifdef FSB_LZ4_PROFILE
+// probe build only (tools/lz4_phase_probe.py): clock64() sums per phase of the LZ4 group decoder
+int FLAGSTAT_cuda_lz4_profile_fetch(unsigned long long* out16, int clear)
+{
+    if (!out16) return FLAGSTAT_CUDA_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out16, fsb200::g_lz4_prof, 16 * sizeof(unsigned long long)));
+    if (clear) {
+        unsigned long long z[16] = {0};
+        CK(cudaMemcpyToSymbol(fsb200::g_lz4_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
 
 #ifdef FSB_TIMELINE
 // probe build only (tools/timeline_probe.py): the per-CTA time stamps of the last group-kernel launch

@@ -126,6 +126,30 @@ __device__ __forceinline__ int lz4g_slow_sequence(const uint8_t* __restrict__ in
     return ip < in_size ? 0 : 1;
 }
 
+// Phase profile (tools/lz4_phase_probe.py builds with -DFSB_LZ4_PROFILE; never in the product):
+// lane 0 of every warp sums clock64() deltas per phase of the group step.
+#ifdef FSB_LZ4_PROFILE
+__device__ unsigned long long g_lz4_prof[16];
+#define LZ4P_DECL long long lz4p_t = clock64(); long long lz4p_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define LZ4P(k)                                   \
+    do {                                          \
+        const long long now_ = clock64();         \
+        lz4p_acc[k] += now_ - lz4p_t;             \
+        lz4p_t = now_;                            \
+    } while (0)
+#define LZ4P_COUNT(k, v) lz4p_acc[k] += (v)
+#define LZ4P_DUMP                                                                       \
+    do {                                                                                \
+        if (lane == 0)                                                                  \
+            for (int k_ = 0; k_ < 12; ++k_) atomicAdd(&g_lz4_prof[k_], (unsigned long long)lz4p_acc[k_]); \
+    } while (0)
+#else
+#define LZ4P_DECL do { } while (0)
+#define LZ4P(k) do { } while (0)
+#define LZ4P_COUNT(k, v) do { } while (0)
+#define LZ4P_DUMP do { } while (0)
+#endif
+
 // Returns the number of bytes produced, or a negative code for a malformed block.
 __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict__ in, uint32_t in_size,
                                                        const Lz4Out& o, uint8_t* win, uint8_t* nx,
@@ -134,7 +158,9 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
     constexpr uint32_t kFull = 0xffffffffu;
     uint32_t ip = 0u, op = 0u, flushed = 0u;
     if (in_size == 0u) return 0;
+    LZ4P_DECL;
     for (;;) {
+        LZ4P(9);  // loop overhead / flush tail of the previous step
         const uint32_t avail = in_size - ip;  // > 0
         uint32_t K = 0u, pos = 0u, endp = 0u;
         if (lane < 8u) {  // the next windows: have their lines on the way
@@ -174,6 +200,7 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
                 nx[p] = (uint8_t)(p + len);  // successor; a position that cannot start a sequence loops
             }
             __syncwarp();
+            LZ4P(0);  // stage + successor sizes
             // 2. successor tables by doubling: nx[L][p] = 2^L-th successor of p
 #pragma unroll
             for (uint32_t L = 1; L < 5u; ++L) {
@@ -194,11 +221,14 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
             endp = nx[p];
             // a lane that landed on a looping position, or walked through one, is past the end
             K = __popc(__ballot_sync(kFull, endp != p));
+            LZ4P(1);  // doubling + walk
         }
         if (K == 0u) {
             lz4g_flush(o, flushed, op, true, lane);
             const int r = lz4g_slow_sequence(in, in_size, o, out_cap, lane, ip, op);
             flushed = op;
+            LZ4P(8);  // slow-path sequence
+            LZ4P_COUNT(10, 1);  // slow sequences
             if (r < 0) return r;
             if (r == 1) break;
             continue;
@@ -233,6 +263,9 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
         const uint32_t o_k = op + incl - tot;  // first output byte of the sequence (mine only)
         const uint32_t m_k = o_k + lit;        // first byte of its match
         if (__any_sync(kFull, mine && (off == 0u || off > m_k))) return -4;
+        LZ4P(2);  // parse + scan
+        LZ4P_COUNT(7, 1);  // group steps; slot 6 sums their sequences
+        LZ4P_COUNT(6, K);
 
         // 4a. literals (input never aliases output); a literal byte is its own root
         const uint32_t maxlit = __reduce_max_sync(kFull, lit);
@@ -242,6 +275,7 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
                 P[o_k - op + i] = (uint16_t)(o_k - op + i);
             }
 
+        LZ4P(3);  // literals
         // 4b. matches.  Every match byte gets a parent: the output byte it copies
         // (src + i, or src + i % off for an overlapping match, so that a run costs one
         // hop).  A parent produced before this group is copied right away and the byte
@@ -289,6 +323,7 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
             }
         }
         __syncwarp();
+        LZ4P(4);  // parent pointers (short + extended matches)
         // pointer jumping, in place: whatever a lane reads from P[] is an ancestor
         for (;;) {
             bool changed = false;
@@ -311,12 +346,15 @@ __device__ __forceinline__ int lz4_decode_block_group(const uint8_t* __restrict_
             if (r != b) o.ring[o.ridx(op + b)] = o.ring[o.ridx(op + r)];
         }
         __syncwarp();
+        LZ4P(5);  // pointer jumping + root copy
         ip += consumed;
         op += total;
         // 5. whole 16-byte chunks to HBM
         lz4g_flush(o, flushed, op, false, lane);
     }
     lz4g_flush(o, flushed, op, true, lane);
+    LZ4P(9);
+    LZ4P_DUMP;
     return (int)op;
 }
 

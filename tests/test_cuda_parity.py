@@ -315,9 +315,9 @@ def test_multi_device_entry_and_errors(cuda_lib):
     assert fs.lib().FLAGSTAT_cuda_launch_count() > 0
 
 
-@pytest.mark.parametrize("n,off", [(4_194_304, 0), (20_000_003, 1), (37_123_457, 3)])
+@pytest.mark.parametrize("n,off", [(8_388_608, 0), (20_000_003, 1), (37_123_457, 3)])
 def test_pageable_host_arrays_take_the_threaded_staging_path(cuda_lib, n, off):
-    """numpy memory is pageable: arrays >= 8 MiB go through run_pageable() (T threads copy
+    """numpy memory is pageable: arrays >= 16 MiB go through run_pageable() (T threads copy
     slices into pinned slots; one DMA + launch per slice).  Same counters as the oracle for
     flagstat, the reference's uint32 signature and pospopcnt; ragged lengths, odd bases."""
     fs = cuda_lib

@@ -77,9 +77,17 @@ def test_patched_reference_dispatch_selects_flagstat_cuda():
     assert os.path.exists(CHECK), "oracle/_ref/dropin_check missing (integration/build_dropin.sh)"
     r = subprocess.run([CHECK], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "n=512000   -> FLAGSTAT_cuda" in r.stdout, r.stdout
+    # default FLAGSTAT_cuda_min_len = 1,048,576 (the measured pageable-memory crossover): long columns go to
+    # the device, the reference's own 512,000-record block stays on the CPU kernels ...
+    assert "n=5300123  -> FLAGSTAT_cuda" in r.stdout, r.stdout
+    assert "n=512000   -> FLAGSTAT_avx" in r.stdout or "n=512000   -> FLAGSTAT_sse4" in r.stdout, r.stdout
     assert "n=65536    -> FLAGSTAT_avx" in r.stdout or "n=65536    -> FLAGSTAT_sse4" in r.stdout, r.stdout
+    # ... and with FLAGSTAT_cuda_set_min_len(4096) every block of the loop (11 blocks) goes to the device:
+    # dropin_check fails ("only N blocks went to FLAGSTAT_cuda") otherwise
+    assert "MISMATCH" not in r.stdout and "FAIL" not in r.stdout, r.stdout
     assert "OK (cuda selected for" in r.stdout
+    selected = int(r.stdout.rsplit("cuda selected for", 1)[1].split()[0])
+    assert selected >= 11 + 2, r.stdout
 
 
 @pytest.mark.gpu

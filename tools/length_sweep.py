@@ -112,18 +112,23 @@ def main():
             row(f"inmemory {n} pospopcnt uniform16{tag}", uniform16, n, mode="pospopcnt", overlapped=ov)
     # static split vs dynamic claims (8 / 16 KiB chunks), and where the default threshold should sit
     for label, minc, cg in (("static", -1, 1), ("dynamic 8 KiB", 1, 1), ("dynamic 16 KiB", 1, 2)):
-        fs.lib().FLAGSTAT_cuda_set_dynamic(minc, cg)
+        if fs.lib().FLAGSTAT_cuda_set_dynamic(minc, cg) != 0:
+            continue  # the dynamic kernel is in -DFSB_ALL_VARIANTS builds only (LIBFLAGSTATS_CUDA_SO=tools/bin/...)
         for n in (1 << 22, 1 << 23, 1 << 24, 1 << 25, 50_000_000, 100_000_000, 1 << 28, 824_541_892, 1 << 31):
             row(f"split={label} hiseqx", hiseqx, n)
             if n in (100_000_000, 824_541_892):
                 row(f"split={label} uniform12", uniform, n)
                 row(f"split={label} hiseqx, overlapped launches", hiseqx, n, overlapped=True)
-    fs.lib().FLAGSTAT_cuda_set_dynamic(0, 1)
+    fs.lib().FLAGSTAT_cuda_set_dynamic(-1, 0)
     # grid-size sensitivity in the mid-size regime
     for per_sm in (1, 2):
         fs.lib().FLAGSTAT_cuda_set_ctas_per_sm(per_sm)
-        for n in (1 << 20, 1 << 22, 1 << 24, 100_000_000):
+        for n in (1 << 22, 1 << 24, 1 << 25, 50_000_000, 1 << 26, 100_000_000, 1 << 27, 200_000_000, 1 << 28,
+                  400_000_000, 1 << 29, 824_541_892):
             row(f"ctas_per_sm={per_sm} hiseqx", hiseqx, n)
+            if n >= 50_000_000 and n <= (1 << 30):
+                row(f"ctas_per_sm={per_sm} uniform12", uniform, n)
+                row(f"ctas_per_sm={per_sm} hiseqx, overlapped launches", hiseqx, n, overlapped=True)
     fs.lib().FLAGSTAT_cuda_set_ctas_per_sm(0)
 
 

@@ -26,7 +26,7 @@ def build():
     deps = [os.path.join(B.CSRC, f) for f in os.listdir(B.CSRC)]
     if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return
-    subprocess.check_call([B.nvcc()] + B.NVCC_FLAGS + ["-DFSB_TIMELINE", "-o", SO, src])
+    subprocess.check_call([B.nvcc()] + B.NVCC_FLAGS + ["-DFSB_TIMELINE", "-DFSB_ALL_VARIANTS", "-o", SO, src])
 
 
 def main():
