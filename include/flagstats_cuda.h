@@ -312,9 +312,9 @@ uint64_t FLAGSTAT_cuda_launch_count(void);
  * 0 (default), 1 (integer-only mask select), 3 (TMA-staged) and 8 (compare-mask forms); the
  * other measured-and-superseded variants need a -DFSB_ALL_VARIANTS build. */
 int FLAGSTAT_cuda_set_variant(int variant);
-/* LZ4 block decoder for A/B tests: 1 = 32 sequences per warp step (default), 0 = one
- * sequence per warp step.  Returns the previous.  Env FLAGSTAT_CUDA_LZ4_VARIANT sets the
- * initial value. */
+/* LZ4 block decoder for A/B tests: 2 = one CTA per block, parse and copy phases (default),
+ * 1 = one warp per block, 32 sequences per step, 0 = one warp per block, one sequence per
+ * step.  Returns the previous.  Env FLAGSTAT_CUDA_LZ4_VARIANT sets the initial value. */
 int FLAGSTAT_cuda_set_lz4_variant(int variant);
 /* Name of the kernel instantiation the selected variant launches (as ncu prints it);
  * mode 0 = flagstat, 1 = pospopcnt, 2 = samtools. */

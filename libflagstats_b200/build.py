@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libflagstats_cuda.so")
 
 SOURCES = ["flagstat_capi.cu"]
-HEADERS = ["flagstat_kernels.cuh", "flagstat_kernel_tma.cuh", "flagstat_kernel_group.cuh", "flagstat_kernel_dyn.cuh", "lz4_block.cuh", "lz4_block_group.cuh", "zstd_frame.cuh", "zstd_block.cuh", "ingest_text.cuh", "flagstat_blockfile.inl", "bitcounter.cuh", "synth.cuh",
+HEADERS = ["flagstat_kernels.cuh", "flagstat_kernel_tma.cuh", "flagstat_kernel_group.cuh", "flagstat_kernel_dyn.cuh", "lz4_block.cuh", "lz4_block_group.cuh", "lz4_block_cta.cuh", "zstd_frame.cuh", "zstd_block.cuh", "ingest_text.cuh", "flagstat_blockfile.inl", "bitcounter.cuh", "synth.cuh",
            os.path.join("..", "..", "include", "flagstats_cuda.h")]
 
 NVCC_FLAGS = [

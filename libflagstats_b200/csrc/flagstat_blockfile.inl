@@ -107,22 +107,49 @@ void copy_streaming(unsigned char* dst, const unsigned char* src, size_t n)
     if (i < n) std::memcpy(dst + i, src + i, n - i);
 }
 
-// FLAGSTAT_CUDA_LZ4_VARIANT: 1 = 32 sequences per warp step (lz4_block_group.cuh, default),
-// 0 = one sequence per warp step (lz4_block.cuh; kept for A/B, profiles/)
+// FLAGSTAT_CUDA_LZ4_VARIANT: 2 = one CTA per block, parse / copy phases (lz4_block_cta.cuh, default),
+// 1 = one warp per block, 32 sequences per warp step (lz4_block_group.cuh), 0 = one warp per block,
+// one sequence per step (lz4_block.cuh); the warp-per-block decoders are kept for A/B (profiles/)
 std::atomic<int> g_lz4_variant{-1};
 int lz4_variant()
 {
     int v = g_lz4_variant.load();
     if (v < 0) {
         const char* e = std::getenv("FLAGSTAT_CUDA_LZ4_VARIANT");
-        v = (e && std::atoi(e) == 0) ? 0 : 1;
+        v = e ? std::atoi(e) : 2;
+        if (v < 0 || v > 2) v = 2;
         g_lz4_variant.store(v);
     }
     return v;
 }
 
+// the CTA decoder's descriptor scratch: one region per CTA of the grid, sized for the largest block
+struct Lz4Scratch {
+    unsigned char* d = nullptr;
+    size_t cap = 0;
+};
+
+unsigned lz4_cta_grid(uint32_t n_blocks, int sms)
+{
+    const unsigned full = 2u * (unsigned)sms;  // two CTAs of 94 KB shared memory per SM
+    return n_blocks < full ? n_blocks : full;
+}
+
+int lz4_scratch_reserve(Lz4Scratch& s, uint32_t n_blocks, uint32_t max_comp, uint32_t max_raw, int sms)
+{
+    const size_t need = (size_t)lz4_cta_grid(n_blocks, sms) * l4_scratch_bytes(max_comp, max_raw);
+    if (need <= s.cap) return 0;
+    if (s.d) cudaFree(s.d);
+    s.d = nullptr;
+    s.cap = 0;
+    CK(cudaMalloc(&s.d, need + need / 4));
+    s.cap = need + need / 4;
+    return 0;
+}
+
+// max_comp / max_raw: the largest block of the batch (sizes the CTA decoder's scratch)
 int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status,
-               uint32_t n_blocks, cudaStream_t st)
+               uint32_t n_blocks, cudaStream_t st, Lz4Scratch& scratch, uint32_t max_comp, uint32_t max_raw)
 {
     // both decoders need more than 48 KiB of dynamic shared memory: that opt-in is a PER-DEVICE
     // function attribute, set for every device in device_info()
@@ -131,6 +158,17 @@ int lz4_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4Block
     DeviceInfo* di = nullptr;
     const int rc = device_info(dev, &di);
     if (rc) return rc;
+    if (lz4_variant() == 2) {
+        const int src = lz4_scratch_reserve(scratch, n_blocks, max_comp, max_raw, di->sms);
+        if (src) return src;
+        const size_t stride = l4_scratch_bytes(max_comp, max_raw);
+        const uint32_t desc_cap = max_comp / 3u + 64u;
+        lz4_decode_cta_kernel<<<lz4_cta_grid(n_blocks, di->sms), kL4Threads, kL4Smem, st>>>(
+            d_comp, d_raw, d_desc, d_status, n_blocks, scratch.d, stride, desc_cap);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CK(cudaGetLastError());
+        return 0;
+    }
     const unsigned grid = (n_blocks + kLz4WarpsPerCta - 1) / kLz4WarpsPerCta;
     if (lz4_variant() == 0)
         lz4_decode_kernel<<<grid, kLz4WarpsPerCta * 32, kLz4Smem, st>>>(d_comp, d_raw, d_desc, d_status, n_blocks);
@@ -170,6 +208,8 @@ struct Lz4Lane {
     int* h_status = nullptr;           // pinned
     int* d_status = nullptr;
     zstd::Work* d_work = nullptr;      // Zstd only: one workspace per block of the batch
+    Lz4Scratch scratch;                // LZ4 CTA decoder: descriptor scratch
+    uint32_t max_comp = 0, max_raw = 0;  // largest block of the batch in flight
     size_t comp_cap = 0, raw_cap = 0;
     int blk_cap = 0, work_cap = 0;
     cudaStream_t st = nullptr;
@@ -188,6 +228,7 @@ void lz4_lane_free(Lz4Lane& l)
     if (l.h_status) cudaFreeHost(l.h_status);
     if (l.d_status) cudaFree(l.d_status);
     if (l.d_work) cudaFree(l.d_work);
+    if (l.scratch.d) cudaFree(l.scratch.d);
     if (l.st) cudaStreamDestroy(l.st);
     l = Lz4Lane();
 }
@@ -265,7 +306,8 @@ int lz4_lane_ship(int mode, int codec, Lz4Lane& l, size_t comp_bytes, size_t raw
     }
     int rc = codec == kCodecZstd
                  ? zstd_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.d_work, l.st)
-                 : lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st);
+                 : lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st, l.scratch, l.max_comp,
+                              l.max_raw);
     if (rc) return rc;
     if (file_debug()) {
         CK(cudaEventRecord(dbg.e1, l.st));
@@ -404,9 +446,12 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
         rc = lz4_lane_reserve(l, comp_bytes, raw_bytes, (int)(last - first), codec);
         if (rc) return rc;
         l.n = (int)(last - first);
+        l.max_comp = l.max_raw = 0;
         size_t c = 0, r = 0;
         for (size_t b = first; b < last; ++b) {
             c = (c + 15u) & ~(size_t)15u;
+            if (idx[b].comp > l.max_comp) l.max_comp = idx[b].comp;
+            if (idx[b].raw > l.max_raw) l.max_raw = idx[b].raw;
             l.h_desc[b - first] = Lz4BlockDesc{c, r, idx[b].comp, idx[b].raw};
             c += idx[b].comp;
             r += idx[b].raw + (idx[b].raw & 1u);
@@ -598,11 +643,13 @@ size_t raw_slot_bytes(uint64_t file_size, int threads)
         v &= ~(size_t)65535u;
         if (v >= (64u << 10) && v <= kRawSlotBytes) return v;
     }
-    // at least ~8 slots per thread, between 1 MiB and the ring slot
-    size_t v = (size_t)(file_size / ((uint64_t)threads * 8u));
-    v = (v + 65535u) & ~(size_t)65535u;
+    // measured (profiles/r4j_raw_reader_sweep.jsonl, 12 readers): 4 MiB slots 47.9 GB/s on the 1.65 GB
+    // column (0.94 of the pinned-array rate of that box), 2 MiB 44.4, 8 MB 44.2, 1 MiB 37.7;
+    // on a 410 MB file 39.4 / 38.4 / 35.5 / 34.3.  Short files get at least ~4 slots per reader.
+    size_t v = 4u << 20;
+    const size_t share = (size_t)(file_size / ((uint64_t)threads * 4u));
+    if (share < v) v = (share + 65535u) & ~(size_t)65535u;
     if (v < (1u << 20)) v = 1u << 20;
-    if (v > (kRawSlotBytes & ~(size_t)65535u)) v = kRawSlotBytes & ~(size_t)65535u;
     return v;
 }
 
@@ -699,7 +746,7 @@ extern "C" {
 int FLAGSTAT_cuda_set_lz4_variant(int v)
 {
     const int prev = lz4_variant();
-    g_lz4_variant.store(v == 0 ? 0 : 1);
+    g_lz4_variant.store((v < 0 || v > 2) ? 2 : v);
     return prev;
 }
 
@@ -746,6 +793,12 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
     Lz4BlockDesc* d_desc = nullptr;
     int* d_status = nullptr;
     zstd::Work* d_work = nullptr;
+    Lz4Scratch scratch;
+    uint32_t max_comp = 0, max_raw = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        if (comp_size[b] > max_comp) max_comp = comp_size[b];
+        if (raw_size[b] > max_raw) max_raw = raw_size[b];
+    }
     int rc = 0;
     do {
         if ((rc = (int)cudaMalloc(&d_comp, comp_bytes ? comp_bytes : 1))) break;
@@ -758,7 +811,7 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
         if (codec == kCodecZstd) {
             if ((rc = (int)cudaMalloc(&d_work, (size_t)n_blocks * sizeof(zstd::Work)))) break;
             if ((rc = zstd_launch(d_comp, d_raw, d_desc, d_status, n_blocks, d_work, nullptr))) break;
-        } else if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr))) {
+        } else if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr, scratch, max_comp, max_raw))) {
             break;
         }
         if ((rc = (int)cudaMemcpy(raw, d_raw, raw_total, cudaMemcpyDeviceToHost))) break;
@@ -769,6 +822,7 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
     cudaFree(d_desc);
     cudaFree(d_status);
     cudaFree(d_work);
+    cudaFree(scratch.d);
     return rc;
     });
 }

@@ -33,6 +33,7 @@
 #include "synth.cuh"
 #include "lz4_block.cuh"
 #include "lz4_block_group.cuh"
+#include "lz4_block_cta.cuh"
 #include "zstd_block.cuh"
 #include "ingest_text.cuh"
 #include <cub/device/device_scan.cuh>
@@ -269,6 +270,8 @@ int device_info(int dev, DeviceInfo** out)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem));
         CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_group_kernel),
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem));
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_cta_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
 #ifdef FSB_ALL_VARIANTS
         for (int c = 0; c < 2; ++c)
             for (int m = 0; m < 3; ++m) {

@@ -1,0 +1,569 @@
+// lz4_block_cta.cuh -- LZ4 block decoder, ONE CTA (256 threads) PER BLOCK, two phases.
+//
+// The two warp-per-block decoders (lz4_block.cuh, lz4_block_group.cuh) take 25-30 ms for ONE
+// 1,024,000-byte block of FLAG words whatever the file size: a block is one serial chain for one
+// warp, and a phase profile of the group decoder (tools/lz4_phase_probe.py,
+// profiles/r4j_lz4_phases.jsonl) puts 60-80 % of its cycles into the match machinery of 32
+// sequences at a time.  A file of 400 blocks keeps 400 warps busy (2 % of the machine) and loses
+// to the reference's loop on 16 host cores.  This decoder puts a whole CTA on a block:
+//
+//   PHASE A  parse -- no output byte is touched; the token chain only depends on the input.
+//     The input is cut into 256-byte WINDOWS, eight per super-step, one per warp.  For every byte
+//     position p of its window a warp computes where a sequence whose token sits at p would end
+//     (nx0[p]; all 256 candidates at once, 8 per lane), then by pointer doubling over the
+//     in-window successors (7 levels) the LAST candidate start a chain entering at p reaches
+//     inside the window, hence exit[p] = where that chain leaves the window.  With the eight
+//     exit maps in shared memory one thread chains the super-step's true entry points
+//     (8 dependent look-ups instead of ~700 dependent token parses), every warp then
+//     enumerates the real sequence starts of its window from its entry (lane k = k-th successor
+//     by binary decomposition of the same tables), parses them, and a scan over the output
+//     lengths turns them into DESCRIPTORS {output position, token position}, 8 bytes each,
+//     in a global scratch array (L2-resident).  Sequences whose lengths use more than four
+//     extension bytes leave the window scheme ("escape") and are parsed by one thread.
+//   PHASE B  copy -- the output is produced in TILES of 8 KiB by all 256 threads: every
+//     descriptor that overlaps the tile is re-parsed by one thread (big ones are queued and
+//     done a warp at a time), literal bytes are stored, every match byte gets a PARENT -- the
+//     output byte it copies; parents before the tile are copied at once from the 64 KiB of
+//     history the CTA keeps in shared memory (an LZ4 offset is < 65536) -- then pointer jumping
+//     over the whole tile resolves chains of matches in log(depth) rounds and a last pass
+//     copies root -> byte.  The tile leaves shared memory as coalesced 16-byte stores.
+//
+// Same block format, same Lz4BlockDesc interface, negative status for anything malformed; every
+// position derived from the input is checked before it is used as an index.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "lz4_block.cuh"
+
+namespace fsb200 {
+
+constexpr int kL4Threads = 256;
+constexpr int kL4Warps = kL4Threads / 32;
+constexpr uint32_t kL4Win = 256;              // input bytes per window
+constexpr uint32_t kL4Stage = kL4Win + 32;    // staged per window: a simple sequence is <= 18 + 4 bytes long
+constexpr uint32_t kL4Levels = 7;             // 2^7 = 128 > 85 = most sequences (>= 3 bytes) in a window
+constexpr uint32_t kL4Tile = 8192;            // output bytes per tile
+constexpr uint32_t kL4RingTiles = 9;          // the tile being built + 64 KiB of history
+constexpr uint32_t kL4Ring = kL4RingTiles * kL4Tile;
+constexpr uint32_t kL4MaxExt = 4;             // extension bytes per length the window scheme follows
+constexpr uint32_t kL4BigBytes = 48;          // a descriptor with more bytes in the tile is done by a whole warp
+constexpr uint32_t kL4BigCap = 1024;          // queue of such descriptors per tile (overflow: done by their thread)
+
+// nx0 codes (u16): < 0xFFF0 = successor position relative to the window start
+constexpr uint32_t kL4Last = 0xFFF1;  // the token's literals end exactly at the end of the input: last sequence
+constexpr uint32_t kL4Esc = 0xFFF2;   // needs the serial parser (long length fields)
+constexpr uint32_t kL4Bad = 0xFFF3;   // runs past the end of the input
+
+struct L4Desc {
+    uint32_t out_pos;  // first output byte of the sequence (its literals)
+    uint32_t tok_pos;  // position of its token in the input
+};
+
+// shared memory: | ring 72 KiB (phase A: the per-warp parse tables) | P 16 KiB | big-descriptor queue | scalars |
+// = 94,464 bytes: two CTAs per SM
+constexpr uint32_t kL4ParsePerWarp = kL4Stage + 32u /*pad*/ + 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ +
+                                     2u * kL4Win /*exit u16*/;  // 3136
+static_assert(kL4ParsePerWarp * kL4Warps <= kL4Ring, "parse tables must fit into the ring area");
+constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 4u * kL4BigCap + 256u;
+
+// scratch one CTA needs for blocks of at most max_comp compressed / max_raw decoded bytes
+__host__ __device__ inline size_t l4_scratch_bytes(uint32_t max_comp, uint32_t max_raw)
+{
+    const size_t descs = (size_t)max_comp / 3u + 64u;                  // a sequence with a match is >= 3 bytes
+    const size_t tiles = ((size_t)max_raw + 15u) / kL4Tile + 4u;
+    return ((descs * sizeof(L4Desc) + tiles * 4u) + 255u) & ~(size_t)255u;
+}
+
+struct L4Shared {  // the scalars at the end of the dynamic shared memory
+    int err;
+    uint32_t entry[kL4Warps];   // entry offset of window w in this super-step, 0xFFFFFFFF = skipped
+    uint32_t cnt[kL4Warps];     // sequences of window w
+    uint32_t outlen[kL4Warps];  // output bytes of window w
+    uint32_t stop_code;         // kL4Last / kL4Esc / kL4Bad / 0
+    uint32_t stop_pos;          // absolute token position of the sequence that stopped the chain
+    uint32_t next_pos;          // where the next super-step starts
+    uint32_t big_n;
+    uint32_t pos, out, nseq;    // running state of phase A
+    uint32_t done;
+};
+
+// Length fields of the sequence whose token is at `p` (absolute), read through `rd(i)` = input
+// byte i (caller guarantees i < in_size).  Follows at most `max_ext` extension bytes per field.
+// Returns false if a field needs more (escape) -- only possible when max_ext is finite.
+// lit_pos = first literal byte.  Does NOT read the match fields (see l4_match_len).
+template <class Rd>
+__device__ __forceinline__ int l4_literal_len(Rd rd, uint32_t p, uint32_t in_size, uint32_t max_ext, uint32_t& lit,
+                                              uint32_t& lit_pos)
+{
+    const uint32_t tok = rd(p);
+    lit = tok >> 4;
+    uint32_t q = p + 1u;
+    if (lit == 15u) {
+        uint32_t n = 0u, b;
+        do {
+            if (q >= in_size) return (int)kL4Bad;
+            if (n == max_ext) return (int)kL4Esc;
+            b = rd(q++);
+            lit += b;
+            ++n;
+        } while (b == 255u);
+    }
+    lit_pos = q;
+    return 0;
+}
+
+// Phase A for one block.  Writes descriptors and the per-tile index; returns the number of
+// sequences, or a negative error.  *total_out receives the decoded size.
+__device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32_t out_cap, L4Desc* __restrict__ desc,
+                        uint32_t desc_cap, unsigned char* parse_smem, L4Shared* sh, uint32_t* total_out)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned char* mine = parse_smem + warp * kL4ParsePerWarp;
+    uint8_t* stage = mine;                                                   // kL4Stage (+32 pad)
+    uint16_t* nx0 = reinterpret_cast<uint16_t*>(mine + kL4Stage + 32u);      // [256]
+    uint8_t* f = mine + kL4Stage + 32u + 2u * kL4Win;                        // [levels][256]
+    uint16_t* exitp = reinterpret_cast<uint16_t*>(f + kL4Levels * kL4Win);   // [256]
+    constexpr uint32_t kFull = 0xffffffffu;
+
+    if (tid == 0) {
+        sh->pos = 0u;
+        sh->out = 0u;
+        sh->nseq = 0u;
+        sh->done = 0u;
+    }
+    __syncthreads();
+
+    for (;;) {
+        const uint32_t B = sh->pos;  // start of this super-step: a true sequence start
+        if (sh->err) return sh->err;
+        if (sh->done) break;
+        // ---- 1. per warp: successor of every position of its window, exit map ----------------------
+        const uint32_t wb = B + warp * kL4Win;
+        const bool have = wb < in_size;
+        if (have) {
+            const uint32_t avail = in_size - wb;
+            for (uint32_t i = lane; i < kL4Stage; i += 32u) stage[i] = i < avail ? in[wb + i] : (uint8_t)0;
+            __syncwarp();
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j) {
+                const uint32_t p = lane + 32u * j;
+                uint32_t code;
+                if (p >= avail) {
+                    code = kL4Bad;
+                } else {
+                    // a candidate whose fields reach past the staged bytes is an escape: the serial
+                    // parser reads it from global memory if the chain really gets there
+                    auto rd = [&](uint32_t i) -> uint32_t { return stage[i - wb]; };
+                    uint32_t lit, lit_pos;
+                    const uint32_t lim = (avail < kL4Stage ? avail : kL4Stage) + wb;  // staged bytes end here
+                    int r = l4_literal_len(rd, wb + p, lim, kL4MaxExt, lit, lit_pos);
+                    if (r == (int)kL4Bad) r = lim < in_size ? (int)kL4Esc : (int)kL4Bad;  // ran off the STAGE, not the input
+                    if (r != 0) {
+                        code = (uint32_t)r;
+                    } else {
+                        const uint32_t lit_end = lit_pos + lit;  // absolute; literals themselves are not read here
+                        if (lit_end > in_size) code = kL4Bad;
+                        else if (lit_end == in_size) code = kL4Last;
+                        else if (in_size - lit_end < 2u) code = kL4Bad;  // no room for the offset
+                        else {
+                            uint32_t q = lit_end + 2u;
+                            code = 0u;
+                            if ((stage[p] & 15u) == 15u) {  // match-length extension bytes
+                                uint32_t n = 0u, b = 255u;
+                                while (b == 255u) {
+                                    if (q >= in_size) { code = kL4Bad; break; }
+                                    if (n == kL4MaxExt || q >= lim) { code = kL4Esc; break; }
+                                    b = stage[q - wb];
+                                    ++q;
+                                    ++n;
+                                }
+                            }
+                            if (code == 0u) {
+                                const uint32_t rel = q - wb;  // successor relative to the window start
+                                code = rel < 0xFFF0u ? rel : kL4Esc;
+                            }
+                        }
+                    }
+                }
+                nx0[p] = (uint16_t)code;
+                f[p] = (uint8_t)(code < kL4Win ? code : p);  // in-window successor, else a fixed point
+            }
+            __syncwarp();
+            for (uint32_t L = 1; L < kL4Levels; ++L) {
+                const uint8_t* a = f + (L - 1u) * kL4Win;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    const uint32_t p = lane + 32u * j;
+                    f[L * kL4Win + p] = a[a[p]];
+                }
+                __syncwarp();
+            }
+            {
+                const uint8_t* a = f + (kL4Levels - 1u) * kL4Win;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    const uint32_t p = lane + 32u * j;
+                    // 2^6 + 2^6 steps: a[a[p]] is the 128th successor = the last start inside the window
+                    exitp[p] = nx0[a[a[p]]];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 2. one thread chains the true entry points through the eight exit maps ---------------------
+        if (tid == 0) {
+            uint32_t e = 0u, w = 0u;
+            sh->stop_code = 0u;
+            for (uint32_t i = 0; i < (uint32_t)kL4Warps; ++i) sh->entry[i] = 0xFFFFFFFFu;
+            uint32_t next = B;
+            while (w < (uint32_t)kL4Warps && B + w * kL4Win < in_size) {
+                sh->entry[w] = e;
+                const uint16_t* ex = reinterpret_cast<const uint16_t*>(parse_smem + w * kL4ParsePerWarp + kL4Stage + 32u +
+                                                                        2u * kL4Win + kL4Levels * kL4Win);
+                const uint32_t x = ex[e];
+                if (x >= 0xFFF0u) {  // the chain of this window ends in a special sequence: at its last start
+                    const uint8_t* a = reinterpret_cast<const uint8_t*>(ex) - kL4Win;  // f[levels - 1]
+                    sh->stop_code = x;
+                    sh->stop_pos = B + w * kL4Win + a[a[e]];
+                    break;
+                }
+                // x >= 256: position B + w * 256 + x
+                const uint32_t adv = x >> 8;
+                e = x & 255u;
+                w += adv;
+                next = B + w * kL4Win + e;
+            }
+            if (sh->stop_code == 0u) sh->next_pos = next;  // chain left the super-step (or the input: checked below)
+        }
+        __syncthreads();
+        // ---- 3. per warp: enumerate the real sequence starts of its window, lengths, local scan -------
+        uint32_t my_cnt = 0u, my_out = 0u;
+        uint32_t q3[3], olen3[3], excl3[3];
+        bool val3[3];
+        const uint32_t e_w = sh->entry[warp];
+        if (have && e_w != 0xFFFFFFFFu) {
+            uint32_t carry = 0u;
+            uint32_t prev_last = 0xFFFFFFFFu;  // q of the last lane of the previous round
+#pragma unroll
+            for (uint32_t r = 0; r < 3u; ++r) {
+                const uint32_t k = lane + 32u * r;
+                uint32_t p = e_w;
+#pragma unroll
+                for (uint32_t L = 0; L < kL4Levels; ++L)
+                    if (k & (1u << L)) p = f[L * kL4Win + p];
+                // k-th successor; it stays on the last start once the chain has left the window
+                uint32_t before = __shfl_up_sync(kFull, p, 1);
+                if (lane == 0) before = prev_last;
+                const uint32_t code = nx0[p];
+                // a real, ordinary sequence: first of the window or different from its predecessor, and
+                // not the special one that ends the chain (that one is handled by thread 0 below)
+                const bool valid = (k == 0u || p != before) && code < 0xFFF0u;
+                prev_last = __shfl_sync(kFull, p, 31);
+                uint32_t olen = 0u;
+                if (valid) {
+                    const uint32_t tok = stage[p];
+                    uint32_t lit = tok >> 4, qq = p + 1u;
+                    if (lit == 15u) {
+                        uint32_t b;
+                        do {
+                            b = stage[qq++];
+                            lit += b;
+                        } while (b == 255u);
+                    }
+                    uint32_t ml = (tok & 15u) + 4u;
+                    if ((tok & 15u) == 15u) {
+                        uint32_t mq = qq + lit + 2u - 0u;  // relative to wb; inside the stage (code < 0xFFF0 guarantees it)
+                        uint32_t b;
+                        do {
+                            b = stage[mq++];
+                            ml += b;
+                        } while (b == 255u);
+                    }
+                    olen = lit + ml;
+                }
+                uint32_t incl = olen;
+#pragma unroll
+                for (uint32_t s = 1u; s < 32u; s <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, s);
+                    if (lane >= s) incl += t;
+                }
+                q3[r] = p;
+                olen3[r] = olen;
+                excl3[r] = carry + incl - olen;
+                val3[r] = valid;
+                carry += __shfl_sync(kFull, incl, 31);
+                my_cnt += __popc(__ballot_sync(kFull, valid));
+            }
+            my_out = carry;
+        } else {
+#pragma unroll
+            for (uint32_t r = 0; r < 3u; ++r) {
+                q3[r] = 0u; olen3[r] = 0u; excl3[r] = 0u; val3[r] = false;
+            }
+        }
+        if (lane == 0) {
+            sh->cnt[warp] = my_cnt;
+            sh->outlen[warp] = my_out;
+        }
+        __syncthreads();
+        // ---- 4. descriptors; the special sequence that ended the chain, if any ---------------------------
+        {
+            uint32_t base_idx = sh->nseq, base_out = sh->out;
+            for (uint32_t w = 0; w < warp; ++w) {
+                base_idx += sh->cnt[w];
+                base_out += sh->outlen[w];
+            }
+            uint32_t tot_idx = base_idx, tot_out = base_out;
+            for (uint32_t w = warp; w < (uint32_t)kL4Warps; ++w) {
+                tot_idx += sh->cnt[w];
+                tot_out += sh->outlen[w];
+            }
+            if (tot_idx + 2u > desc_cap || tot_out > out_cap) {
+                if (tid == 0) sh->err = -4;  // more sequences than the input can hold / output overrun
+            } else {
+                uint32_t rank = 0u;
+#pragma unroll
+                for (uint32_t r = 0; r < 3u; ++r) {
+                    const uint32_t m = __ballot_sync(kFull, val3[r]);
+                    if (val3[r]) {
+                        const uint32_t i = base_idx + rank + __popc(m & ((1u << lane) - 1u));
+                        desc[i] = L4Desc{base_out + excl3[r], wb + q3[r]};
+                    }
+                    rank += __popc(m);
+                }
+                (void)olen3;
+            }
+            __syncthreads();
+            if (tid == 0 && sh->err == 0) {
+                uint32_t nseq = tot_idx, out = tot_out;
+                // the sequence that stopped the chain: its token position is the last start of the
+                // stopping window's chain
+                if (sh->stop_code != 0u) {
+                    const uint32_t p = sh->stop_pos;
+                    if (sh->stop_code == kL4Bad) {
+                        sh->err = -1;
+                    } else {
+                        // serial parse from global memory (any length of extension runs)
+                        auto rd = [&](uint32_t i) -> uint32_t { return in[i]; };
+                        uint32_t lit, lit_pos;
+                        const int r = l4_literal_len(rd, p, in_size, 0xFFFFFFFFu, lit, lit_pos);
+                        if (r != 0 || lit > in_size - lit_pos) {
+                            sh->err = -2;
+                        } else if (lit_pos + lit == in_size) {  // last sequence: literals only
+                            if (lit > out_cap - out) sh->err = -2;
+                            else {
+                                desc[nseq++] = L4Desc{out, p};
+                                out += lit;
+                                sh->done = 1u;
+                            }
+                        } else if (in_size - (lit_pos + lit) < 2u) {
+                            sh->err = -3;
+                        } else {
+                            uint32_t qq = lit_pos + lit + 2u;
+                            uint32_t ml = (in[p] & 15u);
+                            if (ml == 15u) {
+                                uint32_t b = 255u;
+                                while (b == 255u) {
+                                    if (qq >= in_size) { sh->err = -1; break; }
+                                    b = in[qq++];
+                                    ml += b;
+                                    if (ml > out_cap) { sh->err = -4; break; }
+                                }
+                            }
+                            ml += 4u;
+                            if (sh->err == 0) {
+                                if (lit > out_cap - out || ml > out_cap - out - lit) sh->err = -4;
+                                else {
+                                    desc[nseq++] = L4Desc{out, p};
+                                    out += lit + ml;
+                                    sh->next_pos = qq;
+                                    if (qq >= in_size) sh->err = -1;  // a match cannot be the end of a block
+                                }
+                            }
+                        }
+                    }
+                } else if (sh->next_pos >= in_size) {
+                    sh->err = -1;  // the chain ran off the end without a last sequence
+                }
+                sh->nseq = nseq;
+                sh->out = out;
+                sh->pos = sh->next_pos;
+            }
+            __syncthreads();
+        }
+    }
+    if (sh->err) return sh->err;
+    *total_out = sh->out;
+    return (int)sh->nseq;
+}
+
+// position of a byte of the output in the shared-memory ring (v = out_pos + ga, see below)
+__device__ __forceinline__ uint32_t l4_ring(uint32_t v) { return v % kL4Ring; }
+
+// Phase B for one block: nseq descriptors -> out[0, total).  Returns total or a negative error.
+__device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* __restrict__ out, uint32_t total,
+                       const L4Desc* __restrict__ desc, uint32_t nseq, uint32_t* __restrict__ tile_first,
+                       uint8_t* ring, uint16_t* P, uint32_t* big, L4Shared* sh)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
+    const uint32_t ga = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    const uint32_t vend = total + ga;
+    const uint32_t ntiles = (vend + kL4Tile - 1u) / kL4Tile;
+    // tile_first[t] = first descriptor whose v position is >= t * tile, nseq if there is none
+    // (one pass over the descriptors; positions are a running sum, hence sorted)
+    for (uint32_t j = tid; j <= nseq; j += kL4Threads) {
+        const uint32_t t0 = j == 0u ? 0u : (desc[j - 1u].out_pos + ga) / kL4Tile + 1u;
+        const uint32_t t1 = j < nseq ? (desc[j].out_pos + ga) / kL4Tile : ntiles;
+        for (uint32_t t = t0; t <= t1 && t <= ntiles; ++t) tile_first[t] = j;
+    }
+    __syncthreads();
+    if (sh->err) return sh->err;
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t tlo = t * kL4Tile;                                   // v-space
+        const uint32_t thi = (tlo + kL4Tile < vend) ? tlo + kL4Tile : vend;
+        const uint32_t tlen = thi - tlo;
+        const uint32_t j1 = tile_first[t + 1u];                              // descriptors < j1 start before the next tile
+        uint32_t j0 = tile_first[t];
+        if (j0 > 0u) --j0;                                                   // the one before may reach into the tile
+        if (tid == 0) sh->big_n = 0u;
+        __syncthreads();
+
+        // bytes [a, b) (v-space, inside the tile) of descriptor j: literals from the input, matches as
+        // parents.  `lanes` threads share the work (1 = the descriptor's own thread, 32 = a warp).
+        auto do_desc = [&](uint32_t j, uint32_t lanes, uint32_t li) {
+            const uint32_t o = desc[j].out_pos + ga;
+            const uint32_t oe = (j + 1u < nseq ? desc[j + 1u].out_pos : total) + ga;
+            const uint32_t p = desc[j].tok_pos;
+            if (p >= in_size || oe < o) { sh->err = -5; return; }
+            auto rd = [&](uint32_t i) -> uint32_t { return in[i]; };
+            uint32_t lit, lit_pos;
+            if (l4_literal_len(rd, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 || lit > in_size - lit_pos || lit > oe - o) {
+                sh->err = -2;
+                return;
+            }
+            const uint32_t m = o + lit;   // first match byte (v)
+            const uint32_t ml = oe - m;   // 0 for the last sequence
+            // literals
+            {
+                const uint32_t a = o > tlo ? o : tlo, b = m < thi ? m : thi;
+                for (uint32_t v = a + li; v < b; v += lanes) {
+                    ring[l4_ring(v)] = in[lit_pos + (v - o)];
+                    P[v - tlo] = (uint16_t)(v - tlo);
+                }
+            }
+            if (ml == 0u) return;
+            if (in_size - (lit_pos + lit) < 2u) { sh->err = -3; return; }
+            const uint32_t off = (uint32_t)in[lit_pos + lit] | ((uint32_t)in[lit_pos + lit + 1u] << 8);
+            if (off == 0u || off > m - ga) { sh->err = -4; return; }
+            const uint32_t a = m > tlo ? m : tlo, b = oe < thi ? oe : thi;
+            const uint32_t src0 = m - off;
+            for (uint32_t v = a + li; v < b; v += lanes) {
+                const uint32_t d = v - m;
+                const uint32_t s = off >= ml ? src0 + d : src0 + d % off;  // the byte this one copies
+                if (s < tlo) {  // produced by an earlier tile: final already
+                    ring[l4_ring(v)] = (tlo - s <= kL4Ring - kL4Tile) ? ring[l4_ring(s)] : out[s - ga];
+                    P[v - tlo] = (uint16_t)(v - tlo);
+                } else {
+                    P[v - tlo] = (uint16_t)(s - tlo);
+                }
+            }
+        };
+
+        for (uint32_t j = j0 + tid; j < j1; j += kL4Threads) {
+            const uint32_t o = desc[j].out_pos + ga;
+            const uint32_t oe = (j + 1u < nseq ? desc[j + 1u].out_pos : total) + ga;
+            const uint32_t a = o > tlo ? o : tlo, b = oe < thi ? oe : thi;
+            if (b <= a) continue;
+            if (b - a > kL4BigBytes) {
+                const uint32_t k = atomicAdd(&sh->big_n, 1u);
+                if (k < kL4BigCap) {
+                    big[k] = j;
+                    continue;
+                }
+            }
+            do_desc(j, 1u, 0u);
+        }
+        __syncthreads();
+        {
+            const uint32_t nb = sh->big_n < kL4BigCap ? sh->big_n : kL4BigCap;
+            for (uint32_t k = tid >> 5; k < nb; k += (uint32_t)kL4Warps) do_desc(big[k], 32u, lane);
+        }
+        __syncthreads();
+        if (sh->err) return sh->err;
+        // pointer jumping over the tile: whatever a thread reads from P[] is an ancestor
+        for (;;) {
+            int changed = 0;
+            for (uint32_t b = tid; b < tlen; b += kL4Threads) {
+                const uint32_t p = P[b];
+                if (p != b) {
+                    const uint32_t q = P[p];
+                    if (q != p) {
+                        P[b] = (uint16_t)q;
+                        changed = 1;
+                    }
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        for (uint32_t b = tid; b < tlen; b += kL4Threads) {
+            const uint32_t r = P[b];
+            if (r != b) ring[l4_ring(tlo + b)] = ring[l4_ring(tlo + r)];  // roots are not written in this pass
+        }
+        __syncthreads();
+        // tile -> global: 16-byte chunks line up (v-space); the first tile starts ga bytes in, the
+        // last one may end inside a chunk
+        {
+            const uint32_t lo = t == 0u ? ga : tlo;
+            const uint32_t lo16 = (lo + 15u) & ~15u, hi16 = thi & ~15u;
+            if (lo16 <= hi16) {
+                for (uint32_t v = lo + tid; v < lo16; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
+                for (uint32_t v = lo16 + tid * 16u; v < hi16; v += kL4Threads * 16u)
+                    *reinterpret_cast<uint4*>(out + (v - ga)) = *reinterpret_cast<const uint4*>(ring + l4_ring(v));
+                for (uint32_t v = hi16 + tid; v < thi; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
+            } else {
+                for (uint32_t v = lo + tid; v < thi; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
+            }
+        }
+        __syncthreads();  // the ring slot of tile t + 1 (= tile t - 4) is free, P[] can be rewritten
+    }
+    return (int)total;
+}
+
+// status[b] = decoded size (must equal raw_size) or a negative error code.  scratch: gridDim.x
+// regions of scratch_stride bytes (l4_scratch_bytes of the largest block).
+__global__ void __launch_bounds__(kL4Threads)
+lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4BlockDesc* __restrict__ bdesc,
+                      int* __restrict__ status, uint32_t n_blocks, unsigned char* scratch, size_t scratch_stride,
+                      uint32_t desc_cap)
+{
+    extern __shared__ __align__(16) unsigned char l4_smem[];
+    uint8_t* ring = l4_smem;
+    uint16_t* P = reinterpret_cast<uint16_t*>(l4_smem + kL4Ring);
+    uint32_t* big = reinterpret_cast<uint32_t*>(l4_smem + kL4Ring + 2u * kL4Tile);
+    L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile + 4u * kL4BigCap);
+    L4Desc* desc = reinterpret_cast<L4Desc*>(scratch + (size_t)blockIdx.x * scratch_stride);
+    uint32_t* tile_first = reinterpret_cast<uint32_t*>(desc + desc_cap);
+
+    for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const Lz4BlockDesc d = bdesc[b];
+        if (threadIdx.x == 0) sh->err = 0;
+        __syncthreads();
+        int r = 0;
+        if (d.comp_size != 0u) {
+            uint32_t total = 0u;
+            const int nseq = l4_parse(comp + d.comp_off, d.comp_size, d.raw_size, desc, desc_cap, ring, sh, &total);
+            __syncthreads();
+            r = nseq;
+            if (nseq >= 0)
+                r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
+                            ring, P, big, sh);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) status[b] = r;
+        __syncthreads();
+    }
+}
+
+}  // namespace fsb200

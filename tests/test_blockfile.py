@@ -25,9 +25,10 @@ def _columns():
     ]
 
 
-@pytest.fixture(params=[1, 0], ids=["group_decoder", "sequence_decoder"])
+@pytest.fixture(params=[2, 1, 0], ids=["cta_decoder", "group_decoder", "sequence_decoder"])
 def lz4_variant(request, cuda_lib):
-    """Both LZ4 decoders: 32 sequences per warp step (default) and one per step."""
+    """All three LZ4 decoders: one CTA per block with parse / copy phases (default), one warp per block
+    with 32 sequences per step, and one warp per block with one sequence per step."""
     prev = cuda_lib.lib().FLAGSTAT_cuda_set_lz4_variant(request.param)
     yield request.param
     cuda_lib.lib().FLAGSTAT_cuda_set_lz4_variant(prev)

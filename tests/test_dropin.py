@@ -96,6 +96,19 @@ def test_unchanged_pyx_runs_on_the_gpu():
     assert mod is not None, "oracle/_ref/pyflagstats*.so missing (integration/build_dropin.sh)"
     import libflagstats_b200 as fs
     before = fs.lib().FLAGSTAT_cuda_launch_count()
+    # both lengths must reach the device (pyflagstats links the same libflagstats_cuda.so this process
+    # has loaded): the default threshold would leave the first one to FLAGSTAT_avx512, whose dict differs
+    # from ours in the slots that kernel fills with raw-bit counts (slots 0,1,3,4,5)
+    prev_min = fs.lib().FLAGSTAT_cuda_min_len()
+    fs.lib().FLAGSTAT_cuda_set_min_len(4096)
+    try:
+        _pyx_checks(mod, fs)
+    finally:
+        fs.lib().FLAGSTAT_cuda_set_min_len(prev_min)
+    assert fs.lib().FLAGSTAT_cuda_launch_count() > before  # same process, same .so: CUDA really ran
+
+
+def _pyx_checks(mod, fs):
     for n in (1_000_003, 100_000_000):
         a = O.synth_uniform(0, n, 3, 0x0FFF)
         d = mod.flagstats(a)  # the reference's own Python entry point
@@ -104,7 +117,6 @@ def test_unchanged_pyx_runs_on_the_gpu():
             _check_dict(d, a)
         assert {k: int(v) for k, v in d["passed"].items()} == {k: int(v) for k, v in ours["passed"].items()}
         assert {k: int(v) for k, v in d["failed"].items()} == {k: int(v) for k, v in ours["failed"].items()}
-    assert fs.lib().FLAGSTAT_cuda_launch_count() > before  # same process, same .so: CUDA really ran
 
 
 SAMCALL = os.path.join(REF_DIR, "samtools_caller")

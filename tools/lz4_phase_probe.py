@@ -14,11 +14,12 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "tools", "bin", "libflagstats_cuda_lz4prof.so")
+os.environ["LIBFLAGSTATS_CUDA_SO"] = SO  # before the package is imported: _capi reads it at import time
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from libflagstats_b200 import build as B  # noqa: E402
 
-SO = os.path.join(ROOT, "tools", "bin", "libflagstats_cuda_lz4prof.so")
 PHASES = ["stage+sizes", "doubling+walk", "parse+scan", "literals", "parent pointers", "pointer jumping+root copy",
           "(sequences)", "(steps)", "slow-path sequences", "loop+flush"]
 
