@@ -421,6 +421,18 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
 
     const int T = io_threads();
     int batch_blocks = kBatchBlocks;
+    if (codec == kCodecLz4 && lz4_variant() == 2) {
+        // The CTA decoder works on 2 x SMs blocks at a time (one wave); batches of that size let the
+        // gather and the H2D copy of batch k + 1 run while batch k is being decoded -- a file of
+        // 1601 blocks used to be ONE batch: gather, copy, decode and count back to back.
+        int dev = 0;
+        DeviceInfo* di = nullptr;
+        CK(cudaGetDevice(&dev));
+        const int irc = device_info(dev, &di);
+        if (irc) return irc;
+        batch_blocks = 2 * di->sms;
+        if (batch_blocks > kBatchBlocks) batch_blocks = kBatchBlocks;
+    }
     if (const char* e = std::getenv("FLAGSTAT_CUDA_LZ4_BATCH")) {  // tests: force several batches
         const int v = std::atoi(e);
         if (v >= 1 && v <= kBatchBlocks) batch_blocks = v;

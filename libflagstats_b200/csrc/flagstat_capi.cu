@@ -1557,6 +1557,18 @@ int FLAGSTAT_cuda_lz4_profile_fetch(unsigned long long* out16, int clear)
     }
     return 0;
 }
+// the same for the CTA decoder (lz4_block_cta.cuh): thread 0 of every CTA
+int FLAGSTAT_cuda_l4_profile_fetch(unsigned long long* out16, int clear)
+{
+    if (!out16) return FLAGSTAT_CUDA_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out16, fsb200::g_l4_prof, 16 * sizeof(unsigned long long)));
+    if (clear) {
+        unsigned long long z[16] = {0};
+        CK(cudaMemcpyToSymbol(fsb200::g_l4_prof, z, sizeof(z)));
+    }
+    return 0;
+}
 #endif
 
 #ifdef FSB_TIMELINE

@@ -1,4 +1,4 @@
-// lz4_block_cta.cuh -- LZ4 block decoder, ONE CTA (256 threads) PER BLOCK, two phases.
+// lz4_block_cta.cuh -- LZ4 block decoder, ONE CTA (512 threads) PER BLOCK, two phases.
 //
 // The two warp-per-block decoders (lz4_block.cuh, lz4_block_group.cuh) take 25-30 ms for ONE
 // 1,024,000-byte block of FLAG words whatever the file size: a block is one serial chain for one
@@ -8,25 +8,28 @@
 // to the reference's loop on 16 host cores.  This decoder puts a whole CTA on a block:
 //
 //   PHASE A  parse -- no output byte is touched; the token chain only depends on the input.
-//     The input is cut into 256-byte WINDOWS, eight per super-step, one per warp.  For every byte
+//     The input is cut into 256-byte WINDOWS, sixteen per super-step, one per warp.  For every byte
 //     position p of its window a warp computes where a sequence whose token sits at p would end
 //     (nx0[p]; all 256 candidates at once, 8 per lane), then by pointer doubling over the
 //     in-window successors (7 levels) the LAST candidate start a chain entering at p reaches
 //     inside the window, hence exit[p] = where that chain leaves the window.  With the eight
 //     exit maps in shared memory one thread chains the super-step's true entry points
-//     (8 dependent look-ups instead of ~700 dependent token parses), every warp then
+//     (16 dependent look-ups instead of ~1400 dependent token parses), every warp then
 //     enumerates the real sequence starts of its window from its entry (lane k = k-th successor
 //     by binary decomposition of the same tables), parses them, and a scan over the output
 //     lengths turns them into DESCRIPTORS {output position, token position}, 8 bytes each,
 //     in a global scratch array (L2-resident).  Sequences whose lengths use more than four
 //     extension bytes leave the window scheme ("escape") and are parsed by one thread.
-//   PHASE B  copy -- the output is produced in TILES of 8 KiB by all 256 threads: every
-//     descriptor that overlaps the tile is re-parsed by one thread (big ones are queued and
-//     done a warp at a time), literal bytes are stored, every match byte gets a PARENT -- the
-//     output byte it copies; parents before the tile are copied at once from the 64 KiB of
-//     history the CTA keeps in shared memory (an LZ4 offset is < 65536) -- then pointer jumping
-//     over the whole tile resolves chains of matches in log(depth) rounds and a last pass
-//     copies root -> byte.  The tile leaves shared memory as coalesced 16-byte stores.
+//   PHASE B  copy -- the output is produced in TILES of 8 KiB by all 512 threads.  The tile's
+//     descriptors and the input bytes they cover are staged in shared memory; every thread then
+//     produces 16 CONSECUTIVE output bytes whatever sequences they belong to (a binary search
+//     finds the first one; one thread per sequence would leave most lanes idle behind the longest
+//     match): literal bytes are stored, every match byte gets a PARENT -- the output byte it
+//     copies; parents before the tile are copied at once from the 56 KiB of history the CTA
+//     keeps in shared memory (an LZ4 offset is < 65536; the rare longer reach reads global
+//     memory) -- then pointer jumping over the whole tile resolves chains of matches in
+//     log(depth) rounds and a last pass copies root -> byte.  The tile leaves shared memory
+//     as coalesced 16-byte stores.
 //
 // Same block format, same Lz4BlockDesc interface, negative status for anything malformed; every
 // position derived from the input is checked before it is used as an index.
@@ -38,34 +41,58 @@
 
 namespace fsb200 {
 
-constexpr int kL4Threads = 256;
+constexpr int kL4Threads = 512;
 constexpr int kL4Warps = kL4Threads / 32;
 constexpr uint32_t kL4Win = 256;              // input bytes per window
-constexpr uint32_t kL4Stage = kL4Win + 32;    // staged per window: a simple sequence is <= 18 + 4 bytes long
+constexpr uint32_t kL4Stage = kL4Win + 32;    // a window sees 32 bytes beyond its end: a simple sequence is <= 18 + 4 bytes long
 constexpr uint32_t kL4Levels = 7;             // 2^7 = 128 > 85 = most sequences (>= 3 bytes) in a window
 constexpr uint32_t kL4Tile = 8192;            // output bytes per tile
-constexpr uint32_t kL4RingTiles = 9;          // the tile being built + 64 KiB of history
-constexpr uint32_t kL4Ring = kL4RingTiles * kL4Tile;
+constexpr uint32_t kL4Ring = 65536;           // the tile being built + 56 KiB of history (a power of two: index = v & mask;
+                                              // the rare match that reaches further back reads global memory)
 constexpr uint32_t kL4MaxExt = 4;             // extension bytes per length the window scheme follows
-constexpr uint32_t kL4BigBytes = 48;          // a descriptor with more bytes in the tile is done by a whole warp
-constexpr uint32_t kL4BigCap = 1024;          // queue of such descriptors per tile (overflow: done by their thread)
+constexpr uint32_t kL4ByteChunk = kL4Tile / kL4Threads;  // 16 output bytes per thread and tile
+constexpr uint32_t kL4TileDescs = kL4Tile / 4u + 4u;     // a sequence with a match produces >= 4 bytes
 
 // nx0 codes (u16): < 0xFFF0 = successor position relative to the window start
 constexpr uint32_t kL4Last = 0xFFF1;  // the token's literals end exactly at the end of the input: last sequence
 constexpr uint32_t kL4Esc = 0xFFF2;   // needs the serial parser (long length fields)
 constexpr uint32_t kL4Bad = 0xFFF3;   // runs past the end of the input
 
+// Phase profile (tools/lz4_phase_probe.py, -DFSB_LZ4_PROFILE; never in the product): thread 0 of the
+// CTA sums clock64() deltas per phase into g_lz4_prof[16 + k].
+#ifdef FSB_LZ4_PROFILE
+__device__ unsigned long long g_l4_prof[16];
+#define L4P_DECL long long l4p_t = clock64()
+#define L4P(k)                                                                     \
+    do {                                                                           \
+        if (threadIdx.x == 0) {                                                    \
+            const long long now_ = clock64();                                      \
+            atomicAdd(&g_l4_prof[k], (unsigned long long)(now_ - l4p_t));          \
+            l4p_t = now_;                                                          \
+        }                                                                          \
+    } while (0)
+#define L4P_COUNT(k, v)                                                            \
+    do {                                                                           \
+        if (threadIdx.x == 0) atomicAdd(&g_l4_prof[k], (unsigned long long)(v));   \
+    } while (0)
+#else
+#define L4P_DECL do { } while (0)
+#define L4P(k) do { } while (0)
+#define L4P_COUNT(k, v) do { } while (0)
+#endif
+
 struct L4Desc {
     uint32_t out_pos;  // first output byte of the sequence (its literals)
     uint32_t tok_pos;  // position of its token in the input
 };
 
-// shared memory: | ring 72 KiB (phase A: the per-warp parse tables) | P 16 KiB | big-descriptor queue | scalars |
-// = 94,464 bytes: two CTAs per SM
-constexpr uint32_t kL4ParsePerWarp = kL4Stage + 32u /*pad*/ + 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ +
-                                     2u * kL4Win /*exit u16*/;  // 3136
-static_assert(kL4ParsePerWarp * kL4Warps <= kL4Ring, "parse tables must fit into the ring area");
-constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 4u * kL4BigCap + 256u;
+// shared memory: | ring 64 KiB (phase A: per-warp parse tables + the staged super-step) | P 16 KiB |
+// tile descriptors 16 KiB | input stage 12 KiB | scalars | = 111,136 bytes: two CTAs per SM
+constexpr uint32_t kL4ParsePerWarp = 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ + 2u * kL4Win /*exit u16*/;  // 2816
+constexpr uint32_t kL4SuperStage = kL4Warps * kL4Win + 32u + 16u;  // the super-step's input bytes (+ alignment slack)
+static_assert(kL4ParsePerWarp * kL4Warps + kL4SuperStage + 16u <= kL4Ring, "parse tables must fit into the ring area");
+constexpr uint32_t kL4InStage = 12288;        // input bytes of one tile staged in shared memory (+ 16 of alignment slack)
+constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + (kL4InStage + 32u) + 256u;
 
 // scratch one CTA needs for blocks of at most max_comp compressed / max_raw decoded bytes
 __host__ __device__ inline size_t l4_scratch_bytes(uint32_t max_comp, uint32_t max_raw)
@@ -83,7 +110,6 @@ struct L4Shared {  // the scalars at the end of the dynamic shared memory
     uint32_t stop_code;         // kL4Last / kL4Esc / kL4Bad / 0
     uint32_t stop_pos;          // absolute token position of the sequence that stopped the chain
     uint32_t next_pos;          // where the next super-step starts
-    uint32_t big_n;
     uint32_t pos, out, nseq;    // running state of phase A
     uint32_t done;
 };
@@ -120,10 +146,10 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned char* mine = parse_smem + warp * kL4ParsePerWarp;
-    uint8_t* stage = mine;                                                   // kL4Stage (+32 pad)
-    uint16_t* nx0 = reinterpret_cast<uint16_t*>(mine + kL4Stage + 32u);      // [256]
-    uint8_t* f = mine + kL4Stage + 32u + 2u * kL4Win;                        // [levels][256]
+    uint16_t* nx0 = reinterpret_cast<uint16_t*>(mine);                       // [256]
+    uint8_t* f = mine + 2u * kL4Win;                                         // [levels][256]
     uint16_t* exitp = reinterpret_cast<uint16_t*>(f + kL4Levels * kL4Win);   // [256]
+    uint8_t* sst = parse_smem + kL4Warps * kL4ParsePerWarp;                  // the super-step's input, 16-byte aligned
     constexpr uint32_t kFull = 0xffffffffu;
 
     if (tid == 0) {
@@ -134,23 +160,45 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
     }
     __syncthreads();
 
+    L4P_DECL;
     for (;;) {
         const uint32_t B = sh->pos;  // start of this super-step: a true sequence start
         if (sh->err) return sh->err;
         if (sh->done) break;
+        L4P_COUNT(12, 1);  // super-steps
         // ---- 1. per warp: successor of every position of its window, exit map ----------------------
+        // the super-step's input [B, B + 16 * 256 + 32) with aligned 16-byte loads (al = B's address mod 16;
+        // bytes in front of the block belong to the same buffer), zero behind the end of the input
+        const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(in) + B) & 15u);
+        {
+            const uint32_t nvec = (al + kL4Warps * kL4Win + 32u + 15u) >> 4;
+            for (uint32_t v = tid; v < nvec; v += kL4Threads) {
+                const long long rel = (long long)B - (long long)al + (long long)(v << 4);  // first byte, relative to `in`
+                if (rel + 16 <= (long long)in_size) {
+                    *reinterpret_cast<uint4*>(sst + (v << 4)) = *reinterpret_cast<const uint4*>(in + rel);
+                } else {
+                    for (uint32_t i = 0; i < 16u; ++i)
+                        sst[(v << 4) + i] = rel + (long long)i < (long long)in_size ? in[rel + i] : (uint8_t)0;
+                }
+            }
+        }
+        __syncthreads();
         const uint32_t wb = B + warp * kL4Win;
         const bool have = wb < in_size;
+        const uint8_t* stage = sst + al + warp * kL4Win;  // this warp's window and the 32 bytes behind it
         if (have) {
             const uint32_t avail = in_size - wb;
-            for (uint32_t i = lane; i < kL4Stage; i += 32u) stage[i] = i < avail ? in[wb + i] : (uint8_t)0;
-            __syncwarp();
 #pragma unroll
             for (uint32_t j = 0; j < 8u; ++j) {
                 const uint32_t p = lane + 32u * j;
                 uint32_t code;
+                const uint32_t tok0 = stage[p];
                 if (p >= avail) {
                     code = kL4Bad;
+                } else if ((tok0 >> 4) != 15u && (tok0 & 15u) != 15u) {
+                    // the common token: no extension bytes, the successor sits right behind the offset
+                    const uint32_t e = wb + p + 1u + (tok0 >> 4);  // end of the literals
+                    code = e + 2u <= in_size ? p + 3u + (tok0 >> 4) : e == in_size ? kL4Last : kL4Bad;
                 } else {
                     // a candidate whose fields reach past the staged bytes is an escape: the serial
                     // parser reads it from global memory if the chain really gets there
@@ -210,6 +258,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
             }
         }
         __syncthreads();
+        L4P(0);  // A1: successor tables + exit maps
         // ---- 2. one thread chains the true entry points through the eight exit maps ---------------------
         if (tid == 0) {
             uint32_t e = 0u, w = 0u;
@@ -218,8 +267,8 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
             uint32_t next = B;
             while (w < (uint32_t)kL4Warps && B + w * kL4Win < in_size) {
                 sh->entry[w] = e;
-                const uint16_t* ex = reinterpret_cast<const uint16_t*>(parse_smem + w * kL4ParsePerWarp + kL4Stage + 32u +
-                                                                        2u * kL4Win + kL4Levels * kL4Win);
+                const uint16_t* ex = reinterpret_cast<const uint16_t*>(parse_smem + w * kL4ParsePerWarp + 2u * kL4Win +
+                                                                        kL4Levels * kL4Win);
                 const uint32_t x = ex[e];
                 if (x >= 0xFFF0u) {  // the chain of this window ends in a special sequence: at its last start
                     const uint8_t* a = reinterpret_cast<const uint8_t*>(ex) - kL4Win;  // f[levels - 1]
@@ -236,6 +285,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
             if (sh->stop_code == 0u) sh->next_pos = next;  // chain left the super-step (or the input: checked below)
         }
         __syncthreads();
+        L4P(1);  // A2: chain
         // ---- 3. per warp: enumerate the real sequence starts of its window, lengths, local scan -------
         uint32_t my_cnt = 0u, my_out = 0u;
         uint32_t q3[3], olen3[3], excl3[3];
@@ -306,6 +356,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
             sh->outlen[warp] = my_out;
         }
         __syncthreads();
+        L4P(2);  // A3: enumerate + parse + scan
         // ---- 4. descriptors; the special sequence that ended the chain, if any ---------------------------
         {
             uint32_t base_idx = sh->nseq, base_out = sh->out;
@@ -390,6 +441,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                 sh->pos = sh->next_pos;
             }
             __syncthreads();
+            L4P(3);  // A4: descriptors + special sequence
         }
     }
     if (sh->err) return sh->err;
@@ -398,14 +450,14 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
 }
 
 // position of a byte of the output in the shared-memory ring (v = out_pos + ga, see below)
-__device__ __forceinline__ uint32_t l4_ring(uint32_t v) { return v % kL4Ring; }
+__device__ __forceinline__ uint32_t l4_ring(uint32_t v) { return v & (kL4Ring - 1u); }
 
 // Phase B for one block: nseq descriptors -> out[0, total).  Returns total or a negative error.
 __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* __restrict__ out, uint32_t total,
                        const L4Desc* __restrict__ desc, uint32_t nseq, uint32_t* __restrict__ tile_first,
-                       uint8_t* ring, uint16_t* P, uint32_t* big, L4Shared* sh)
+                       uint8_t* ring, uint16_t* P, uint32_t* dpos, uint32_t* dtok, uint8_t* in_s, L4Shared* sh)
 {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x;
     // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
     const uint32_t ga = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
     const uint32_t vend = total + ga;
@@ -419,121 +471,233 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
     }
     __syncthreads();
     if (sh->err) return sh->err;
+    L4P_DECL;
+    L4P(4);  // B0: tile index (includes nothing else)
 
     for (uint32_t t = 0; t < ntiles; ++t) {
+        L4P_COUNT(13, 1);  // tiles
         const uint32_t tlo = t * kL4Tile;                                   // v-space
         const uint32_t thi = (tlo + kL4Tile < vend) ? tlo + kL4Tile : vend;
         const uint32_t tlen = thi - tlo;
         const uint32_t j1 = tile_first[t + 1u];                              // descriptors < j1 start before the next tile
         uint32_t j0 = tile_first[t];
         if (j0 > 0u) --j0;                                                   // the one before may reach into the tile
-        if (tid == 0) sh->big_n = 0u;
-        __syncthreads();
-
-        // bytes [a, b) (v-space, inside the tile) of descriptor j: literals from the input, matches as
-        // parents.  `lanes` threads share the work (1 = the descriptor's own thread, 32 = a warp).
-        auto do_desc = [&](uint32_t j, uint32_t lanes, uint32_t li) {
-            const uint32_t o = desc[j].out_pos + ga;
-            const uint32_t oe = (j + 1u < nseq ? desc[j + 1u].out_pos : total) + ga;
-            const uint32_t p = desc[j].tok_pos;
-            if (p >= in_size || oe < o) { sh->err = -5; return; }
-            auto rd = [&](uint32_t i) -> uint32_t { return in[i]; };
-            uint32_t lit, lit_pos;
-            if (l4_literal_len(rd, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 || lit > in_size - lit_pos || lit > oe - o) {
-                sh->err = -2;
-                return;
+        const uint32_t nd = j1 - j0;
+        if (nd + 1u > kL4TileDescs) return -5;  // (cannot happen: >= 4 output bytes per sequence but the last)
+        // this tile's descriptors: dpos[k] = v position of descriptor j0 + k, dpos[nd] = where the last one ends
+        for (uint32_t k = tid; k <= nd; k += kL4Threads) {
+            const uint32_t j = j0 + k;
+            if (j < nseq) {
+                const L4Desc dd = desc[j];
+                dpos[k] = dd.out_pos + ga;
+                dtok[k] = dd.tok_pos;
+            } else {
+                dpos[k] = vend;
+                dtok[k] = in_size;
             }
-            const uint32_t m = o + lit;   // first match byte (v)
-            const uint32_t ml = oe - m;   // 0 for the last sequence
-            // literals
-            {
-                const uint32_t a = o > tlo ? o : tlo, b = m < thi ? m : thi;
-                for (uint32_t v = a + li; v < b; v += lanes) {
-                    ring[l4_ring(v)] = in[lit_pos + (v - o)];
-                    P[v - tlo] = (uint16_t)(v - tlo);
-                }
-            }
-            if (ml == 0u) return;
-            if (in_size - (lit_pos + lit) < 2u) { sh->err = -3; return; }
-            const uint32_t off = (uint32_t)in[lit_pos + lit] | ((uint32_t)in[lit_pos + lit + 1u] << 8);
-            if (off == 0u || off > m - ga) { sh->err = -4; return; }
-            const uint32_t a = m > tlo ? m : tlo, b = oe < thi ? oe : thi;
-            const uint32_t src0 = m - off;
-            for (uint32_t v = a + li; v < b; v += lanes) {
-                const uint32_t d = v - m;
-                const uint32_t s = off >= ml ? src0 + d : src0 + d % off;  // the byte this one copies
-                if (s < tlo) {  // produced by an earlier tile: final already
-                    ring[l4_ring(v)] = (tlo - s <= kL4Ring - kL4Tile) ? ring[l4_ring(s)] : out[s - ga];
-                    P[v - tlo] = (uint16_t)(v - tlo);
-                } else {
-                    P[v - tlo] = (uint16_t)(s - tlo);
-                }
-            }
-        };
-
-        for (uint32_t j = j0 + tid; j < j1; j += kL4Threads) {
-            const uint32_t o = desc[j].out_pos + ga;
-            const uint32_t oe = (j + 1u < nseq ? desc[j + 1u].out_pos : total) + ga;
-            const uint32_t a = o > tlo ? o : tlo, b = oe < thi ? oe : thi;
-            if (b <= a) continue;
-            if (b - a > kL4BigBytes) {
-                const uint32_t k = atomicAdd(&sh->big_n, 1u);
-                if (k < kL4BigCap) {
-                    big[k] = j;
-                    continue;
-                }
-            }
-            do_desc(j, 1u, 0u);
+        }
+        // the input bytes of this tile's sequences: [first token, end of the last sequence), staged with
+        // aligned 16-byte loads (st_lo = that range widened to 16-byte boundaries of the ADDRESS); a range
+        // that does not fit (incompressible data) is read from global memory beyond the staged part
+        const uint32_t i_lo = j0 < nseq ? desc[j0].tok_pos : in_size;
+        const uint32_t i_hi = j1 < nseq ? desc[j1].tok_pos : in_size;
+        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(in) + i_lo) & 15u);
+        const uint32_t st_lo = i_lo - (mis <= i_lo ? mis : 0u);  // cannot go below the start of the input
+        const uint32_t st_al = (uint32_t)((reinterpret_cast<uintptr_t>(in) + st_lo) & 15u);  // 0 unless clipped at 0
+        uint32_t st_hi = i_hi > st_lo ? i_hi : st_lo;
+        if (st_hi - st_lo > kL4InStage) st_hi = st_lo + kL4InStage;
+        if (st_al == 0u) {
+            const uint32_t nv = (st_hi - st_lo) >> 4;
+            for (uint32_t v = tid; v < nv; v += kL4Threads)
+                *reinterpret_cast<uint4*>(in_s + (v << 4)) = *reinterpret_cast<const uint4*>(in + st_lo + (v << 4));
+            for (uint32_t i = st_lo + (nv << 4) + tid; i < st_hi; i += kL4Threads) in_s[i - st_lo] = in[i];
+        } else {
+            for (uint32_t i = st_lo + tid; i < st_hi; i += kL4Threads) in_s[i - st_lo] = in[i];
         }
         __syncthreads();
-        {
-            const uint32_t nb = sh->big_n < kL4BigCap ? sh->big_n : kL4BigCap;
-            for (uint32_t k = tid >> 5; k < nb; k += (uint32_t)kL4Warps) do_desc(big[k], 32u, lane);
+        L4P(6);  // B1a: descriptors + input -> shared memory
+        auto rdin = [&](uint32_t i) -> uint32_t { return (i >= st_lo && i < st_hi) ? in_s[i - st_lo] : in[i]; };
+
+        // Every thread produces kL4ByteChunk = 16 CONSECUTIVE bytes of the tile, whatever sequences they
+        // belong to, and keeps them -- 16 ring bytes (rb) and 16 parents (pp, packed u16 pairs) -- in
+        // registers through all three steps; shared memory is written with 16-byte stores only.
+        const uint32_t lo_v = t == 0u ? ga : tlo;               // the first tile starts ga bytes in
+        const uint32_t c0 = tlo + tid * kL4ByteChunk;           // this thread's chunk, v-space, 16-byte aligned
+        const uint32_t e0 = tid * kL4ByteChunk;                 // ... and as an index into P[]
+        const uint32_t first = c0 > lo_v ? c0 : lo_v;
+        const uint32_t last = c0 + kL4ByteChunk < thi ? c0 + kL4ByteChunk : thi;
+        uint32_t rb[4] = {0u, 0u, 0u, 0u};
+        uint32_t pp[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) pp[j] = (e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16);  // every byte its own root
+        uint32_t act = 0u;  // bit i: byte i copies a byte of this tile that is not known yet
+        // ---- B1: literals and parents.  Binary search for the sequence that covers the first byte, then
+        // sequence by sequence; the 16 positions are unrolled so that rb / pp stay in registers.
+        if (first < last) {
+            uint32_t covered = 0u;
+            if (nd == 0u) {
+                sh->err = -5;  // bytes without a sequence (cannot happen)
+            } else {
+                uint32_t lo = 0u, hi = nd;  // largest k < nd with dpos[k] <= first  (dpos[0] <= lo_v)
+                while (hi - lo > 1u) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (dpos[mid] <= first) lo = mid;
+                    else hi = mid;
+                }
+                L4P(10);  // B1b: binary search (thread 0's own)
+                for (uint32_t k = lo; k < nd; ++k) {
+                    L4P_COUNT(11, 1);  // sequences thread 0 walks
+                    const uint32_t o = dpos[k], oe = dpos[k + 1u];
+                    if (o >= last) break;
+                    if (oe <= first) continue;
+                    const uint32_t p = dtok[k];
+                    uint32_t lit = 0u, lit_pos = 0u;
+                    if (p >= in_size || oe < o || l4_literal_len(rdin, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 ||
+                        lit > in_size - lit_pos || lit > oe - o) {
+                        sh->err = -2;
+                        break;
+                    }
+                    const uint32_t m = o + lit;   // first match byte
+                    const uint32_t ml = oe - m;   // 0: the block's last sequence
+                    uint32_t off = 1u, src0 = 0u;
+                    if (ml != 0u) {
+                        if (in_size - (lit_pos + lit) < 2u) {
+                            sh->err = -3;
+                            break;
+                        }
+                        off = rdin(lit_pos + lit) | (rdin(lit_pos + lit + 1u) << 8);
+                        if (off == 0u || off > m - ga) {
+                            sh->err = -4;
+                            break;
+                        }
+                        src0 = m - off;
+                    }
+                    const uint32_t a = o > first ? o : first, b = oe < last ? oe : last;
+                    covered += b - a;
+                    // literals of this sequence inside the chunk: a few bytes at most for FLAG data
+                    {
+                        const uint32_t le = m < b ? m : b;
+                        for (uint32_t v = a; v < le; ++v) {
+                            const uint32_t i = v - c0;
+                            const uint32_t byte = rdin(lit_pos + (v - o)) << (8u * (i & 3u));
+                            const uint32_t w = i >> 2;
+                            if (w == 0u) rb[0] |= byte;
+                            else if (w == 1u) rb[1] |= byte;
+                            else if (w == 2u) rb[2] |= byte;
+                            else rb[3] |= byte;
+                        }
+                    }
+                    // match bytes inside the chunk: positions [x, y) of the 16
+                    const uint32_t ms = m > a ? m : a;
+                    if (ms < b) {
+                        const uint32_t x = ms - c0, y = b - c0;
+                        if (off >= ml && ms - off >= tlo) {
+                            // The common case: a plain copy whose source lies inside this tile.  The parent of
+                            // byte v is v - off: the identity pair minus off in both halves, blended in under
+                            // the positions of the run -- a handful of instructions per PAIR, none per byte.
+                            act |= ((1u << y) - 1u) & ~((1u << x) - 1u);
+#pragma unroll
+                            for (uint32_t j = 0; j < 8u; ++j) {
+                                if (2u * j + 1u >= x && 2u * j < y) {
+                                    const uint32_t lo16 = e0 + 2u * j - off, hi16 = e0 + 2u * j + 1u - off;  // parents (may be
+                                    // meaningless for a half outside [x, y): that half keeps its old value)
+                                    const bool tl = 2u * j >= x, th = 2u * j + 1u < y;
+                                    uint32_t w = pp[j];
+                                    if (tl) w = (w & 0xFFFF0000u) | (lo16 & 0xFFFFu);
+                                    if (th) w = (w & 0x0000FFFFu) | (hi16 << 16);
+                                    pp[j] = w;
+                                }
+                            }
+                        } else {
+                            // history (an earlier tile) or an overlapping match: byte by byte
+                            const bool overlap = off < ml;
+#pragma unroll
+                            for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
+                                if (i >= x && i < y) {
+                                    const uint32_t d = c0 + i - m;
+                                    const uint32_t sp = overlap ? src0 + d % off : src0 + d;
+                                    if (sp < tlo) {  // produced by an earlier tile: final already
+                                        const uint32_t byte =
+                                            (tlo - sp <= kL4Ring - kL4Tile) ? ring[l4_ring(sp)] : out[sp - ga];
+                                        rb[i >> 2] |= byte << (8u * (i & 3u));
+                                    } else {
+                                        const uint32_t par = sp - tlo;
+                                        pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (par << 16))
+                                                              : ((pp[i >> 1] & 0xFFFF0000u) | par);
+                                        act |= 1u << i;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (covered != last - first && sh->err == 0) sh->err = -5;  // a gap between sequences (cannot happen)
+            }
         }
+        L4P(5);  // B1c: thread 0's own walk over its sequences
+        *reinterpret_cast<uint4*>(ring + l4_ring(c0)) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+        *reinterpret_cast<uint4*>(P + e0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+        *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
         __syncthreads();
+        L4P(14);  // B1d: stores + waiting for the slowest thread
         if (sh->err) return sh->err;
-        // pointer jumping over the tile: whatever a thread reads from P[] is an ancestor
+        // ---- B3: pointer jumping.  Two hops per round; a byte whose parent does not move any more sits on
+        // a root (P[x] < x for every byte that is not one) and drops out.  Whatever a thread reads from P[]
+        // while its owner is storing is an ancestor either way.
         for (;;) {
+            L4P_COUNT(15, 1);  // rounds
             int changed = 0;
-            for (uint32_t b = tid; b < tlen; b += kL4Threads) {
-                const uint32_t p = P[b];
-                if (p != b) {
-                    const uint32_t q = P[p];
-                    if (q != p) {
-                        P[b] = (uint16_t)q;
+#pragma unroll
+            for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
+                if (act & (1u << i)) {
+                    const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
+                    const uint32_t q = P[P[par]];
+                    if (q != par) {
+                        pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (q << 16)) : ((pp[i >> 1] & 0xFFFF0000u) | q);
                         changed = 1;
+                    } else {
+                        act &= ~(1u << i);
                     }
                 }
             }
+            if (changed) {
+                *reinterpret_cast<uint4*>(P + e0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+            }
             if (!__syncthreads_or(changed)) break;
         }
-        for (uint32_t b = tid; b < tlen; b += kL4Threads) {
-            const uint32_t r = P[b];
-            if (r != b) ring[l4_ring(tlo + b)] = ring[l4_ring(tlo + r)];  // roots are not written in this pass
+        L4P(7);  // B3: pointer jumping
+        // ---- B4: root -> byte, then the chunk goes to the ring (history of the next tiles) and to global
+        // memory straight from the registers.  Roots are literal / history bytes: final since B1.
+#pragma unroll
+        for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
+            const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
+            if (par != e0 + i) rb[i >> 2] |= (uint32_t)ring[l4_ring(tlo + par)] << (8u * (i & 3u));
         }
-        __syncthreads();
-        // tile -> global: 16-byte chunks line up (v-space); the first tile starts ga bytes in, the
-        // last one may end inside a chunk
+        L4P(8);  // B4: root -> byte
+        __syncthreads();  // every thread has read the roots it needs: chunks may be overwritten now
         {
-            const uint32_t lo = t == 0u ? ga : tlo;
-            const uint32_t lo16 = (lo + 15u) & ~15u, hi16 = thi & ~15u;
-            if (lo16 <= hi16) {
-                for (uint32_t v = lo + tid; v < lo16; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
-                for (uint32_t v = lo16 + tid * 16u; v < hi16; v += kL4Threads * 16u)
-                    *reinterpret_cast<uint4*>(out + (v - ga)) = *reinterpret_cast<const uint4*>(ring + l4_ring(v));
-                for (uint32_t v = hi16 + tid; v < thi; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
+            const uint4 bytes = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+            *reinterpret_cast<uint4*>(ring + l4_ring(c0)) = bytes;
+            if (first == c0 && last == c0 + kL4ByteChunk) {
+                *reinterpret_cast<uint4*>(out + (c0 - ga)) = bytes;
             } else {
-                for (uint32_t v = lo + tid; v < thi; v += kL4Threads) out[v - ga] = ring[l4_ring(v)];
+#pragma unroll
+                for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
+                    const uint32_t v = c0 + i;
+                    if (v >= first && v < last) out[v - ga] = (uint8_t)(rb[i >> 2] >> (8u * (i & 3u)));
+                }
             }
         }
-        __syncthreads();  // the ring slot of tile t + 1 (= tile t - 4) is free, P[] can be rewritten
+        __syncthreads();  // P[], dpos[], in_s[] and the chunk's ring bytes are free for the next tile
+        L4P(9);  // B5: chunk -> ring + global
     }
     return (int)total;
 }
 
 // status[b] = decoded size (must equal raw_size) or a negative error code.  scratch: gridDim.x
 // regions of scratch_stride bytes (l4_scratch_bytes of the largest block).
-__global__ void __launch_bounds__(kL4Threads)
+__global__ void __launch_bounds__(kL4Threads, 2)  // two CTAs per SM: at most 64 registers
 lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4BlockDesc* __restrict__ bdesc,
                       int* __restrict__ status, uint32_t n_blocks, unsigned char* scratch, size_t scratch_stride,
                       uint32_t desc_cap)
@@ -541,8 +705,10 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
     extern __shared__ __align__(16) unsigned char l4_smem[];
     uint8_t* ring = l4_smem;
     uint16_t* P = reinterpret_cast<uint16_t*>(l4_smem + kL4Ring);
-    uint32_t* big = reinterpret_cast<uint32_t*>(l4_smem + kL4Ring + 2u * kL4Tile);
-    L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile + 4u * kL4BigCap);
+    uint32_t* dpos = reinterpret_cast<uint32_t*>(l4_smem + kL4Ring + 2u * kL4Tile);
+    uint32_t* dtok = dpos + kL4TileDescs;
+    uint8_t* in_s = l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs;
+    L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + kL4InStage + 32u);
     L4Desc* desc = reinterpret_cast<L4Desc*>(scratch + (size_t)blockIdx.x * scratch_stride);
     uint32_t* tile_first = reinterpret_cast<uint32_t*>(desc + desc_cap);
 
@@ -558,7 +724,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
             r = nseq;
             if (nseq >= 0)
                 r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
-                            ring, P, big, sh);
+                            ring, P, dpos, dtok, in_s, sh);
         }
         __syncthreads();
         if (threadIdx.x == 0) status[b] = r;

@@ -374,3 +374,55 @@ def _capi_u64p():
 def _capi_u32p():
     from libflagstats_b200 import _capi
     return _capi.u32p
+
+
+def test_gpu_lz4_decode_fuzz_agrees_with_the_oracle(cuda_lib, lz4_variant):
+    """Byte flips, truncations and random tails on real liblz4 blocks: every decoder variant must give
+    the oracle's verdict (oracle/lz4_oracle.c, pinned against liblz4) -- the same bytes when the block is
+    still well-formed and decodes to exactly raw_size, a status != raw_size otherwise -- and never fault."""
+    from libflagstats_b200 import blockfile
+
+    rng = np.random.default_rng(11)
+    cats = np.array([99, 147, 83, 163, 97, 145, 73, 137, 2113], np.uint16)
+    bases = [
+        np.repeat(cats[rng.integers(0, 9, 4000)], rng.geometric(1 / 6, 4000)).tobytes()[:30_011],
+        cats[rng.integers(0, 9, 9000)].tobytes(),
+        np.full(40_000, 99, np.uint16).tobytes(),                       # one long overlapping match
+        rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(),           # incompressible: one long literal run
+        (np.arange(3000, dtype=np.uint16) * 7).tobytes() + np.full(9000, 163, np.uint16).tobytes(),
+    ]
+    blocks, sizes = [], []
+    for raw in bases:
+        comp = O.liblz4_compress(raw)
+        blocks.append(comp)
+        sizes.append(len(raw))
+        for _ in range(14):
+            b = bytearray(comp)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                for _k in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif kind == 1:
+                b = b[: int(rng.integers(1, len(b)))]
+            elif kind == 2:
+                b += bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))
+            else:
+                i = int(rng.integers(0, len(b)))
+                b[i] = 0xFF  # long length fields: the serial ("escape") parser
+                b[i + 1:i + 1] = bytes([0xFF] * int(rng.integers(0, 6)))
+            blocks.append(bytes(b))
+            sizes.append(len(raw) if rng.integers(0, 5) else len(raw) + int(rng.integers(-9, 10)))
+    out, status = blockfile.lz4_decode(blocks, sizes)
+    agree_ok = agree_bad = 0
+    for blk, n, got, st in zip(blocks, sizes, out, status):
+        try:
+            want = O.lz4_decompress(blk, n) if n > 0 else None
+        except ValueError:
+            want = None
+        if want is not None:
+            assert st == n and got == want
+            agree_ok += 1
+        else:
+            assert st != n or n <= 0
+            agree_bad += 1
+    assert agree_ok >= len(bases) and agree_bad >= 20  # both verdicts really occurred

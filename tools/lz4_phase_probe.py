@@ -48,8 +48,34 @@ def main():
     n = n_blocks * 512_000
     lib = fs.lib()
     lib.FLAGSTAT_cuda_lz4_profile_fetch.argtypes = [C.c_void_p, C.c_int]
+    lib.FLAGSTAT_cuda_l4_profile_fetch.argtypes = [C.c_void_p, C.c_int]
+    cta_phases = ["A1 successor tables + exit maps", "A2 chain", "A3 enumerate + parse + scan", "A4 descriptors + special",
+                  "B0 tile index", "B1 bytes -> literals + parents (16 bytes per thread)", "B2 (unused)",
+                  "B3 pointer jumping", "B4 root -> byte", "B5 tile -> global"]
     for name, col in (("runs (ratio ~5)", containers.runs_column(n)), ("iid (ratio ~2.2)", containers.iid_column(n))):
         blob = containers.container(col, "lz4")
+        # the CTA decoder (default): thread 0 of every CTA
+        lib.FLAGSTAT_cuda_set_lz4_variant(2)
+        blockfile.flagstat_container(blob, blockfile.LZ4)
+        prof = np.zeros(16, np.uint64)
+        lib.FLAGSTAT_cuda_l4_profile_fetch(prof.ctypes.data, 1)
+        t0 = time.perf_counter()
+        f, got = blockfile.flagstat_container(blob, blockfile.LZ4)
+        dt = time.perf_counter() - t0
+        lib.FLAGSTAT_cuda_l4_profile_fetch(prof.ctypes.data, 1)
+        cyc = [int(x) for x in prof]
+        tot = sum(cyc[:10]) + cyc[10] + cyc[14]
+        print(json.dumps({"decoder": "cta", "b1_detail_cycles_per_tile": {"B1a staging": round(cyc[6] / max(cyc[13], 1)),
+                          "B1b thread 0 binary search": round(cyc[10] / max(cyc[13], 1)), "B1c thread 0 walk": round(cyc[5] / max(cyc[13], 1)),
+                          "B1d stores + wait for slowest": round(cyc[14] / max(cyc[13], 1)),
+                          "sequences thread 0 walks per tile": round(cyc[11] / max(cyc[13], 1), 2)}, "column": name, "blocks": n_blocks, "ratio": round(2 * n / len(blob), 2),
+                          "container_call_s": round(dt, 4), "cycles_thread0_all_ctas": tot,
+                          "share": {cta_phases[k]: round(cyc[k] / tot, 3) for k in range(10)},
+                          "super_steps": cyc[12], "tiles": cyc[13], "jump_rounds": cyc[15],
+                          "cycles_per_block": round(tot / n_blocks), "cycles_per_tile_phase_b": round((sum(cyc[5:10]) + cyc[10] + cyc[14]) / max(cyc[13], 1)),
+                          "cycles_per_super_step_phase_a": round(sum(cyc[0:4]) / max(cyc[12], 1)),
+                          "rounds_per_tile": round(cyc[15] / max(cyc[13], 1), 2)}), flush=True)
+        lib.FLAGSTAT_cuda_set_lz4_variant(1)
         f, got = blockfile.flagstat_container(blob, blockfile.LZ4)  # warm (allocations)
         prof = np.zeros(16, np.uint64)
         lib.FLAGSTAT_cuda_lz4_profile_fetch(prof.ctypes.data, 1)
@@ -60,7 +86,7 @@ def main():
         cyc = [int(x) for x in prof[:12]]
         tot = sum(cyc[k] for k in (0, 1, 2, 3, 4, 5, 8, 9))
         seqs = cyc[6]
-        rec = {"column": name, "blocks": n_blocks, "ratio": round(2 * n / len(blob), 2), "records": got,
+        rec = {"decoder": "warp group", "column": name, "blocks": n_blocks, "ratio": round(2 * n / len(blob), 2), "records": got,
                "container_call_s": round(dt, 4), "sequences_in_group_steps": seqs, "group_steps": cyc[7],
                "slow_path_sequences": cyc[10], "sequences_per_step": round(seqs / max(cyc[7], 1), 1),
                "cycles_per_step": round(tot / max(cyc[7], 1), 0),

@@ -82,15 +82,31 @@ raws = [c.tobytes() for c in cols] * 2
 hb, hr = _handmade_chain_block()
 blocks.append(hb)
 raws.append(hr)
-for v in (1, 0):
+# malformed blocks too (byte flips, truncations, runs of 0xFF length bytes): whatever the verdict, no
+# access outside the buffers and no use of uninitialised shared memory
+bad, bad_sizes = [], []
+for comp, raw in zip(blocks[:5], raws[:5]):
+    for k in range(6):
+        b = bytearray(comp)
+        if k % 3 == 0:
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif k % 3 == 1:
+            b = b[: int(rng.integers(1, len(b)))]
+        else:
+            i = int(rng.integers(0, len(b)))
+            b[i:i + 1] = bytes([0xFF] * int(rng.integers(1, 7)))
+        bad.append(bytes(b))
+        bad_sizes.append(len(raw))
+for v in (2, 1, 0):
     lib.FLAGSTAT_cuda_set_lz4_variant(v)
     out, status = blockfile.lz4_decode(blocks, [len(r) for r in raws])
     assert status == [len(r) for r in raws], (v, status)
     assert all(o == r for o, r in zip(out, raws)), v
+    blockfile.lz4_decode(bad, bad_sizes)
     blob = O.write_lz4_container(cols[0], block_bytes=20_002)
     f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
     assert n == cols[0].size and f.tolist() == O.numpy_flagstat(cols[0]).tolist(), v
-lib.FLAGSTAT_cuda_set_lz4_variant(1)
+lib.FLAGSTAT_cuda_set_lz4_variant(2)
 # pageable host arrays: threaded staging
 a = O.synth_hiseqx(0, 6_000_001, 4, 5000)
 assert fs.flagstat_u64(a).tolist() == O.flagstat_simd(a).tolist()
