@@ -536,7 +536,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         if (first < last) {
             uint32_t covered = 0u;
             if (nd == 0u) {
-                sh->err = -5;  // bytes without a sequence (cannot happen)
+                atomicCAS(&sh->err, 0, -5);  // bytes without a sequence (cannot happen)
             } else {
                 uint32_t lo = 0u, hi = nd;  // largest k < nd with dpos[k] <= first  (dpos[0] <= lo_v)
                 while (hi - lo > 1u) {
@@ -554,7 +554,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                     uint32_t lit = 0u, lit_pos = 0u;
                     if (p >= in_size || oe < o || l4_literal_len(rdin, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 ||
                         lit > in_size - lit_pos || lit > oe - o) {
-                        sh->err = -2;
+                        atomicCAS(&sh->err, 0, -2);
                         break;
                     }
                     const uint32_t m = o + lit;   // first match byte
@@ -562,12 +562,12 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                     uint32_t off = 1u, src0 = 0u;
                     if (ml != 0u) {
                         if (in_size - (lit_pos + lit) < 2u) {
-                            sh->err = -3;
+                            atomicCAS(&sh->err, 0, -3);
                             break;
                         }
                         off = rdin(lit_pos + lit) | (rdin(lit_pos + lit + 1u) << 8);
                         if (off == 0u || off > m - ga) {
-                            sh->err = -4;
+                            atomicCAS(&sh->err, 0, -4);
                             break;
                         }
                         src0 = m - off;
@@ -631,7 +631,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                         }
                     }
                 }
-                if (covered != last - first && sh->err == 0) sh->err = -5;  // a gap between sequences (cannot happen)
+                if (covered != last - first) atomicCAS(&sh->err, 0, -5);  // a gap between sequences (cannot happen)
             }
         }
         L4P(5);  // B1c: thread 0's own walk over its sequences
@@ -642,8 +642,8 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         L4P(14);  // B1d: stores + waiting for the slowest thread
         if (sh->err) return sh->err;
         // ---- B3: pointer jumping.  Two hops per round; a byte whose parent does not move any more sits on
-        // a root (P[x] < x for every byte that is not one) and drops out.  Whatever a thread reads from P[]
-        // while its owner is storing is an ancestor either way.
+        // a root (P[x] < x for every byte that is not one) and drops out.  A round reads P[], then (behind a
+        // barrier) every owner stores its 16 entries.
         for (;;) {
             L4P_COUNT(15, 1);  // rounds
             int changed = 0;
@@ -660,6 +660,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                     }
                 }
             }
+            __syncthreads();  // every thread has read what it needs from P[]: owners may store now (no data race)
             if (changed) {
                 *reinterpret_cast<uint4*>(P + e0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
                 *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
