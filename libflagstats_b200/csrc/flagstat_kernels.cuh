@@ -404,13 +404,19 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 // xa.world != 0 the CTAs of a launch add their per-CTA totals into xa.acc
 // instead of the caller's counters; the CTA that draws the last ticket then
 //   1. takes the rank's 32 totals out of xa.acc (and re-zeroes it),
-//   2. stores them into slot [epoch & 1][rank] of EVERY rank's buffer with
-//      plain 8-byte stores over NVLink, fences, and raises flag[epoch & 1][rank]
-//      = epoch there (st.release.sys),
-//   3. waits until all `world` flags in its OWN buffer carry this epoch
-//      (ld.acquire.sys), adds the `world` slots and writes the global counters.
-// The exchange is 256 bytes per peer and overlaps the tail of the slower ranks'
-// kernels; there is no separate collective launch.
+//   2. stores them into slot [epoch & 1][rank] of EVERY rank's buffer with plain
+//      stores over NVLink, each 64-bit counter as TWO self-validating 8-byte words
+//      {32 bits of the counter, 32-bit tag of the epoch},
+//   3. reads the `world` slots of its OWN buffer until every word carries this epoch's
+//      tag, adds them and writes the global counters.
+// A word is valid exactly when its tag matches, and an aligned 8-byte store is never
+// torn, so there is no flag, and no fence between data and flag: the pushing CTA fires
+// its stores and is done (round 1 pushed 32 plain words, __threadfence_system(), then a
+// flag per peer -- the fence waits for the acknowledgement of every remote store, and with
+// overlapped steps that wait sat on the critical path: the next kernel's CTA that inherits
+// the exchanging CTA's SM slot starts late by the length of the exchange, draws the last
+// ticket itself, and the delay adds up once per step; 7 us at 8 GPUs).
+// The exchange is 512 bytes per peer; there is no separate collective launch.
 //
 // Deferred collection (FLAGSTAT_cuda_device_allreduce_deferred) splits step 3 off: a launch
 // only does 1-2 for its own epoch, and FIRST finishes step 3 of the epoch its predecessor on
@@ -419,7 +425,7 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 // whole step ahead of the slowest rank, so per-step jitter between GPUs no longer adds up
 // (with step 3 in the same launch every step ends with the slowest rank of THAT step).  The
 // parity double buffer is still sufficient: rank r overwrites slot [e & 1] with epoch e + 2
-// only after it has collected e + 1, and a peer raises its flag for e + 1 only after it has
+// only after it has collected e + 1, and a peer pushes e + 1 only after it has
 // collected (i.e. finished reading) e.  tests/test_exchange_protocol_model.py runs both
 // orders, and mixtures of them, under every interleaving.
 //
@@ -438,11 +444,10 @@ __device__ __forceinline__ void emit_counters(unsigned long long* __restrict__ o
 // epoch e (it needs their e+1 data to finish e+1), so a slot is never rewritten
 // while a peer may still read it.
 constexpr int kMaxRanks = 16;
-constexpr int kXchgSlotWords = 32;
+constexpr int kXchgSlotWords = 64;  // 32 counters x {low half | tag, high half | tag}
 // layout of one exchange buffer, in 8-byte words
-constexpr int kXchgSlots = 0;                                           // [2][kMaxRanks][32]
-constexpr int kXchgFlags = kXchgSlots + 2 * kMaxRanks * kXchgSlotWords;  // [2][kMaxRanks]
-constexpr int kXchgAcc = kXchgFlags + 2 * kMaxRanks;                     // [32] per-launch accumulator
+constexpr int kXchgSlots = 0;                                           // [2][kMaxRanks][64]
+constexpr int kXchgAcc = kXchgSlots + 2 * kMaxRanks * kXchgSlotWords;    // [32] per-launch accumulator
 constexpr int kXchgTicket = kXchgAcc + 32;                               // [1]
 constexpr int kXchgErr = kXchgTicket + 1;                                // [1] != 0 after a timeout
 constexpr int kXchgWords = kXchgErr + 1;
@@ -515,10 +520,27 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-// Wait (all lanes of one warp) until every rank's totals of epoch `e` have landed in this rank's
-// buffer, add them and write `nout` global counters to dst.  false = a peer never delivered
-// (or the exchange had already failed): dst untouched, error recorded here, on the host and on
-// every peer, so that nobody keeps waiting for a rank that has given up.
+// Tag of an epoch inside the packed words: never 0 (a zeroed buffer holds no valid word), and
+// different for e and e + 2, the two epochs that share a parity slot.
+__device__ __forceinline__ unsigned long long xchg_tag(unsigned long long e)
+{
+    return (e % 0xFFFFFFFFull + 1ull) << 32;
+}
+__device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, unsigned long long& a,
+                                                  unsigned long long& b)
+{
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// Read (all lanes of one warp, lane = counter) every rank's totals of epoch `e` out of this rank's
+// buffer, waiting for words that have not landed yet, add them and write `nout` global counters
+// to dst.  false = a peer never delivered (or the exchange had already failed): dst untouched,
+// error recorded here, on the host and on every peer, so that nobody keeps waiting for a rank
+// that has given up.
 __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ dst, uint32_t lane,
                                              const XchgArgs& xa, unsigned long long e, int accumulate,
                                              uint32_t nout)
@@ -526,18 +548,42 @@ __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ ds
     unsigned long long* mine = xa.buf[xa.rank];
     const int world = xa.world;
     const uint32_t par = (uint32_t)(e & 1ull);
+    const unsigned long long tag = xchg_tag(e);
+    constexpr unsigned long long kTagMask = 0xFFFFFFFF00000000ull;
+    const unsigned long long* w = mine + kXchgSlots + par * kMaxRanks * kXchgSlotWords + 2u * (lane & 31u);
     bool ok = true;
-    if ((int)lane < world) {
-        const unsigned long long* f = mine + kXchgFlags + par * kMaxRanks + lane;
-        const unsigned long long t0 = global_timer_ns();
-        uint32_t spins = 0;
-        while (ld_acquire_sys(f) != e) {
-            if ((++spins & 63u) == 0u &&
-                (global_timer_ns() - t0 > xa.timeout_ns || ld_relaxed_sys(mine + kXchgErr) != 0ull)) {
-                ok = false;
-                break;
+    unsigned long long v = 0ull;
+    if (lane < nout) {
+        unsigned long long old = 0ull;
+        if (accumulate) old = dst[lane];
+        // four ranks at a time: eight words in flight per lane, one memory round trip when
+        // the peers' words are already there (they normally are: deferred collection)
+        for (int r0 = 0; r0 < world && ok; r0 += 4) {
+            unsigned long long lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                lo[k] = hi[k] = tag;
+                if (r0 + k < world) ld_relaxed_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (r0 + k >= world) continue;
+                if (((lo[k] ^ tag) | (hi[k] ^ tag)) & kTagMask) {  // not there yet: poll this one
+                    const unsigned long long t0 = global_timer_ns();
+                    uint32_t spins = 0;
+                    do {
+                        if ((++spins & 63u) == 0u &&
+                            (global_timer_ns() - t0 > xa.timeout_ns || ld_relaxed_sys(mine + kXchgErr) != 0ull)) {
+                            ok = false;
+                            break;
+                        }
+                        ld_relaxed_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
+                    } while (((lo[k] ^ tag) | (hi[k] ^ tag)) & kTagMask);
+                }
+                v += (lo[k] & 0xFFFFFFFFull) | (hi[k] << 32);
             }
         }
+        v += old;
     }
     if (!__all_sync(0xffffffffu, ok)) {
         if ((int)lane < world) st_relaxed_sys(xa.buf[lane] + kXchgErr, e);  // own buffer included
@@ -545,13 +591,7 @@ __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ ds
         __threadfence_system();
         return false;
     }
-    __threadfence_system();
-    if (lane < nout) {
-        unsigned long long v = 0ull;
-        for (int r = 0; r < world; ++r)
-            v += ld_relaxed_sys(mine + kXchgSlots + (par * kMaxRanks + (uint32_t)r) * kXchgSlotWords + lane);
-        dst[lane] = accumulate ? dst[lane] + v : v;
-    }
+    if (lane < nout) dst[lane] = v;
     return true;
 }
 
@@ -563,35 +603,39 @@ __device__ __noinline__ void xchg_last_cta(unsigned long long* __restrict__ out,
     constexpr uint32_t kOut = MODE == kPospopcnt ? 16u : 32u;
     unsigned long long* mine = xa.buf[xa.rank];
     __threadfence();  // the other CTAs' atomics into acc happen-before their ticket
+    const int world = xa.world;
+    unsigned long long err = 0ull;
+    if (world > 1) err = ld_relaxed_sys(mine + kXchgErr);  // in flight together with the exchange below
     unsigned long long v = 0ull;
     if (lane < kOut) v = atomicExch(mine + kXchgAcc + lane, 0ull);
     if (lane == 0) atomicExch(mine + kXchgTicket, 0ull);
-    const int world = xa.world;
     if (world <= 1) {
         if (lane < kOut) out[lane] = xa.accumulate ? out[lane] + v : v;
         return;
     }
     // a failed exchange stays failed (the parity argument needs every rank to have completed
     // every epoch): nothing more is pushed or written, the host reports ESTATE / ETIMEOUT
-    if (const unsigned long long err = ld_relaxed_sys(mine + kXchgErr)) {
+    if (err) {
         if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, err);  // a peer's give-up reaches this host too
         return;
     }
     // 1. the epoch the previous launch left pending: its readers must be done with the slots
     //    of parity (epoch & 1) before step 2 overwrites them with epoch's own totals -- they are,
-    //    because a peer raises its flag for prev_epoch + 1 = epoch only after ITS step 1
-    if (xa.prev_epoch != 0ull &&
-        !xchg_collect(xa.prev_out, lane, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout))
-        return;
-    // 2. push this launch's totals to every rank, then raise the flags
+    //    because a peer pushes prev_epoch + 1 = epoch only after ITS step 1.  The fence keeps this
+    //    rank's reads of step 1 in front of its stores of step 2 for the same reason; nothing
+    //    remote is outstanding at this point, so it is cheap.
+    if (xa.prev_epoch != 0ull) {
+        if (!xchg_collect(xa.prev_out, lane, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout))
+            return;
+        __threadfence_system();
+    }
+    // 2. push this launch's totals to every rank: fire and forget
     const uint32_t par = (uint32_t)(xa.epoch & 1ull);
-    const uint32_t slot = kXchgSlots + (par * kMaxRanks + (uint32_t)xa.rank) * kXchgSlotWords;
-    for (int r = 0; r < world; ++r)
-        if (lane < kOut) st_relaxed_sys(xa.buf[r] + slot + lane, v);
-    __threadfence_system();
-    __syncwarp();
-    if ((int)lane < world)
-        st_release_sys(xa.buf[lane] + kXchgFlags + par * kMaxRanks + (uint32_t)xa.rank, xa.epoch);
+    const uint32_t slot = kXchgSlots + (par * kMaxRanks + (uint32_t)xa.rank) * kXchgSlotWords + 2u * lane;
+    const unsigned long long tag = xchg_tag(xa.epoch);
+    if (lane < kOut)
+        for (int r = 0; r < world; ++r)
+            st_relaxed_sys_v2(xa.buf[r] + slot, (v & 0xFFFFFFFFull) | tag, (v >> 32) | tag);
     // 3. unless deferred: wait for the peers' totals of this very epoch
     if (!xa.deferred) xchg_collect(out, lane, xa, xa.epoch, xa.accumulate, kOut);
 }

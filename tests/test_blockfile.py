@@ -322,11 +322,12 @@ def test_lz4_container_on_a_second_device_after_the_first(cuda_lib):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
+    from libflagstats_b200 import blockfile
     fs = cuda_lib
     a = O.synth_hiseqx(0, 3 * fs.BLOCK_RECORDS + 777, 1, 1000)
     blob = O.write_lz4_container(a, compressor=O.liblz4_compress)
     want = O.numpy_flagstat(a).tolist()
-    for variant in (1, 0):
+    for variant in (2, 1, 0):
         prev = fs.lib().FLAGSTAT_cuda_set_lz4_variant(variant)
         try:
             for dev in (0, 1, 0, 1):
