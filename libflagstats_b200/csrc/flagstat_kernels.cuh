@@ -530,10 +530,11 @@ __device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigne
 {
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, unsigned long long& a,
+// acquire: whatever this thread stores afterwards (its own push of the next epoch) is ordered behind the read
+__device__ __forceinline__ void ld_acquire_sys_v2(const unsigned long long* p, unsigned long long& a,
                                                   unsigned long long& b)
 {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    asm volatile("ld.acquire.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 // Read (all lanes of one warp, lane = counter) every rank's totals of epoch `e` out of this rank's
@@ -543,7 +544,7 @@ __device__ __forceinline__ void ld_relaxed_sys_v2(const unsigned long long* p, u
 // that has given up.
 __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ dst, uint32_t lane,
                                              const XchgArgs& xa, unsigned long long e, int accumulate,
-                                             uint32_t nout)
+                                             uint32_t nout, unsigned long long failed_before = 0ull)
 {
     unsigned long long* mine = xa.buf[xa.rank];
     const int world = xa.world;
@@ -563,7 +564,11 @@ __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ ds
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 lo[k] = hi[k] = tag;
-                if (r0 + k < world) ld_relaxed_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
+                if (r0 + k < world) ld_acquire_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
+            }
+            if (failed_before) {  // (looked at only now: its load travels together with the ones above)
+                ok = false;
+                break;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -577,7 +582,7 @@ __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ ds
                             ok = false;
                             break;
                         }
-                        ld_relaxed_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
+                        ld_acquire_sys_v2(w + (r0 + k) * kXchgSlotWords, lo[k], hi[k]);
                     } while (((lo[k] ^ tag) | (hi[k] ^ tag)) & kTagMask);
                 }
                 v += (lo[k] & 0xFFFFFFFFull) | (hi[k] << 32);
@@ -586,8 +591,9 @@ __device__ __forceinline__ bool xchg_collect(unsigned long long* __restrict__ ds
         v += old;
     }
     if (!__all_sync(0xffffffffu, ok)) {
-        if ((int)lane < world) st_relaxed_sys(xa.buf[lane] + kXchgErr, e);  // own buffer included
-        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, e);
+        const unsigned long long code = failed_before ? failed_before : e;  // the first failure keeps its epoch
+        if ((int)lane < world) st_relaxed_sys(xa.buf[lane] + kXchgErr, code);  // own buffer included
+        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, code);
         __threadfence_system();
         return false;
     }
@@ -613,21 +619,19 @@ __device__ __noinline__ void xchg_last_cta(unsigned long long* __restrict__ out,
         if (lane < kOut) out[lane] = xa.accumulate ? out[lane] + v : v;
         return;
     }
-    // a failed exchange stays failed (the parity argument needs every rank to have completed
-    // every epoch): nothing more is pushed or written, the host reports ESTATE / ETIMEOUT
-    if (err) {
-        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, err);  // a peer's give-up reaches this host too
-        return;
-    }
     // 1. the epoch the previous launch left pending: its readers must be done with the slots
     //    of parity (epoch & 1) before step 2 overwrites them with epoch's own totals -- they are,
-    //    because a peer pushes prev_epoch + 1 = epoch only after ITS step 1.  The fence keeps this
-    //    rank's reads of step 1 in front of its stores of step 2 for the same reason; nothing
-    //    remote is outstanding at this point, so it is cheap.
+    //    because a peer pushes prev_epoch + 1 = epoch only after ITS step 1, and the acquire loads
+    //    of step 1 keep this rank's own stores of step 2 behind its reads (a __threadfence_system()
+    //    here cost 3 us per step: MEMBAR.SC.SYS on the critical path, profiles/r4x_*).
+    // A failed exchange stays failed (the parity argument needs every rank to have completed
+    // every epoch): nothing more is pushed or written, the host reports ESTATE / ETIMEOUT.
     if (xa.prev_epoch != 0ull) {
-        if (!xchg_collect(xa.prev_out, lane, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout))
+        if (!xchg_collect(xa.prev_out, lane, xa, xa.prev_epoch, xa.prev_accumulate, (uint32_t)xa.prev_nout, err))
             return;
-        __threadfence_system();
+    } else if (err) {
+        if (lane == 0 && xa.host_err) st_relaxed_sys(xa.host_err, err);  // a peer's give-up reaches this host too
+        return;
     }
     // 2. push this launch's totals to every rank: fire and forget
     const uint32_t par = (uint32_t)(xa.epoch & 1ull);
