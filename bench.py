@@ -96,6 +96,11 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
+    def wait_first_sample(self, timeout_s: float) -> None:
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
@@ -558,6 +563,14 @@ def ours(args) -> int:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # nvidia-smi starts polling NOW, not right in front of the timed region: while it initialises
+    # (it attaches to every GPU of the box: longer the more GPUs there are) kernel launches on all
+    # GPUs are disturbed -- the first timed leg of a multi-GPU run used to come out 3 - 7 us per step
+    # slower than the same steps measured a little later (profiles/r4z_*)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
     # warm-up: W steps, then keep stepping until ~0.3 s of load has passed so that the
     # timed region sees the clocks the GPU sustains under this kernel (on this pool the
     # first ~100 ms after idle run ~5 % faster than the power-capped steady state)
@@ -602,10 +615,14 @@ def ours(args) -> int:
             fence()
 
     # ---- device-resident timed region: exactly K steps ---------------------
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
+        sampler.wait_first_sample(3.0)  # nvidia-smi is in its steady polling state
+    fence()
+    # the wait above idled the GPUs: a few steps bring them back to the state the settle loop left
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if xchg is not None:
+        finish_steps()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = fs.lib().FLAGSTAT_cuda_launch_count()
     fence()
@@ -651,23 +668,35 @@ def ours(args) -> int:
         xchg.set_overlap(True)
         deferred = was_deferred
 
-    # overlapped steps with the wait in the same launch (round-1 behaviour), for the record
+    # overlapped steps with the OTHER collection order, for the record (wait in the same launch if the
+    # headline used deferred collection, and the other way round): same K steps, same stream
     immediate_ms = None
-    if xchg is not None and overlap and deferred and world > 1:
-        deferred = False
+    deferred_ms = None
+    if xchg is not None and overlap and world > 1:
+        main_deferred = deferred
+        finish_steps()
+        deferred = not main_deferred
         for _ in range(3):
             step()
+        finish_steps()
         fence()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         i0.record(stream)
         for _ in range(args.steps):
             step()
+        finish_steps()
         i1.record(stream)
         fence()
         t = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        immediate_ms = float(t.item()) / args.steps
-        deferred = True
+        other_ok = counters.cpu().numpy().view(np.uint64).tolist() == result.tolist()
+        if deferred:
+            deferred_ms = float(t.item()) / args.steps if other_ok else None
+            immediate_ms = ms_total / args.steps
+        else:
+            immediate_ms = float(t.item()) / args.steps if other_ok else None
+            deferred_ms = ms_total / args.steps
+        deferred = main_deferred
 
     # the same K steps with the other exchange (kernel + separate NCCL all-reduce), for the record
     alt_ms = None
@@ -947,6 +976,7 @@ def ours(args) -> int:
         "overlap_fallback": overlap_fallback,
         "ms_per_step_serialised_launches": serial_ms,
         "ms_per_step_overlapped_wait_in_launch": immediate_ms,
+        "ms_per_step_overlapped_deferred_collection": deferred_ms,
         "serialised_same_result": serial_ok,
         "ms_per_step_with_nccl_allreduce": alt_ms,
         "nccl_path_same_result": (alt_ok if alt_ms is not None else None),
