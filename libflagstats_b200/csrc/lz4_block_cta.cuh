@@ -21,15 +21,18 @@
 //     in a global scratch array (L2-resident).  Sequences whose lengths use more than four
 //     extension bytes leave the window scheme ("escape") and are parsed by one thread.
 //   PHASE B  copy -- the output is produced in TILES of 8 KiB by all 512 threads.  The tile's
-//     descriptors and the input bytes they cover are staged in shared memory; every thread then
-//     produces 16 CONSECUTIVE output bytes whatever sequences they belong to (a binary search
-//     finds the first one; one thread per sequence would leave most lanes idle behind the longest
-//     match): literal bytes are stored, every match byte gets a PARENT -- the output byte it
-//     copies; parents before the tile are copied at once from the 56 KiB of history the CTA
-//     keeps in shared memory (an LZ4 offset is < 65536; the rare longer reach reads global
-//     memory) -- then pointer jumping over the whole tile resolves chains of matches in
-//     log(depth) rounds and a last pass copies root -> byte.  The tile leaves shared memory
-//     as coalesced 16-byte stores.
+//     descriptors and the input bytes they cover are staged in shared memory.  B1: one thread
+//     per SEQUENCE stores its literal bytes and gives every match byte a PARENT -- the output
+//     byte it copies (two parents per 32-bit store); parents before the tile are copied at once
+//     from the 56 KiB of history the CTA keeps in shared memory (an LZ4 offset is < 65536; the
+//     rare longer reach reads global memory); matches longer than 64 bytes go on a list that the
+//     warps then work off together, 32 bytes at a time, so that no lane waits behind a long
+//     match.  (The first version gave every thread 16 consecutive output bytes and let it walk
+//     the sequences under them: 5.6 warp instructions per output byte, 42 % of the kernel;
+//     profiles/r4q_lz4_phases_cta.jsonl.)  B3: every thread takes 16 consecutive bytes' parents
+//     into registers and pointer jumping over the whole tile resolves chains of matches in
+//     log3(depth) rounds; B4 copies root -> byte.  The tile leaves shared memory as coalesced
+//     16-byte stores.
 //
 // Same block format, same Lz4BlockDesc interface, negative status for anything malformed; every
 // position derived from the input is checked before it is used as an index.
@@ -52,6 +55,8 @@ constexpr uint32_t kL4Ring = 65536;           // the tile being built + 56 KiB o
 constexpr uint32_t kL4MaxExt = 4;             // extension bytes per length the window scheme follows
 constexpr uint32_t kL4ByteChunk = kL4Tile / kL4Threads;  // 16 output bytes per thread and tile
 constexpr uint32_t kL4TileDescs = kL4Tile / 4u + 4u;     // a sequence with a match produces >= 4 bytes
+constexpr uint32_t kL4LongMatch = 64;                    // match bytes (inside the tile) above which the warps share a match
+constexpr uint32_t kL4MaxLong = kL4Tile / kL4LongMatch;  // ... of which a tile holds at most this many
 
 // nx0 codes (u16): < 0xFFF0 = successor position relative to the window start
 constexpr uint32_t kL4Last = 0xFFF1;  // the token's literals end exactly at the end of the input: last sequence
@@ -87,12 +92,18 @@ struct L4Desc {
 };
 
 // shared memory: | ring 64 KiB (phase A: per-warp parse tables + the staged super-step) | P 16 KiB |
-// tile descriptors 16 KiB | input stage 12 KiB | scalars | = 111,136 bytes: two CTAs per SM
+// tile descriptors 16 KiB | input stage 12 KiB | scalars | long matches 2 KiB | = 113,184 bytes: two CTAs per SM
 constexpr uint32_t kL4ParsePerWarp = 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ + 2u * kL4Win /*exit u16*/;  // 2816
 constexpr uint32_t kL4SuperStage = kL4Warps * kL4Win + 32u + 16u;  // the super-step's input bytes (+ alignment slack)
 static_assert(kL4ParsePerWarp * kL4Warps + kL4SuperStage + 16u <= kL4Ring, "parse tables must fit into the ring area");
 constexpr uint32_t kL4InStage = 12288;        // input bytes of one tile staged in shared memory (+ 16 of alignment slack)
-constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + (kL4InStage + 32u) + 256u;
+struct L4Long {  // a long match (or run of literals), clipped to the tile (v-space)
+    uint32_t a, b;  // its bytes inside the tile: [a, b)
+    uint32_t m;     // first byte of the match; literals: input position of byte v is v + m
+    uint32_t off;   // 0: literals
+};
+constexpr size_t kL4Smem =
+    (size_t)kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + (kL4InStage + 32u) + 256u + sizeof(L4Long) * kL4MaxLong;
 
 // scratch one CTA needs for blocks of at most max_comp compressed / max_raw decoded bytes
 __host__ __device__ inline size_t l4_scratch_bytes(uint32_t max_comp, uint32_t max_raw)
@@ -112,7 +123,9 @@ struct L4Shared {  // the scalars at the end of the dynamic shared memory
     uint32_t next_pos;          // where the next super-step starts
     uint32_t pos, out, nseq;    // running state of phase A
     uint32_t done;
+    uint32_t n_long;            // phase B: long matches of this tile
 };
+static_assert(sizeof(L4Shared) <= 256, "the scalars have 256 bytes");
 
 // Length fields of the sequence whose token is at `p` (absolute), read through `rd(i)` = input
 // byte i (caller guarantees i < in_size).  Follows at most `max_ext` extension bytes per field.
@@ -452,12 +465,43 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
 // position of a byte of the output in the shared-memory ring (v = out_pos + ga, see below)
 __device__ __forceinline__ uint32_t l4_ring(uint32_t v) { return v & (kL4Ring - 1u); }
 
+// One match byte range [a, b) of a match that starts at m with offset off (all v-space, clipped to the
+// tile [tlo, ...)), bytes a + first, a + first + step, ...: a source before the tile is final already (copied
+// from the history ring, or from global memory beyond its reach), a source inside the tile becomes
+// the byte's parent.  An overlapping match (off < length) repeats its first `off` bytes: the parent is
+// taken inside that first period, so that its chain is one hop long whatever the length.
+__device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t m, uint32_t off, bool overlap,
+                                               uint32_t first, uint32_t step, uint32_t tlo, uint32_t ga,
+                                               uint8_t* ring, uint16_t* P, const uint8_t* out)
+{
+    // (out is written by this CTA: plain loads, never the read-only path)
+    const uint32_t src0 = m - off;
+    uint32_t v = a + first;
+    if (v >= b) return;
+    uint32_t r = v - m, rstep = step;  // r = (v - m) mod off, kept incrementally
+    if (overlap) {
+        r %= off;
+        rstep %= off;
+    }
+    for (; v < b; v += step) {
+        const uint32_t sp = src0 + r;
+        if (sp < tlo) {
+            ring[l4_ring(v)] = (tlo - sp <= kL4Ring - kL4Tile) ? ring[l4_ring(sp)] : out[sp - ga];
+        } else {
+            P[v - tlo] = (uint16_t)(sp - tlo);
+        }
+        r += rstep;
+        if (overlap && r >= off) r -= off;
+    }
+}
+
 // Phase B for one block: nseq descriptors -> out[0, total).  Returns total or a negative error.
 __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* __restrict__ out, uint32_t total,
                        const L4Desc* __restrict__ desc, uint32_t nseq, uint32_t* __restrict__ tile_first,
-                       uint8_t* ring, uint16_t* P, uint32_t* dpos, uint32_t* dtok, uint8_t* in_s, L4Shared* sh)
+                       uint8_t* ring, uint16_t* P, uint32_t* dpos, uint32_t* dtok, uint8_t* in_s, L4Shared* sh,
+                       L4Long* longs)
 {
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
     const uint32_t ga = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
     const uint32_t vend = total + ga;
@@ -478,7 +522,6 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         L4P_COUNT(13, 1);  // tiles
         const uint32_t tlo = t * kL4Tile;                                   // v-space
         const uint32_t thi = (tlo + kL4Tile < vend) ? tlo + kL4Tile : vend;
-        const uint32_t tlen = thi - tlo;
         const uint32_t j1 = tile_first[t + 1u];                              // descriptors < j1 start before the next tile
         uint32_t j0 = tile_first[t];
         if (j0 > 0u) --j0;                                                   // the one before may reach into the tile
@@ -514,136 +557,112 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         } else {
             for (uint32_t i = st_lo + tid; i < st_hi; i += kL4Threads) in_s[i - st_lo] = in[i];
         }
+        // every byte of the tile starts as its own root
+        const uint32_t c0 = tlo + tid * kL4ByteChunk;           // this thread's chunk in B3 - B5, v-space, 16-byte aligned
+        const uint32_t e0 = tid * kL4ByteChunk;                 // ... and as an index into P[]
+        {
+            uint32_t id[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j) id[j] = (e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16);
+            *reinterpret_cast<uint4*>(P + e0) = make_uint4(id[0], id[1], id[2], id[3]);
+            *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(id[4], id[5], id[6], id[7]);
+        }
+        if (tid == 0) sh->n_long = 0u;
         __syncthreads();
         L4P(6);  // B1a: descriptors + input -> shared memory
         auto rdin = [&](uint32_t i) -> uint32_t { return (i >= st_lo && i < st_hi) ? in_s[i - st_lo] : in[i]; };
-
-        // Every thread produces kL4ByteChunk = 16 CONSECUTIVE bytes of the tile, whatever sequences they
-        // belong to, and keeps them -- 16 ring bytes (rb) and 16 parents (pp, packed u16 pairs) -- in
-        // registers through all three steps; shared memory is written with 16-byte stores only.
         const uint32_t lo_v = t == 0u ? ga : tlo;               // the first tile starts ga bytes in
-        const uint32_t c0 = tlo + tid * kL4ByteChunk;           // this thread's chunk, v-space, 16-byte aligned
-        const uint32_t e0 = tid * kL4ByteChunk;                 // ... and as an index into P[]
-        const uint32_t first = c0 > lo_v ? c0 : lo_v;
-        const uint32_t last = c0 + kL4ByteChunk < thi ? c0 + kL4ByteChunk : thi;
-        uint32_t rb[4] = {0u, 0u, 0u, 0u};
-        uint32_t pp[8];
-#pragma unroll
-        for (uint32_t j = 0; j < 8u; ++j) pp[j] = (e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16);  // every byte its own root
-        uint32_t act = 0u;  // bit i: byte i copies a byte of this tile that is not known yet
-        // ---- B1: literals and parents.  Binary search for the sequence that covers the first byte, then
-        // sequence by sequence; the 16 positions are unrolled so that rb / pp stay in registers.
-        if (first < last) {
-            uint32_t covered = 0u;
-            if (nd == 0u) {
-                atomicCAS(&sh->err, 0, -5);  // bytes without a sequence (cannot happen)
+
+        // ---- B1: one thread per sequence: literals -> ring, match bytes -> parents (or history bytes -> ring)
+        for (uint32_t k = tid; k < nd; k += kL4Threads) {
+            const uint32_t o = dpos[k], oe = dpos[k + 1u];
+            if (oe <= lo_v || o >= thi) continue;  // (the descriptor in front of the tile may end before it)
+            const uint32_t p = dtok[k];
+            uint32_t lit = 0u, lit_pos = 0u;
+            if (p >= in_size || oe < o || l4_literal_len(rdin, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 ||
+                lit > in_size - lit_pos || lit > oe - o) {
+                atomicCAS(&sh->err, 0, -2);
+                break;
+            }
+            const uint32_t m = o + lit;   // first match byte
+            const uint32_t ml = oe - m;   // 0: the block's last sequence
+            // literals inside the tile: a few bytes at most for FLAG data (incompressible input: one long run)
+            {
+                const uint32_t a = o > lo_v ? o : lo_v, b = m < thi ? m : thi;
+                if (a < b && b - a > kL4LongMatch) {
+                    const uint32_t i = atomicAdd(&sh->n_long, 1u);
+                    if (i < kL4MaxLong) longs[i] = L4Long{a, b, lit_pos - o, 0u};
+                } else {
+                    for (uint32_t v = a; v < b; ++v) ring[l4_ring(v)] = (uint8_t)rdin(lit_pos + (v - o));
+                }
+            }
+            if (ml == 0u) continue;
+            if (in_size - (lit_pos + lit) < 2u) {
+                atomicCAS(&sh->err, 0, -3);
+                break;
+            }
+            const uint32_t off = rdin(lit_pos + lit) | (rdin(lit_pos + lit + 1u) << 8);
+            if (off == 0u || off > m - ga) {
+                atomicCAS(&sh->err, 0, -4);
+                break;
+            }
+            const uint32_t a = m > lo_v ? m : lo_v, b = oe < thi ? oe : thi;
+            if (a >= b) continue;
+            if (b - a > kL4LongMatch) {
+                const uint32_t i = atomicAdd(&sh->n_long, 1u);
+                if (i < kL4MaxLong) longs[i] = L4Long{a, b, m, off};  // (always: a tile has room for no more)
+                continue;
+            }
+            if (off >= ml && a - off >= tlo) {
+                // the common case, a plain copy whose source lies inside this tile: parent(v) = v - off,
+                // two parents per 32-bit store
+                uint32_t x = a - tlo, y = b - tlo;
+                uint32_t par = x - off;
+                if (x & 1u) {
+                    P[x] = (uint16_t)par;
+                    ++x;
+                    ++par;
+                }
+                for (; x + 2u <= y; x += 2u, par += 2u) *reinterpret_cast<uint32_t*>(P + x) = par | ((par + 1u) << 16);
+                if (x < y) P[x] = (uint16_t)par;
             } else {
-                uint32_t lo = 0u, hi = nd;  // largest k < nd with dpos[k] <= first  (dpos[0] <= lo_v)
-                while (hi - lo > 1u) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (dpos[mid] <= first) lo = mid;
-                    else hi = mid;
-                }
-                L4P(10);  // B1b: binary search (thread 0's own)
-                for (uint32_t k = lo; k < nd; ++k) {
-                    L4P_COUNT(11, 1);  // sequences thread 0 walks
-                    const uint32_t o = dpos[k], oe = dpos[k + 1u];
-                    if (o >= last) break;
-                    if (oe <= first) continue;
-                    const uint32_t p = dtok[k];
-                    uint32_t lit = 0u, lit_pos = 0u;
-                    if (p >= in_size || oe < o || l4_literal_len(rdin, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 ||
-                        lit > in_size - lit_pos || lit > oe - o) {
-                        atomicCAS(&sh->err, 0, -2);
-                        break;
-                    }
-                    const uint32_t m = o + lit;   // first match byte
-                    const uint32_t ml = oe - m;   // 0: the block's last sequence
-                    uint32_t off = 1u, src0 = 0u;
-                    if (ml != 0u) {
-                        if (in_size - (lit_pos + lit) < 2u) {
-                            atomicCAS(&sh->err, 0, -3);
-                            break;
-                        }
-                        off = rdin(lit_pos + lit) | (rdin(lit_pos + lit + 1u) << 8);
-                        if (off == 0u || off > m - ga) {
-                            atomicCAS(&sh->err, 0, -4);
-                            break;
-                        }
-                        src0 = m - off;
-                    }
-                    const uint32_t a = o > first ? o : first, b = oe < last ? oe : last;
-                    covered += b - a;
-                    // literals of this sequence inside the chunk: a few bytes at most for FLAG data
-                    {
-                        const uint32_t le = m < b ? m : b;
-                        for (uint32_t v = a; v < le; ++v) {
-                            const uint32_t i = v - c0;
-                            const uint32_t byte = rdin(lit_pos + (v - o)) << (8u * (i & 3u));
-                            const uint32_t w = i >> 2;
-                            if (w == 0u) rb[0] |= byte;
-                            else if (w == 1u) rb[1] |= byte;
-                            else if (w == 2u) rb[2] |= byte;
-                            else rb[3] |= byte;
-                        }
-                    }
-                    // match bytes inside the chunk: positions [x, y) of the 16
-                    const uint32_t ms = m > a ? m : a;
-                    if (ms < b) {
-                        const uint32_t x = ms - c0, y = b - c0;
-                        if (off >= ml && ms - off >= tlo) {
-                            // The common case: a plain copy whose source lies inside this tile.  The parent of
-                            // byte v is v - off: the identity pair minus off in both halves, blended in under
-                            // the positions of the run -- a handful of instructions per PAIR, none per byte.
-                            act |= ((1u << y) - 1u) & ~((1u << x) - 1u);
-#pragma unroll
-                            for (uint32_t j = 0; j < 8u; ++j) {
-                                if (2u * j + 1u >= x && 2u * j < y) {
-                                    const uint32_t lo16 = e0 + 2u * j - off, hi16 = e0 + 2u * j + 1u - off;  // parents (may be
-                                    // meaningless for a half outside [x, y): that half keeps its old value)
-                                    const bool tl = 2u * j >= x, th = 2u * j + 1u < y;
-                                    uint32_t w = pp[j];
-                                    if (tl) w = (w & 0xFFFF0000u) | (lo16 & 0xFFFFu);
-                                    if (th) w = (w & 0x0000FFFFu) | (hi16 << 16);
-                                    pp[j] = w;
-                                }
-                            }
-                        } else {
-                            // history (an earlier tile) or an overlapping match: byte by byte
-                            const bool overlap = off < ml;
-#pragma unroll
-                            for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
-                                if (i >= x && i < y) {
-                                    const uint32_t d = c0 + i - m;
-                                    const uint32_t sp = overlap ? src0 + d % off : src0 + d;
-                                    if (sp < tlo) {  // produced by an earlier tile: final already
-                                        const uint32_t byte =
-                                            (tlo - sp <= kL4Ring - kL4Tile) ? ring[l4_ring(sp)] : out[sp - ga];
-                                        rb[i >> 2] |= byte << (8u * (i & 3u));
-                                    } else {
-                                        const uint32_t par = sp - tlo;
-                                        pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (par << 16))
-                                                              : ((pp[i >> 1] & 0xFFFF0000u) | par);
-                                        act |= 1u << i;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                if (covered != last - first) atomicCAS(&sh->err, 0, -5);  // a gap between sequences (cannot happen)
+                l4_match_bytes(a, b, m, off, off < ml, 0u, 1u, tlo, ga, ring, P, out);
             }
         }
-        L4P(5);  // B1c: thread 0's own walk over its sequences
-        *reinterpret_cast<uint4*>(ring + l4_ring(c0)) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
-        *reinterpret_cast<uint4*>(P + e0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-        *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
         __syncthreads();
-        L4P(14);  // B1d: stores + waiting for the slowest thread
+        L4P(5);  // B1c: sequences
         if (sh->err) return sh->err;
-        // ---- B3: pointer jumping.  Two hops per round; a byte whose parent does not move any more sits on
+        // long matches and long runs of literals: one warp each, 32 bytes per step
+        {
+            const uint32_t nl = sh->n_long < kL4MaxLong ? sh->n_long : kL4MaxLong;
+            for (uint32_t i = warp; i < nl; i += (uint32_t)kL4Warps) {
+                const L4Long g = longs[i];
+                if (g.off == 0u) {
+                    for (uint32_t v = g.a + lane; v < g.b; v += 32u) ring[l4_ring(v)] = (uint8_t)rdin(v + g.m);
+                } else {
+                    l4_match_bytes(g.a, g.b, g.m, g.off, g.off < g.b - g.m, lane, 32u, tlo, ga, ring, P, out);
+                }
+            }
+            if (nl != 0u) __syncthreads();
+        }
+        L4P(14);  // B1d: long matches
+        // ---- B3: pointer jumping.  Every thread owns 16 consecutive bytes: their parents (pp, packed u16
+        // pairs) stay in registers.  Two hops per round; a byte whose parent does not move any more sits on
         // a root (P[x] < x for every byte that is not one) and drops out.  A round reads P[], then (behind a
         // barrier) every owner stores its 16 entries.
+        uint32_t pp[8];
+        uint32_t act = 0u;  // bit i: byte i copies a byte of this tile that is not known yet
+        {
+            const uint4 p0 = *reinterpret_cast<const uint4*>(P + e0), p1 = *reinterpret_cast<const uint4*>(P + e0 + 8u);
+            pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w;
+            pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; ++j) {
+                const uint32_t d = pp[j] ^ ((e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16));
+                if (d & 0xFFFFu) act |= 1u << (2u * j);
+                if (d >> 16) act |= 1u << (2u * j + 1u);
+            }
+        }
         for (;;) {
             L4P_COUNT(15, 1);  // rounds
             int changed = 0;
@@ -670,14 +689,24 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         L4P(7);  // B3: pointer jumping
         // ---- B4: root -> byte, then the chunk goes to the ring (history of the next tiles) and to global
         // memory straight from the registers.  Roots are literal / history bytes: final since B1.
+        uint32_t rb[4];
+        {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(ring + l4_ring(c0));
+            rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w;
+        }
 #pragma unroll
         for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
             const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
-            if (par != e0 + i) rb[i >> 2] |= (uint32_t)ring[l4_ring(tlo + par)] << (8u * (i & 3u));
+            if (par != e0 + i) {
+                const uint32_t sft = 8u * (i & 3u);
+                rb[i >> 2] = (rb[i >> 2] & ~(0xFFu << sft)) | ((uint32_t)ring[l4_ring(tlo + par)] << sft);
+            }
         }
         L4P(8);  // B4: root -> byte
         __syncthreads();  // every thread has read the roots it needs: chunks may be overwritten now
         {
+            const uint32_t first = c0 > lo_v ? c0 : lo_v;
+            const uint32_t last = c0 + kL4ByteChunk < thi ? c0 + kL4ByteChunk : thi;
             const uint4 bytes = make_uint4(rb[0], rb[1], rb[2], rb[3]);
             *reinterpret_cast<uint4*>(ring + l4_ring(c0)) = bytes;
             if (first == c0 && last == c0 + kL4ByteChunk) {
@@ -710,6 +739,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
     uint32_t* dtok = dpos + kL4TileDescs;
     uint8_t* in_s = l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs;
     L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + kL4InStage + 32u);
+    L4Long* longs = reinterpret_cast<L4Long*>(l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + kL4InStage + 32u + 256u);
     L4Desc* desc = reinterpret_cast<L4Desc*>(scratch + (size_t)blockIdx.x * scratch_stride);
     uint32_t* tile_first = reinterpret_cast<uint32_t*>(desc + desc_cap);
 
@@ -725,7 +755,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
             r = nseq;
             if (nseq >= 0)
                 r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
-                            ring, P, dpos, dtok, in_s, sh);
+                            ring, P, dpos, dtok, in_s, sh, longs);
         }
         __syncthreads();
         if (threadIdx.x == 0) status[b] = r;

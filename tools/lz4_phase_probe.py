@@ -50,7 +50,7 @@ def main():
     lib.FLAGSTAT_cuda_lz4_profile_fetch.argtypes = [C.c_void_p, C.c_int]
     lib.FLAGSTAT_cuda_l4_profile_fetch.argtypes = [C.c_void_p, C.c_int]
     cta_phases = ["A1 successor tables + exit maps", "A2 chain", "A3 enumerate + parse + scan", "A4 descriptors + special",
-                  "B0 tile index", "B1 bytes -> literals + parents (16 bytes per thread)", "B2 (unused)",
+                  "B0 tile index", "B1 sequences -> literals + parents (one thread per sequence)", "B1a staging",
                   "B3 pointer jumping", "B4 root -> byte", "B5 tile -> global"]
     for name, col in (("runs (ratio ~5)", containers.runs_column(n)), ("iid (ratio ~2.2)", containers.iid_column(n))):
         blob = containers.container(col, "lz4")
@@ -66,9 +66,8 @@ def main():
         cyc = [int(x) for x in prof]
         tot = sum(cyc[:10]) + cyc[10] + cyc[14]
         print(json.dumps({"decoder": "cta", "b1_detail_cycles_per_tile": {"B1a staging": round(cyc[6] / max(cyc[13], 1)),
-                          "B1b thread 0 binary search": round(cyc[10] / max(cyc[13], 1)), "B1c thread 0 walk": round(cyc[5] / max(cyc[13], 1)),
-                          "B1d stores + wait for slowest": round(cyc[14] / max(cyc[13], 1)),
-                          "sequences thread 0 walks per tile": round(cyc[11] / max(cyc[13], 1), 2)}, "column": name, "blocks": n_blocks, "ratio": round(2 * n / len(blob), 2),
+                          "B1c sequences (incl. waiting for the slowest thread)": round(cyc[5] / max(cyc[13], 1)),
+                          "B1d long matches + loading the parents": round(cyc[14] / max(cyc[13], 1))}, "column": name, "blocks": n_blocks, "ratio": round(2 * n / len(blob), 2),
                           "container_call_s": round(dt, 4), "cycles_thread0_all_ctas": tot,
                           "share": {cta_phases[k]: round(cyc[k] / tot, 3) for k in range(10)},
                           "super_steps": cyc[12], "tiles": cyc[13], "jump_rounds": cyc[15],
