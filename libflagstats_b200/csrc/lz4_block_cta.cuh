@@ -54,7 +54,6 @@ constexpr uint32_t kL4Ring = 65536;           // the tile being built + 56 KiB o
                                               // the rare match that reaches further back reads global memory)
 constexpr uint32_t kL4MaxExt = 4;             // extension bytes per length the window scheme follows
 constexpr uint32_t kL4ByteChunk = kL4Tile / kL4Threads;  // 16 output bytes per thread and tile
-constexpr uint32_t kL4TileDescs = kL4Tile / 4u + 4u;     // a sequence with a match produces >= 4 bytes
 constexpr uint32_t kL4LongMatch = 64;                    // match bytes (inside the tile) above which the warps share a match
 constexpr uint32_t kL4MaxLong = kL4Tile / kL4LongMatch;  // ... of which a tile holds at most this many
 
@@ -86,24 +85,25 @@ __device__ unsigned long long g_l4_prof[16];
 #define L4P_COUNT(k, v) do { } while (0)
 #endif
 
-struct L4Desc {
+struct __align__(16) L4Desc {
     uint32_t out_pos;  // first output byte of the sequence (its literals)
-    uint32_t tok_pos;  // position of its token in the input
+    uint32_t lit_pos;  // position of its first literal byte in the input
+    uint32_t lit;      // literal bytes; the match follows them and ends where the next sequence starts
+    uint32_t off;      // match offset (0: the block's last sequence, literals only)
 };
 
 // shared memory: | ring 64 KiB (phase A: per-warp parse tables + the staged super-step) | P 16 KiB |
-// tile descriptors 16 KiB | input stage 12 KiB | scalars | long matches 2 KiB | = 113,184 bytes: two CTAs per SM
+// scalars | long matches 2 KiB | = 84,224 bytes: two CTAs per SM (descriptors and literals are read
+// straight from global memory: staging them per tile cost 9 % of the kernel in barriers and latency)
 constexpr uint32_t kL4ParsePerWarp = 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ + 2u * kL4Win /*exit u16*/;  // 2816
 constexpr uint32_t kL4SuperStage = kL4Warps * kL4Win + 32u + 16u;  // the super-step's input bytes (+ alignment slack)
 static_assert(kL4ParsePerWarp * kL4Warps + kL4SuperStage + 16u <= kL4Ring, "parse tables must fit into the ring area");
-constexpr uint32_t kL4InStage = 12288;        // input bytes of one tile staged in shared memory (+ 16 of alignment slack)
 struct L4Long {  // a long match (or run of literals), clipped to the tile (v-space)
     uint32_t a, b;  // its bytes inside the tile: [a, b)
     uint32_t m;     // first byte of the match; literals: input position of byte v is v + m
     uint32_t off;   // 0: literals
 };
-constexpr size_t kL4Smem =
-    (size_t)kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + (kL4InStage + 32u) + 256u + sizeof(L4Long) * kL4MaxLong;
+constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 256u + sizeof(L4Long) * kL4MaxLong;
 
 // scratch one CTA needs for blocks of at most max_comp compressed / max_raw decoded bytes
 __host__ __device__ inline size_t l4_scratch_bytes(uint32_t max_comp, uint32_t max_raw)
@@ -124,6 +124,7 @@ struct L4Shared {  // the scalars at the end of the dynamic shared memory
     uint32_t pos, out, nseq;    // running state of phase A
     uint32_t done;
     uint32_t n_long;            // phase B: long matches of this tile
+    uint32_t odd;               // phase B: != 0 if a sequence boundary or an offset of this tile is odd
 };
 static_assert(sizeof(L4Shared) <= 256, "the scalars have 256 bytes");
 
@@ -301,7 +302,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
         L4P(1);  // A2: chain
         // ---- 3. per warp: enumerate the real sequence starts of its window, lengths, local scan -------
         uint32_t my_cnt = 0u, my_out = 0u;
-        uint32_t q3[3], olen3[3], excl3[3];
+        uint32_t lp3[3], lo3[3], excl3[3];  // first literal (window-relative), literals | offset << 16, output position
         bool val3[3];
         const uint32_t e_w = sh->entry[warp];
         if (have && e_w != 0xFFFFFFFFu) {
@@ -322,7 +323,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                 // not the special one that ends the chain (that one is handled by thread 0 below)
                 const bool valid = (k == 0u || p != before) && code < 0xFFF0u;
                 prev_last = __shfl_sync(kFull, p, 31);
-                uint32_t olen = 0u;
+                uint32_t olen = 0u, lpos = 0u, litoff = 0u;
                 if (valid) {
                     const uint32_t tok = stage[p];
                     uint32_t lit = tok >> 4, qq = p + 1u;
@@ -333,9 +334,15 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                             lit += b;
                         } while (b == 255u);
                     }
+                    // the offset: behind a long run of literals it may lie beyond the staged bytes (it is inside
+                    // the input: A1 checked that); the match-length extension is staged (code < 0xFFF0 guarantees it)
+                    uint32_t mq = qq + lit;
+                    const uint32_t off = warp * kL4Win + mq + 2u <= kL4Warps * kL4Win + 32u
+                                             ? (uint32_t)stage[mq] | ((uint32_t)stage[mq + 1u] << 8)
+                                             : (uint32_t)in[wb + mq] | ((uint32_t)in[wb + mq + 1u] << 8);
+                    mq += 2u;
                     uint32_t ml = (tok & 15u) + 4u;
                     if ((tok & 15u) == 15u) {
-                        uint32_t mq = qq + lit + 2u - 0u;  // relative to wb; inside the stage (code < 0xFFF0 guarantees it)
                         uint32_t b;
                         do {
                             b = stage[mq++];
@@ -343,6 +350,8 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                         } while (b == 255u);
                     }
                     olen = lit + ml;
+                    lpos = qq;
+                    litoff = lit | (off << 16);  // lit <= 15 + 4 * 255 here
                 }
                 uint32_t incl = olen;
 #pragma unroll
@@ -350,8 +359,8 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                     const uint32_t t = __shfl_up_sync(kFull, incl, s);
                     if (lane >= s) incl += t;
                 }
-                q3[r] = p;
-                olen3[r] = olen;
+                lp3[r] = lpos;
+                lo3[r] = litoff;
                 excl3[r] = carry + incl - olen;
                 val3[r] = valid;
                 carry += __shfl_sync(kFull, incl, 31);
@@ -361,7 +370,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
         } else {
 #pragma unroll
             for (uint32_t r = 0; r < 3u; ++r) {
-                q3[r] = 0u; olen3[r] = 0u; excl3[r] = 0u; val3[r] = false;
+                lp3[r] = 0u; lo3[r] = 0u; excl3[r] = 0u; val3[r] = false;
             }
         }
         if (lane == 0) {
@@ -391,11 +400,10 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                     const uint32_t m = __ballot_sync(kFull, val3[r]);
                     if (val3[r]) {
                         const uint32_t i = base_idx + rank + __popc(m & ((1u << lane) - 1u));
-                        desc[i] = L4Desc{base_out + excl3[r], wb + q3[r]};
+                        desc[i] = L4Desc{base_out + excl3[r], wb + lp3[r], lo3[r] & 0xFFFFu, lo3[r] >> 16};
                     }
                     rank += __popc(m);
                 }
-                (void)olen3;
             }
             __syncthreads();
             if (tid == 0 && sh->err == 0) {
@@ -416,7 +424,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                         } else if (lit_pos + lit == in_size) {  // last sequence: literals only
                             if (lit > out_cap - out) sh->err = -2;
                             else {
-                                desc[nseq++] = L4Desc{out, p};
+                                desc[nseq++] = L4Desc{out, lit_pos, lit, 0u};
                                 out += lit;
                                 sh->done = 1u;
                             }
@@ -424,6 +432,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                             sh->err = -3;
                         } else {
                             uint32_t qq = lit_pos + lit + 2u;
+                            const uint32_t off = (uint32_t)in[qq - 2u] | ((uint32_t)in[qq - 1u] << 8);
                             uint32_t ml = (in[p] & 15u);
                             if (ml == 15u) {
                                 uint32_t b = 255u;
@@ -438,7 +447,7 @@ __device__ int l4_parse(const uint8_t* __restrict__ in, uint32_t in_size, uint32
                             if (sh->err == 0) {
                                 if (lit > out_cap - out || ml > out_cap - out - lit) sh->err = -4;
                                 else {
-                                    desc[nseq++] = L4Desc{out, p};
+                                    desc[nseq++] = L4Desc{out, lit_pos, lit, off == 0u ? 0x10000u : off};  // (0 is invalid: B1 rejects it)
                                     out += lit + ml;
                                     sh->next_pos = qq;
                                     if (qq >= in_size) sh->err = -1;  // a match cannot be the end of a block
@@ -495,13 +504,99 @@ __device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t 
     }
 }
 
+// B3 + B4 for the 16 bytes a thread owns, at a granularity of G bytes (1, or 2 when every sequence
+// boundary and offset of the tile is even -- FLAG words: the usual case -- which halves the work):
+// the thread's E = 16 / G parents stay in registers as packed u16 pairs; pointer jumping, two hops per
+// round -- an element whose parent does not move any more sits on a root (P[x] < x for every element
+// that is not one) and drops out; a round reads the table, then (behind a barrier) every owner
+// stores its entries --; then root -> bytes.  T = the table the rounds read (P for G = 1; for G = 2
+// the element parents are written over the first half of P once everybody has loaded its bytes'
+// parents).  rb receives the thread's 16 final bytes.
+template <uint32_t G>
+__device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t c0, uint32_t e0,
+                                           uint32_t (&rb)[4])
+{
+    constexpr uint32_t E = kL4ByteChunk / G;  // elements per thread
+    constexpr uint32_t W = E / 2u;            // packed pairs
+    const uint32_t u0 = e0 / G;               // first element of this thread
+    uint32_t pp[W];
+    {
+        const uint4 p0 = *reinterpret_cast<const uint4*>(P + e0), p1 = *reinterpret_cast<const uint4*>(P + e0 + 8u);
+        if (G == 1u) {
+            pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w;
+            if (W > 4u) { pp[W - 4u] = p1.x; pp[W - 3u] = p1.y; pp[W - 2u] = p1.z; pp[W - 1u] = p1.w; }
+        } else {
+            // parent element of a byte pair = (parent of its first byte) / 2
+            const uint32_t b8[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (uint32_t j = 0; j < W; ++j) pp[j] = ((b8[2u * j] & 0xFFFFu) >> 1) | (((b8[2u * j + 1u] & 0xFFFFu) >> 1) << 16);
+            __syncthreads();  // everybody has its bytes' parents: the element table may overwrite them
+            if (W == 4u) *reinterpret_cast<uint4*>(P + u0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+            __syncthreads();
+        }
+    }
+    uint32_t act = 0u;  // bit i: element i copies an element of this tile that is not known yet
+#pragma unroll
+    for (uint32_t j = 0; j < W; ++j) {
+        const uint32_t d = pp[j] ^ ((u0 + 2u * j) | ((u0 + 2u * j + 1u) << 16));
+        if (d & 0xFFFFu) act |= 1u << (2u * j);
+        if (d >> 16) act |= 1u << (2u * j + 1u);
+    }
+    for (;;) {
+        L4P_COUNT(15, 1);  // rounds
+        int changed = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < E; ++i) {
+            if (act & (1u << i)) {
+                const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
+                const uint32_t q = P[P[par]];
+                if (q != par) {
+                    pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (q << 16)) : ((pp[i >> 1] & 0xFFFF0000u) | q);
+                    changed = 1;
+                } else {
+                    act &= ~(1u << i);
+                }
+            }
+        }
+        __syncthreads();  // every thread has read what it needs from the table: owners may store now (no data race)
+        if (changed) {
+            *reinterpret_cast<uint4*>(P + u0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+            if (W > 4u) *reinterpret_cast<uint4*>(P + u0 + 8u) = make_uint4(pp[W - 4u], pp[W - 3u], pp[W - 2u], pp[W - 1u]);
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    L4P(7);  // B3: pointer jumping
+    // root -> bytes.  Roots are literal / history bytes: final since B1.
+    {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(ring + l4_ring(c0));
+        rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w;
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < E; ++i) {
+        const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
+        if (par != u0 + i) {
+            if (G == 1u) {
+                const uint32_t sft = 8u * (i & 3u);
+                rb[i >> 2] = (rb[i >> 2] & ~(0xFFu << sft)) | ((uint32_t)ring[l4_ring(tlo + par)] << sft);
+            } else {
+                const uint32_t sft = 16u * (i & 1u);
+                const uint32_t two = *reinterpret_cast<const uint16_t*>(ring + l4_ring(tlo + 2u * par));
+                rb[i >> 1] = (rb[i >> 1] & ~(0xFFFFu << sft)) | (two << sft);
+            }
+        }
+    }
+    L4P(8);  // B4: root -> byte
+}
+
 // Phase B for one block: nseq descriptors -> out[0, total).  Returns total or a negative error.
-__device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* __restrict__ out, uint32_t total,
-                       const L4Desc* __restrict__ desc, uint32_t nseq, uint32_t* __restrict__ tile_first,
-                       uint8_t* ring, uint16_t* P, uint32_t* dpos, uint32_t* dtok, uint8_t* in_s, L4Shared* sh,
-                       L4Long* longs)
+// (desc and tile_first were written by this CTA: no const / __restrict__, so that they are never read through
+// the non-coherent path, which may hold the previous block's lines)
+__device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* out, uint32_t total,
+                       L4Desc* desc, uint32_t nseq, uint32_t* tile_first,
+                       uint8_t* ring, uint16_t* P, L4Shared* sh, L4Long* longs)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr uint32_t kFull = 0xffffffffu;
     // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
     const uint32_t ga = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
     const uint32_t vend = total + ga;
@@ -526,37 +621,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
         uint32_t j0 = tile_first[t];
         if (j0 > 0u) --j0;                                                   // the one before may reach into the tile
         const uint32_t nd = j1 - j0;
-        if (nd + 1u > kL4TileDescs) return -5;  // (cannot happen: >= 4 output bytes per sequence but the last)
-        // this tile's descriptors: dpos[k] = v position of descriptor j0 + k, dpos[nd] = where the last one ends
-        for (uint32_t k = tid; k <= nd; k += kL4Threads) {
-            const uint32_t j = j0 + k;
-            if (j < nseq) {
-                const L4Desc dd = desc[j];
-                dpos[k] = dd.out_pos + ga;
-                dtok[k] = dd.tok_pos;
-            } else {
-                dpos[k] = vend;
-                dtok[k] = in_size;
-            }
-        }
-        // the input bytes of this tile's sequences: [first token, end of the last sequence), staged with
-        // aligned 16-byte loads (st_lo = that range widened to 16-byte boundaries of the ADDRESS); a range
-        // that does not fit (incompressible data) is read from global memory beyond the staged part
-        const uint32_t i_lo = j0 < nseq ? desc[j0].tok_pos : in_size;
-        const uint32_t i_hi = j1 < nseq ? desc[j1].tok_pos : in_size;
-        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(in) + i_lo) & 15u);
-        const uint32_t st_lo = i_lo - (mis <= i_lo ? mis : 0u);  // cannot go below the start of the input
-        const uint32_t st_al = (uint32_t)((reinterpret_cast<uintptr_t>(in) + st_lo) & 15u);  // 0 unless clipped at 0
-        uint32_t st_hi = i_hi > st_lo ? i_hi : st_lo;
-        if (st_hi - st_lo > kL4InStage) st_hi = st_lo + kL4InStage;
-        if (st_al == 0u) {
-            const uint32_t nv = (st_hi - st_lo) >> 4;
-            for (uint32_t v = tid; v < nv; v += kL4Threads)
-                *reinterpret_cast<uint4*>(in_s + (v << 4)) = *reinterpret_cast<const uint4*>(in + st_lo + (v << 4));
-            for (uint32_t i = st_lo + (nv << 4) + tid; i < st_hi; i += kL4Threads) in_s[i - st_lo] = in[i];
-        } else {
-            for (uint32_t i = st_lo + tid; i < st_hi; i += kL4Threads) in_s[i - st_lo] = in[i];
-        }
+        const uint32_t lo_v = t == 0u ? ga : tlo;               // the first tile starts ga bytes in
         // every byte of the tile starts as its own root
         const uint32_t c0 = tlo + tid * kL4ByteChunk;           // this thread's chunk in B3 - B5, v-space, 16-byte aligned
         const uint32_t e0 = tid * kL4ByteChunk;                 // ... and as an index into P[]
@@ -567,25 +632,40 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             *reinterpret_cast<uint4*>(P + e0) = make_uint4(id[0], id[1], id[2], id[3]);
             *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(id[4], id[5], id[6], id[7]);
         }
-        if (tid == 0) sh->n_long = 0u;
+        if (tid == 0) {
+            sh->n_long = 0u;
+            sh->odd = (lo_v | thi) & 1u;
+        }
         __syncthreads();
-        L4P(6);  // B1a: descriptors + input -> shared memory
-        auto rdin = [&](uint32_t i) -> uint32_t { return (i >= st_lo && i < st_hi) ? in_s[i - st_lo] : in[i]; };
-        const uint32_t lo_v = t == 0u ? ga : tlo;               // the first tile starts ga bytes in
+        L4P(6);  // B1a: identity parents
 
-        // ---- B1: one thread per sequence: literals -> ring, match bytes -> parents (or history bytes -> ring)
-        for (uint32_t k = tid; k < nd; k += kL4Threads) {
-            const uint32_t o = dpos[k], oe = dpos[k + 1u];
+        // ---- B1: one thread per sequence, descriptors straight from global memory (the next one is loaded
+        // while this one is worked on): literals -> ring, match bytes -> parents (or history bytes -> ring)
+        uint32_t odd = 0u;
+        bool bad = false;
+        uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+        if (warp * 32u + lane < nd) dn = *reinterpret_cast<const uint4*>(desc + j0 + warp * 32u + lane);
+        for (uint32_t kb = warp * 32u; kb < nd; kb += kL4Threads) {
+            const uint32_t k = kb + lane;
+            const bool have = k < nd;
+            const uint4 d = dn;
+            if (k + kL4Threads < nd) dn = *reinterpret_cast<const uint4*>(desc + j0 + k + kL4Threads);
+            // where the sequence ends = where the next one starts: the neighbour lane has it
+            uint32_t oe = __shfl_down_sync(kFull, d.x, 1);
+            if (lane == 31u || k + 1u >= nd) oe = (have && j0 + k + 1u < nseq) ? desc[j0 + k + 1u].out_pos : total;
+            if (!have || bad) continue;  // (a lane stays in the loop whatever happens: the shuffle above names all 32)
+            const uint32_t o = d.x + ga;
+            oe += ga;
             if (oe <= lo_v || o >= thi) continue;  // (the descriptor in front of the tile may end before it)
-            const uint32_t p = dtok[k];
-            uint32_t lit = 0u, lit_pos = 0u;
-            if (p >= in_size || oe < o || l4_literal_len(rdin, p, in_size, 0xFFFFFFFFu, lit, lit_pos) != 0 ||
-                lit > in_size - lit_pos || lit > oe - o) {
+            const uint32_t lit_pos = d.y, lit = d.z, off = d.w;
+            if (oe < o || lit_pos > in_size || lit > in_size - lit_pos || lit > oe - o) {
+                bad = true;
                 atomicCAS(&sh->err, 0, -2);
-                break;
+                continue;
             }
             const uint32_t m = o + lit;   // first match byte
             const uint32_t ml = oe - m;   // 0: the block's last sequence
+            odd |= o | m | off;
             // literals inside the tile: a few bytes at most for FLAG data (incompressible input: one long run)
             {
                 const uint32_t a = o > lo_v ? o : lo_v, b = m < thi ? m : thi;
@@ -593,18 +673,14 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                     const uint32_t i = atomicAdd(&sh->n_long, 1u);
                     if (i < kL4MaxLong) longs[i] = L4Long{a, b, lit_pos - o, 0u};
                 } else {
-                    for (uint32_t v = a; v < b; ++v) ring[l4_ring(v)] = (uint8_t)rdin(lit_pos + (v - o));
+                    for (uint32_t v = a; v < b; ++v) ring[l4_ring(v)] = in[lit_pos + (v - o)];
                 }
             }
             if (ml == 0u) continue;
-            if (in_size - (lit_pos + lit) < 2u) {
-                atomicCAS(&sh->err, 0, -3);
-                break;
-            }
-            const uint32_t off = rdin(lit_pos + lit) | (rdin(lit_pos + lit + 1u) << 8);
-            if (off == 0u || off > m - ga) {
+            if (off == 0u || off > 0xFFFFu || off > m - ga) {
+                bad = true;
                 atomicCAS(&sh->err, 0, -4);
-                break;
+                continue;
             }
             const uint32_t a = m > lo_v ? m : lo_v, b = oe < thi ? oe : thi;
             if (a >= b) continue;
@@ -629,6 +705,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 l4_match_bytes(a, b, m, off, off < ml, 0u, 1u, tlo, ga, ring, P, out);
             }
         }
+        if (odd & 1u) atomicOr(&sh->odd, 1u);
         __syncthreads();
         L4P(5);  // B1c: sequences
         if (sh->err) return sh->err;
@@ -638,7 +715,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             for (uint32_t i = warp; i < nl; i += (uint32_t)kL4Warps) {
                 const L4Long g = longs[i];
                 if (g.off == 0u) {
-                    for (uint32_t v = g.a + lane; v < g.b; v += 32u) ring[l4_ring(v)] = (uint8_t)rdin(v + g.m);
+                    for (uint32_t v = g.a + lane; v < g.b; v += 32u) ring[l4_ring(v)] = in[v + g.m];
                 } else {
                     l4_match_bytes(g.a, g.b, g.m, g.off, g.off < g.b - g.m, lane, 32u, tlo, ga, ring, P, out);
                 }
@@ -646,64 +723,13 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             if (nl != 0u) __syncthreads();
         }
         L4P(14);  // B1d: long matches
-        // ---- B3: pointer jumping.  Every thread owns 16 consecutive bytes: their parents (pp, packed u16
-        // pairs) stay in registers.  Two hops per round; a byte whose parent does not move any more sits on
-        // a root (P[x] < x for every byte that is not one) and drops out.  A round reads P[], then (behind a
-        // barrier) every owner stores its 16 entries.
-        uint32_t pp[8];
-        uint32_t act = 0u;  // bit i: byte i copies a byte of this tile that is not known yet
-        {
-            const uint4 p0 = *reinterpret_cast<const uint4*>(P + e0), p1 = *reinterpret_cast<const uint4*>(P + e0 + 8u);
-            pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w;
-            pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
-#pragma unroll
-            for (uint32_t j = 0; j < 8u; ++j) {
-                const uint32_t d = pp[j] ^ ((e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16));
-                if (d & 0xFFFFu) act |= 1u << (2u * j);
-                if (d >> 16) act |= 1u << (2u * j + 1u);
-            }
-        }
-        for (;;) {
-            L4P_COUNT(15, 1);  // rounds
-            int changed = 0;
-#pragma unroll
-            for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
-                if (act & (1u << i)) {
-                    const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
-                    const uint32_t q = P[P[par]];
-                    if (q != par) {
-                        pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (q << 16)) : ((pp[i >> 1] & 0xFFFF0000u) | q);
-                        changed = 1;
-                    } else {
-                        act &= ~(1u << i);
-                    }
-                }
-            }
-            __syncthreads();  // every thread has read what it needs from P[]: owners may store now (no data race)
-            if (changed) {
-                *reinterpret_cast<uint4*>(P + e0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-                *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
-            }
-            if (!__syncthreads_or(changed)) break;
-        }
-        L4P(7);  // B3: pointer jumping
-        // ---- B4: root -> byte, then the chunk goes to the ring (history of the next tiles) and to global
-        // memory straight from the registers.  Roots are literal / history bytes: final since B1.
+        // ---- B3, B4: parents -> roots -> bytes (l4_resolve), per FLAG word where the tile allows it
         uint32_t rb[4];
-        {
-            const uint4 r0 = *reinterpret_cast<const uint4*>(ring + l4_ring(c0));
-            rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w;
-        }
-#pragma unroll
-        for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
-            const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
-            if (par != e0 + i) {
-                const uint32_t sft = 8u * (i & 3u);
-                rb[i >> 2] = (rb[i >> 2] & ~(0xFFu << sft)) | ((uint32_t)ring[l4_ring(tlo + par)] << sft);
-            }
-        }
-        L4P(8);  // B4: root -> byte
+        if (sh->odd == 0u) l4_resolve<2u>(P, ring, tlo, c0, e0, rb);
+        else l4_resolve<1u>(P, ring, tlo, c0, e0, rb);
         __syncthreads();  // every thread has read the roots it needs: chunks may be overwritten now
+        // ---- B5: the chunk goes to the ring (history of the next tiles) and to global memory straight from
+        // the registers
         {
             const uint32_t first = c0 > lo_v ? c0 : lo_v;
             const uint32_t last = c0 + kL4ByteChunk < thi ? c0 + kL4ByteChunk : thi;
@@ -719,7 +745,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 }
             }
         }
-        __syncthreads();  // P[], dpos[], in_s[] and the chunk's ring bytes are free for the next tile
+        __syncthreads();  // P[] and the chunk's ring bytes are free for the next tile
         L4P(9);  // B5: chunk -> ring + global
     }
     return (int)total;
@@ -735,11 +761,8 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
     extern __shared__ __align__(16) unsigned char l4_smem[];
     uint8_t* ring = l4_smem;
     uint16_t* P = reinterpret_cast<uint16_t*>(l4_smem + kL4Ring);
-    uint32_t* dpos = reinterpret_cast<uint32_t*>(l4_smem + kL4Ring + 2u * kL4Tile);
-    uint32_t* dtok = dpos + kL4TileDescs;
-    uint8_t* in_s = l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs;
-    L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + kL4InStage + 32u);
-    L4Long* longs = reinterpret_cast<L4Long*>(l4_smem + kL4Ring + 2u * kL4Tile + 8u * kL4TileDescs + kL4InStage + 32u + 256u);
+    L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile);
+    L4Long* longs = reinterpret_cast<L4Long*>(l4_smem + kL4Ring + 2u * kL4Tile + 256u);
     L4Desc* desc = reinterpret_cast<L4Desc*>(scratch + (size_t)blockIdx.x * scratch_stride);
     uint32_t* tile_first = reinterpret_cast<uint32_t*>(desc + desc_cap);
 
@@ -755,7 +778,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
             r = nseq;
             if (nseq >= 0)
                 r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
-                            ring, P, dpos, dtok, in_s, sh, longs);
+                            ring, P, sh, longs);
         }
         __syncthreads();
         if (threadIdx.x == 0) status[b] = r;
