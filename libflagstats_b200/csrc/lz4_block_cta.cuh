@@ -79,10 +79,12 @@ __device__ unsigned long long g_l4_prof[16];
     do {                                                                           \
         if (threadIdx.x == 0) atomicAdd(&g_l4_prof[k], (unsigned long long)(v));   \
     } while (0)
+#define L4P_RESET l4p_t = clock64()
 #else
 #define L4P_DECL do { } while (0)
 #define L4P(k) do { } while (0)
 #define L4P_COUNT(k, v) do { } while (0)
+#define L4P_RESET do { } while (0)
 #endif
 
 struct __align__(16) L4Desc {
@@ -93,8 +95,9 @@ struct __align__(16) L4Desc {
 };
 
 // shared memory: | ring 64 KiB (phase A: per-warp parse tables + the staged super-step) | P 16 KiB |
-// scalars | long matches 2 KiB | = 84,224 bytes: two CTAs per SM (descriptors and literals are read
-// straight from global memory: staging them per tile cost 9 % of the kernel in barriers and latency)
+// scalars | long matches 2 KiB | descriptors of one tile 28 KiB | = 112,896 bytes: two CTAs per SM.  The
+// descriptors of tile t + 1 travel (cp.async) while tile t is being resolved; literal bytes -- rare in FLAG
+// data -- are read straight from global memory.
 constexpr uint32_t kL4ParsePerWarp = 2u * kL4Win /*nx0 u16*/ + kL4Levels * kL4Win /*f[L] u8*/ + 2u * kL4Win /*exit u16*/;  // 2816
 constexpr uint32_t kL4SuperStage = kL4Warps * kL4Win + 32u + 16u;  // the super-step's input bytes (+ alignment slack)
 static_assert(kL4ParsePerWarp * kL4Warps + kL4SuperStage + 16u <= kL4Ring, "parse tables must fit into the ring area");
@@ -103,7 +106,9 @@ struct L4Long {  // a long match (or run of literals), clipped to the tile (v-sp
     uint32_t m;     // first byte of the match; literals: input position of byte v is v + m
     uint32_t off;   // 0: literals
 };
-constexpr size_t kL4Smem = (size_t)kL4Ring + 2u * kL4Tile + 256u + sizeof(L4Long) * kL4MaxLong;
+constexpr uint32_t kL4DescStage = 1792;  // descriptors of one tile staged in shared memory (a tile of FLAG data has 500 - 1300)
+constexpr size_t kL4Smem =
+    (size_t)kL4Ring + 2u * kL4Tile + 256u + sizeof(L4Long) * kL4MaxLong + sizeof(L4Desc) * kL4DescStage;
 
 // scratch one CTA needs for blocks of at most max_comp compressed / max_raw decoded bytes
 __host__ __device__ inline size_t l4_scratch_bytes(uint32_t max_comp, uint32_t max_raw)
@@ -124,7 +129,6 @@ struct L4Shared {  // the scalars at the end of the dynamic shared memory
     uint32_t pos, out, nseq;    // running state of phase A
     uint32_t done;
     uint32_t n_long;            // phase B: long matches of this tile
-    uint32_t odd;               // phase B: != 0 if a sequence boundary or an offset of this tile is odd
 };
 static_assert(sizeof(L4Shared) <= 256, "the scalars have 256 bytes");
 
@@ -504,86 +508,61 @@ __device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t 
     }
 }
 
-// B3 + B4 for the 16 bytes a thread owns, at a granularity of G bytes (1, or 2 when every sequence
-// boundary and offset of the tile is even -- FLAG words: the usual case -- which halves the work):
-// the thread's E = 16 / G parents stay in registers as packed u16 pairs; pointer jumping, two hops per
-// round -- an element whose parent does not move any more sits on a root (P[x] < x for every element
-// that is not one) and drops out; a round reads the table, then (behind a barrier) every owner
-// stores its entries --; then root -> bytes.  T = the table the rounds read (P for G = 1; for G = 2
-// the element parents are written over the first half of P once everybody has loaded its bytes'
-// parents).  rb receives the thread's 16 final bytes.
-template <uint32_t G>
-__device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t c0, uint32_t e0,
-                                           uint32_t (&rb)[4])
+// B3 + B4 for the 16 bytes a thread owns: EIGHT PAIRS, pair j at tile offset j * 1024 + 2 * tid.  (The first
+// version gave a thread 16 consecutive bytes: for a given byte of the chunk the 32 lanes of a warp then read
+// P[] 32 bytes apart -- four banks, eight-way conflicts on both hops of every round.  With pairs interleaved
+// over the threads the lanes of a warp read neighbouring entries.)  The 16 parents stay in registers as packed
+// u16 pairs; pointer jumping, two hops per round -- a byte whose parent does not move any more sits on a root
+// (P[x] < x for every byte that is not one) and drops out; a round reads P[], then (behind a barrier) every
+// owner stores its entries --; then root -> byte.  rb[j] receives pair j's two final bytes.
+constexpr uint32_t kL4Pairs = kL4ByteChunk / 2u;                 // 8
+constexpr uint32_t kL4PairStride = 2u * kL4Threads;              // 1024 bytes between a thread's pairs
+__device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t tid, uint32_t (&rb)[kL4Pairs])
 {
-    constexpr uint32_t E = kL4ByteChunk / G;  // elements per thread
-    constexpr uint32_t W = E / 2u;            // packed pairs
-    const uint32_t u0 = e0 / G;               // first element of this thread
-    uint32_t pp[W];
-    {
-        const uint4 p0 = *reinterpret_cast<const uint4*>(P + e0), p1 = *reinterpret_cast<const uint4*>(P + e0 + 8u);
-        if (G == 1u) {
-            pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w;
-            if (W > 4u) { pp[W - 4u] = p1.x; pp[W - 3u] = p1.y; pp[W - 2u] = p1.z; pp[W - 1u] = p1.w; }
-        } else {
-            // parent element of a byte pair = (parent of its first byte) / 2
-            const uint32_t b8[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    L4P_DECL;
+    const uint32_t x0 = 2u * tid;  // tile offset of pair 0
+    uint32_t pp[kL4Pairs];
+    uint32_t act = 0u;  // bit i: byte i (pair i / 2, half i & 1) copies a byte of this tile that is not known yet
 #pragma unroll
-            for (uint32_t j = 0; j < W; ++j) pp[j] = ((b8[2u * j] & 0xFFFFu) >> 1) | (((b8[2u * j + 1u] & 0xFFFFu) >> 1) << 16);
-            __syncthreads();  // everybody has its bytes' parents: the element table may overwrite them
-            if (W == 4u) *reinterpret_cast<uint4*>(P + u0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-            __syncthreads();
-        }
-    }
-    uint32_t act = 0u;  // bit i: element i copies an element of this tile that is not known yet
-#pragma unroll
-    for (uint32_t j = 0; j < W; ++j) {
-        const uint32_t d = pp[j] ^ ((u0 + 2u * j) | ((u0 + 2u * j + 1u) << 16));
+    for (uint32_t j = 0; j < kL4Pairs; ++j) {
+        const uint32_t x = x0 + j * kL4PairStride;
+        pp[j] = *reinterpret_cast<const uint32_t*>(P + x);
+        const uint32_t d = pp[j] ^ (x | ((x + 1u) << 16));
         if (d & 0xFFFFu) act |= 1u << (2u * j);
         if (d >> 16) act |= 1u << (2u * j + 1u);
     }
     for (;;) {
         L4P_COUNT(15, 1);  // rounds
-        int changed = 0;
+        uint32_t changed = 0u;  // bit j: pair j has a new parent
 #pragma unroll
-        for (uint32_t i = 0; i < E; ++i) {
+        for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
             if (act & (1u << i)) {
                 const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
                 const uint32_t q = P[P[par]];
                 if (q != par) {
                     pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (q << 16)) : ((pp[i >> 1] & 0xFFFF0000u) | q);
-                    changed = 1;
+                    changed |= 1u << (i >> 1);
                 } else {
                     act &= ~(1u << i);
                 }
             }
         }
-        __syncthreads();  // every thread has read what it needs from the table: owners may store now (no data race)
-        if (changed) {
-            *reinterpret_cast<uint4*>(P + u0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-            if (W > 4u) *reinterpret_cast<uint4*>(P + u0 + 8u) = make_uint4(pp[W - 4u], pp[W - 3u], pp[W - 2u], pp[W - 1u]);
-        }
-        if (!__syncthreads_or(changed)) break;
+        __syncthreads();  // every thread has read what it needs from P[]: owners may store now (no data race)
+#pragma unroll
+        for (uint32_t j = 0; j < kL4Pairs; ++j)
+            if (changed & (1u << j)) *reinterpret_cast<uint32_t*>(P + x0 + j * kL4PairStride) = pp[j];
+        if (!__syncthreads_or((int)changed)) break;
     }
     L4P(7);  // B3: pointer jumping
-    // root -> bytes.  Roots are literal / history bytes: final since B1.
-    {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(ring + l4_ring(c0));
-        rb[0] = r0.x; rb[1] = r0.y; rb[2] = r0.z; rb[3] = r0.w;
-    }
+    // root -> byte.  Roots are literal / history bytes: final since B1.
 #pragma unroll
-    for (uint32_t i = 0; i < E; ++i) {
-        const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
-        if (par != u0 + i) {
-            if (G == 1u) {
-                const uint32_t sft = 8u * (i & 3u);
-                rb[i >> 2] = (rb[i >> 2] & ~(0xFFu << sft)) | ((uint32_t)ring[l4_ring(tlo + par)] << sft);
-            } else {
-                const uint32_t sft = 16u * (i & 1u);
-                const uint32_t two = *reinterpret_cast<const uint16_t*>(ring + l4_ring(tlo + 2u * par));
-                rb[i >> 1] = (rb[i >> 1] & ~(0xFFFFu << sft)) | (two << sft);
-            }
-        }
+    for (uint32_t j = 0; j < kL4Pairs; ++j) {
+        const uint32_t x = x0 + j * kL4PairStride;
+        uint32_t two = *reinterpret_cast<const uint16_t*>(ring + l4_ring(tlo + x));
+        const uint32_t p0 = pp[j] & 0xFFFFu, p1 = pp[j] >> 16;
+        if (p0 != x) two = (two & 0xFF00u) | ring[l4_ring(tlo + p0)];
+        if (p1 != x + 1u) two = (two & 0x00FFu) | ((uint32_t)ring[l4_ring(tlo + p1)] << 8);
+        rb[j] = two;
     }
     L4P(8);  // B4: root -> byte
 }
@@ -593,10 +572,9 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
 // the non-coherent path, which may hold the previous block's lines)
 __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* out, uint32_t total,
                        L4Desc* desc, uint32_t nseq, uint32_t* tile_first,
-                       uint8_t* ring, uint16_t* P, L4Shared* sh, L4Long* longs)
+                       uint8_t* ring, uint16_t* P, L4Shared* sh, L4Long* longs, L4Desc* dsm)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    constexpr uint32_t kFull = 0xffffffffu;
     // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
     const uint32_t ga = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
     const uint32_t vend = total + ga;
@@ -613,61 +591,74 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
     L4P_DECL;
     L4P(4);  // B0: tile index (includes nothing else)
 
+    // descriptors of a tile: staged in shared memory by cp.async while the tile before is being resolved
+    auto tile_range = [&](uint32_t t, uint32_t& j0, uint32_t& nd) {
+        const uint32_t j1 = tile_first[t + 1u];  // descriptors < j1 start before the next tile
+        j0 = tile_first[t];
+        if (j0 > 0u) --j0;                       // the one before may reach into the tile
+        nd = j1 - j0;
+    };
+    auto stage_descs = [&](uint32_t t) {
+        uint32_t j0, nd;
+        tile_range(t, j0, nd);
+        const uint32_t ns = nd + 1u < kL4DescStage ? nd + 1u : kL4DescStage;  // one more: where the last one ends
+        for (uint32_t k = tid; k < ns; k += kL4Threads) {
+            if (j0 + k < nseq) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + k);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(desc + j0 + k) : "memory");
+            } else {
+                dsm[k] = L4Desc{total, in_size, 0u, 0u};
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (ntiles != 0u) stage_descs(0u);
+
     for (uint32_t t = 0; t < ntiles; ++t) {
         L4P_COUNT(13, 1);  // tiles
         const uint32_t tlo = t * kL4Tile;                                   // v-space
         const uint32_t thi = (tlo + kL4Tile < vend) ? tlo + kL4Tile : vend;
-        const uint32_t j1 = tile_first[t + 1u];                              // descriptors < j1 start before the next tile
-        uint32_t j0 = tile_first[t];
-        if (j0 > 0u) --j0;                                                   // the one before may reach into the tile
-        const uint32_t nd = j1 - j0;
+        uint32_t j0, nd;
+        tile_range(t, j0, nd);
+        const uint32_t ns = nd + 1u < kL4DescStage ? nd + 1u : kL4DescStage;
         const uint32_t lo_v = t == 0u ? ga : tlo;               // the first tile starts ga bytes in
         // every byte of the tile starts as its own root
-        const uint32_t c0 = tlo + tid * kL4ByteChunk;           // this thread's chunk in B3 - B5, v-space, 16-byte aligned
-        const uint32_t e0 = tid * kL4ByteChunk;                 // ... and as an index into P[]
         {
+            const uint32_t e0 = tid * kL4ByteChunk;
             uint32_t id[8];
 #pragma unroll
             for (uint32_t j = 0; j < 8u; ++j) id[j] = (e0 + 2u * j) | ((e0 + 2u * j + 1u) << 16);
             *reinterpret_cast<uint4*>(P + e0) = make_uint4(id[0], id[1], id[2], id[3]);
             *reinterpret_cast<uint4*>(P + e0 + 8u) = make_uint4(id[4], id[5], id[6], id[7]);
         }
-        if (tid == 0) {
-            sh->n_long = 0u;
-            sh->odd = (lo_v | thi) & 1u;
-        }
+        if (tid == 0) sh->n_long = 0u;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        L4P(6);  // B1a: identity parents
+        L4P(6);  // B1a: identity parents, waiting for the descriptors
 
-        // ---- B1: one thread per sequence, descriptors straight from global memory (the next one is loaded
-        // while this one is worked on): literals -> ring, match bytes -> parents (or history bytes -> ring)
-        uint32_t odd = 0u;
-        bool bad = false;
-        uint4 dn = make_uint4(0u, 0u, 0u, 0u);
-        if (warp * 32u + lane < nd) dn = *reinterpret_cast<const uint4*>(desc + j0 + warp * 32u + lane);
-        for (uint32_t kb = warp * 32u; kb < nd; kb += kL4Threads) {
-            const uint32_t k = kb + lane;
-            const bool have = k < nd;
-            const uint4 d = dn;
-            if (k + kL4Threads < nd) dn = *reinterpret_cast<const uint4*>(desc + j0 + k + kL4Threads);
-            // where the sequence ends = where the next one starts: the neighbour lane has it
-            uint32_t oe = __shfl_down_sync(kFull, d.x, 1);
-            if (lane == 31u || k + 1u >= nd) oe = (have && j0 + k + 1u < nseq) ? desc[j0 + k + 1u].out_pos : total;
-            if (!have || bad) continue;  // (a lane stays in the loop whatever happens: the shuffle above names all 32)
+        // ---- B1: one thread per sequence: literals -> ring, match bytes -> parents (or history bytes -> ring)
+        for (uint32_t k = tid; k < nd; k += kL4Threads) {
+            uint4 d;
+            uint32_t oe;
+            if (k + 1u < ns) {
+                d = *reinterpret_cast<const uint4*>(dsm + k);
+                oe = dsm[k + 1u].out_pos;
+            } else {  // (more sequences in the tile than the stage holds: incompressible input)
+                d = *reinterpret_cast<const uint4*>(desc + j0 + k);
+                oe = j0 + k + 1u < nseq ? desc[j0 + k + 1u].out_pos : total;
+            }
             const uint32_t o = d.x + ga;
             oe += ga;
             if (oe <= lo_v || o >= thi) continue;  // (the descriptor in front of the tile may end before it)
             const uint32_t lit_pos = d.y, lit = d.z, off = d.w;
             if (oe < o || lit_pos > in_size || lit > in_size - lit_pos || lit > oe - o) {
-                bad = true;
                 atomicCAS(&sh->err, 0, -2);
-                continue;
+                break;
             }
             const uint32_t m = o + lit;   // first match byte
             const uint32_t ml = oe - m;   // 0: the block's last sequence
-            odd |= o | m | off;
             // literals inside the tile: a few bytes at most for FLAG data (incompressible input: one long run)
-            {
+            if (lit != 0u) {
                 const uint32_t a = o > lo_v ? o : lo_v, b = m < thi ? m : thi;
                 if (a < b && b - a > kL4LongMatch) {
                     const uint32_t i = atomicAdd(&sh->n_long, 1u);
@@ -678,9 +669,8 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             }
             if (ml == 0u) continue;
             if (off == 0u || off > 0xFFFFu || off > m - ga) {
-                bad = true;
                 atomicCAS(&sh->err, 0, -4);
-                continue;
+                break;
             }
             const uint32_t a = m > lo_v ? m : lo_v, b = oe < thi ? oe : thi;
             if (a >= b) continue;
@@ -689,10 +679,11 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 if (i < kL4MaxLong) longs[i] = L4Long{a, b, m, off};  // (always: a tile has room for no more)
                 continue;
             }
+            uint32_t x = a - tlo;
+            const uint32_t y = b - tlo;
             if (off >= ml && a - off >= tlo) {
                 // the common case, a plain copy whose source lies inside this tile: parent(v) = v - off,
                 // two parents per 32-bit store
-                uint32_t x = a - tlo, y = b - tlo;
                 uint32_t par = x - off;
                 if (x & 1u) {
                     P[x] = (uint16_t)par;
@@ -701,14 +692,40 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 }
                 for (; x + 2u <= y; x += 2u, par += 2u) *reinterpret_cast<uint32_t*>(P + x) = par | ((par + 1u) << 16);
                 if (x < y) P[x] = (uint16_t)par;
+            } else if (off < ml && m - off >= tlo && a == m && (off == 1u || (off & 1u) == 0u)) {
+                // a repeating match (a run of equal FLAG words: offset 2) whose first period lies inside this
+                // tile: parent(v) = first period + (v - m) mod off -- the chain is one hop long whatever the
+                // length --, again two parents per store
+                const uint32_t s0 = m - off - tlo;
+                uint32_t r = 0u;
+                if (off == 1u) {
+                    if (x & 1u) P[x++] = (uint16_t)s0;
+                    for (; x + 2u <= y; x += 2u) *reinterpret_cast<uint32_t*>(P + x) = s0 | (s0 << 16);
+                    if (x < y) P[x] = (uint16_t)s0;
+                } else {
+                    if (x & 1u) {  // odd start, even offset: single parents (pairs would straddle the period)
+                        for (; x < y; ++x) {
+                            P[x] = (uint16_t)(s0 + r);
+                            if (++r == off) r = 0u;
+                        }
+                    } else {
+                        for (; x + 2u <= y; x += 2u) {
+                            const uint32_t par = s0 + r;
+                            *reinterpret_cast<uint32_t*>(P + x) = par | ((par + 1u) << 16);
+                            r += 2u;
+                            if (r == off) r = 0u;
+                        }
+                        if (x < y) P[x] = (uint16_t)(s0 + r);
+                    }
+                }
             } else {
                 l4_match_bytes(a, b, m, off, off < ml, 0u, 1u, tlo, ga, ring, P, out);
             }
         }
-        if (odd & 1u) atomicOr(&sh->odd, 1u);
         __syncthreads();
         L4P(5);  // B1c: sequences
         if (sh->err) return sh->err;
+        if (t + 1u < ntiles) stage_descs(t + 1u);  // (nobody reads this tile's any more; they land during B3)
         // long matches and long runs of literals: one warp each, 32 bytes per step
         {
             const uint32_t nl = sh->n_long < kL4MaxLong ? sh->n_long : kL4MaxLong;
@@ -723,26 +740,22 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             if (nl != 0u) __syncthreads();
         }
         L4P(14);  // B1d: long matches
-        // ---- B3, B4: parents -> roots -> bytes (l4_resolve), per FLAG word where the tile allows it
-        uint32_t rb[4];
-        if (sh->odd == 0u) l4_resolve<2u>(P, ring, tlo, c0, e0, rb);
-        else l4_resolve<1u>(P, ring, tlo, c0, e0, rb);
-        __syncthreads();  // every thread has read the roots it needs: chunks may be overwritten now
-        // ---- B5: the chunk goes to the ring (history of the next tiles) and to global memory straight from
-        // the registers
-        {
-            const uint32_t first = c0 > lo_v ? c0 : lo_v;
-            const uint32_t last = c0 + kL4ByteChunk < thi ? c0 + kL4ByteChunk : thi;
-            const uint4 bytes = make_uint4(rb[0], rb[1], rb[2], rb[3]);
-            *reinterpret_cast<uint4*>(ring + l4_ring(c0)) = bytes;
-            if (first == c0 && last == c0 + kL4ByteChunk) {
-                *reinterpret_cast<uint4*>(out + (c0 - ga)) = bytes;
-            } else {
+        // ---- B3, B4: parents -> roots -> bytes
+        uint32_t rb[kL4Pairs];
+        l4_resolve(P, ring, tlo, tid, rb);
+        L4P_RESET;
+        __syncthreads();  // every thread has read the roots it needs: the tile's ring bytes may be overwritten now
+        // ---- B5: the pairs go to the ring (history of the next tiles) and to global memory straight from the
+        // registers: a warp stores 64 consecutive bytes at a time
 #pragma unroll
-                for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
-                    const uint32_t v = c0 + i;
-                    if (v >= first && v < last) out[v - ga] = (uint8_t)(rb[i >> 2] >> (8u * (i & 3u)));
-                }
+        for (uint32_t j = 0; j < kL4Pairs; ++j) {
+            const uint32_t v = tlo + 2u * tid + j * kL4PairStride;
+            *reinterpret_cast<uint16_t*>(ring + l4_ring(v)) = (uint16_t)rb[j];
+            if (v >= lo_v && v + 2u <= thi) {
+                *reinterpret_cast<uint16_t*>(out + (v - ga)) = (uint16_t)rb[j];  // (out - ga is 16-byte aligned, v even)
+            } else {
+                if (v >= lo_v && v < thi) out[v - ga] = (uint8_t)rb[j];
+                if (v + 1u >= lo_v && v + 1u < thi) out[v + 1u - ga] = (uint8_t)(rb[j] >> 8);
             }
         }
         __syncthreads();  // P[] and the chunk's ring bytes are free for the next tile
@@ -763,6 +776,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
     uint16_t* P = reinterpret_cast<uint16_t*>(l4_smem + kL4Ring);
     L4Shared* sh = reinterpret_cast<L4Shared*>(l4_smem + kL4Ring + 2u * kL4Tile);
     L4Long* longs = reinterpret_cast<L4Long*>(l4_smem + kL4Ring + 2u * kL4Tile + 256u);
+    L4Desc* dsm = reinterpret_cast<L4Desc*>(l4_smem + kL4Ring + 2u * kL4Tile + 256u + sizeof(L4Long) * kL4MaxLong);
     L4Desc* desc = reinterpret_cast<L4Desc*>(scratch + (size_t)blockIdx.x * scratch_stride);
     uint32_t* tile_first = reinterpret_cast<uint32_t*>(desc + desc_cap);
 
@@ -778,7 +792,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
             r = nseq;
             if (nseq >= 0)
                 r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
-                            ring, P, sh, longs);
+                            ring, P, sh, longs, dsm);
         }
         __syncthreads();
         if (threadIdx.x == 0) status[b] = r;
