@@ -512,9 +512,9 @@ __device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t 
 // version gave a thread 16 consecutive bytes: for a given byte of the chunk the 32 lanes of a warp then read
 // P[] 32 bytes apart -- four banks, eight-way conflicts on both hops of every round.  With pairs interleaved
 // over the threads the lanes of a warp read neighbouring entries.)  The 16 parents stay in registers as packed
-// u16 pairs; pointer jumping, two hops per round -- a byte whose parent does not move any more sits on a root
-// (P[x] < x for every byte that is not one) and drops out; a round reads P[], then (behind a barrier) every
-// owner stores its entries --; then root -> byte.  rb[j] receives pair j's two final bytes.
+// u16 pairs; pointer jumping, two hops per round, a PAIR at a time -- a pair whose parents do not move any more
+// sits on roots (P[x] < x for every byte that is not one) and drops out; a round reads P[], then (behind a
+// barrier) every owner stores its entries --; then root -> byte.  rb[j] receives pair j's two final bytes.
 constexpr uint32_t kL4Pairs = kL4ByteChunk / 2u;                 // 8
 constexpr uint32_t kL4PairStride = 2u * kL4Threads;              // 1024 bytes between a thread's pairs
 __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t tid, uint32_t (&rb)[kL4Pairs])
@@ -522,28 +522,33 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
     L4P_DECL;
     const uint32_t x0 = 2u * tid;  // tile offset of pair 0
     uint32_t pp[kL4Pairs];
-    uint32_t act = 0u;  // bit i: byte i (pair i / 2, half i & 1) copies a byte of this tile that is not known yet
+    uint32_t act = 0u;  // bit j: a byte of pair j copies a byte of this tile that is not known yet
 #pragma unroll
     for (uint32_t j = 0; j < kL4Pairs; ++j) {
         const uint32_t x = x0 + j * kL4PairStride;
         pp[j] = *reinterpret_cast<const uint32_t*>(P + x);
-        const uint32_t d = pp[j] ^ (x | ((x + 1u) << 16));
-        if (d & 0xFFFFu) act |= 1u << (2u * j);
-        if (d >> 16) act |= 1u << (2u * j + 1u);
+        if (pp[j] != (x | ((x + 1u) << 16))) act |= 1u << j;
     }
+    // parents of the two bytes p0 = w & 0xFFFF, p1 = w >> 16: ONE 32-bit load when they are an aligned pair
+    // themselves (p1 = p0 + 1, p0 even) -- nearly always: FLAG words are two bytes, matches between them
+    // have even offsets, and only ~2 % of the sequences start or end on an odd byte
+    auto hop = [&](uint32_t w) -> uint32_t {
+        const uint32_t p0 = w & 0xFFFFu;
+        if (w == (w & 0xFFFEu) * 0x10001u + 0x10000u) return *reinterpret_cast<const uint32_t*>(P + p0);
+        return (uint32_t)P[p0] | ((uint32_t)P[w >> 16] << 16);
+    };
     for (;;) {
         L4P_COUNT(15, 1);  // rounds
-        uint32_t changed = 0u;  // bit j: pair j has a new parent
+        uint32_t changed = 0u;  // bit j: pair j has new parents
 #pragma unroll
-        for (uint32_t i = 0; i < kL4ByteChunk; ++i) {
-            if (act & (1u << i)) {
-                const uint32_t par = (i & 1u) ? (pp[i >> 1] >> 16) : (pp[i >> 1] & 0xFFFFu);
-                const uint32_t q = P[P[par]];
-                if (q != par) {
-                    pp[i >> 1] = (i & 1u) ? ((pp[i >> 1] & 0x0000FFFFu) | (q << 16)) : ((pp[i >> 1] & 0xFFFF0000u) | q);
-                    changed |= 1u << (i >> 1);
+        for (uint32_t j = 0; j < kL4Pairs; ++j) {
+            if (act & (1u << j)) {
+                const uint32_t q = hop(hop(pp[j]));
+                if (q != pp[j]) {
+                    pp[j] = q;
+                    changed |= 1u << j;
                 } else {
-                    act &= ~(1u << i);
+                    act &= ~(1u << j);  // both parents are roots
                 }
             }
         }
@@ -681,7 +686,19 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
             }
             uint32_t x = a - tlo;
             const uint32_t y = b - tlo;
-            if (off >= ml && a - off >= tlo) {
+            if (off >= ml && a - off < tlo && tlo + off - a <= kL4Ring - kL4Tile) {
+                // a plain copy that begins in the history ring (an earlier tile: final bytes): copy those,
+                // two at a time where FLAG words line up; what is left of the match has its source in this tile
+                const uint32_t he = b < tlo + off ? b : tlo + off;  // v < tlo + off <=> source before the tile
+                uint32_t v = a;
+                if (((v | off) & 1u) == 0u)
+                    for (; v + 2u <= he; v += 2u)
+                        *reinterpret_cast<uint16_t*>(ring + l4_ring(v)) = *reinterpret_cast<const uint16_t*>(ring + l4_ring(v - off));
+                for (; v < he; ++v) ring[l4_ring(v)] = ring[l4_ring(v - off)];
+                x = he - tlo;
+            }
+            if (x >= y) continue;
+            if (off >= ml && x >= off) {
                 // the common case, a plain copy whose source lies inside this tile: parent(v) = v - off,
                 // two parents per 32-bit store
                 uint32_t par = x - off;

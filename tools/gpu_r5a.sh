@@ -14,3 +14,4 @@ for (nb,cb),v in sorted(rows.items()):
     print(f"decode {nb} blocks comp {cb/1e6:.0f} MB: best {min(v):.3f} ms = {rb/min(v)/1e6:.1f} GB/s out, median {sorted(v)[len(v)//2]:.3f} ms, n={len(v)}")
 PY
 echo "== phases"; timeout 600 python tools/lz4_phase_probe.py 400 > $OUT/lz4_phases.jsonl 2> $OUT/lz4_phases.err; echo "rc=$?"; grep '"cta"' $OUT/lz4_phases.jsonl | cut -c1-900; tail -3 $OUT/lz4_phases.err
+echo "== ncu"; bash tools/ncu_lz4.sh ${TAG}_ncu 296 > $OUT/ncu_session.txt 2>&1; grep -v "^\[" $OUT/ncu_session.txt | head -30
