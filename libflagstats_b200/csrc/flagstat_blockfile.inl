@@ -76,6 +76,22 @@ int io_threads()
     return t;
 }
 
+// Threads for gathering compressed payloads into a pinned staging buffer: every CPU of the affinity mask
+// (the calling thread waits for them anyway), at most 24.  FLAGSTAT_CUDA_IO_THREADS overrides.
+int gather_threads()
+{
+    if (const char* e = std::getenv("FLAGSTAT_CUDA_IO_THREADS")) {
+        const int t = std::atoi(e);
+        if (t > 0) return t > 24 ? 24 : t;
+    }
+    int cpus = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+    if (cpus <= 0) cpus = (int)std::thread::hardware_concurrency();
+    if (cpus < 2) cpus = 2;
+    return cpus > 24 ? 24 : cpus;
+}
+
 // Copy into a pinned staging slot with non-temporal stores: the slot is written once and then
 // read by the DMA engine, never by this core, so the destination lines need not be read for
 // ownership nor kept in cache -- a quarter less DRAM traffic than memcpy on the staged path
@@ -332,8 +348,9 @@ int lz4_lane_ship(int mode, int codec, Lz4Lane& l, size_t comp_bytes, size_t raw
     return 0;
 }
 
+constexpr int kLz4Lanes = 3;  // batch k is decoded while k + 1 crosses PCIe and k + 2 is gathered on the host
 struct Lz4Ctx {
-    Lz4Lane lanes[2];
+    Lz4Lane lanes[kLz4Lanes];
     uint64_t* d_flags = nullptr;
     int dev = -1;
 };
@@ -419,7 +436,8 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
     uint64_t* d_flags = ctx->d_flags;
     CK(cudaMemset(d_flags, 0, 32 * sizeof(uint64_t)));
 
-    const int T = io_threads();
+    const int T = gather_threads();
+    const bool nt = staging_nt();
     int batch_blocks = kBatchBlocks;
     if (codec == kCodecLz4 && lz4_variant() == 2) {
         // The CTA decoder works on 2 x SMs blocks at a time (one wave); batches of that size let the
@@ -475,7 +493,8 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
             for (size_t b = first + (size_t)t; b < last; b += (size_t)T) {
                 unsigned char* dst = l.h_comp + l.h_desc[b - first].comp_off;
                 if (src.mem) {
-                    std::memcpy(dst, src.mem + idx[b].src_off, idx[b].comp);
+                    if (nt) copy_streaming(dst, src.mem + idx[b].src_off, idx[b].comp);
+                    else std::memcpy(dst, src.mem + idx[b].src_off, idx[b].comp);
                 } else {
                     size_t got = 0;
                     while (got < idx[b].comp) {
@@ -503,10 +522,10 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
         if (err.load()) return err.load();
         rc = lz4_lane_ship(mode, codec, l, c, r, all_even, d_flags);
         if (rc) return rc;
-        cur ^= 1;
+        cur = (cur + 1) % kLz4Lanes;
         first = last;
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kLz4Lanes; ++i) {
         rc = lz4_lane_retire(lanes[i]);
         if (rc) return rc;
     }
