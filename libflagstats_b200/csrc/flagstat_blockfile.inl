@@ -209,6 +209,105 @@ int zstd_launch(const unsigned char* d_comp, unsigned char* d_raw, const Lz4Bloc
     return 0;
 }
 
+// Zstd frames, second version (default): entropy stage -> descriptors + literals, then the LZ4 copy phase
+// (zstd_block.cuh).  FLAGSTAT_CUDA_ZSTD_VARIANT=0 runs the first version (one thread per frame) for A/B.
+int zstd_variant()
+{
+    const char* e = std::getenv("FLAGSTAT_CUDA_ZSTD_VARIANT");
+    return (e && std::atoi(e) == 0) ? 0 : 1;
+}
+
+struct Zstd2 {   // buffers of one batch; grow on demand
+    ZstdFrameAux* h_aux = nullptr;  // pinned
+    ZstdFrameAux* d_aux = nullptr;
+    ZstdParsed* d_parsed = nullptr;
+    unsigned char* d_lit = nullptr;
+    L4Desc* d_descs = nullptr;
+    uint32_t* d_tf = nullptr;
+    size_t blk_cap = 0, lit_cap = 0, desc_cap = 0, tf_cap = 0;
+};
+
+void zstd2_free(Zstd2& z)
+{
+    if (z.h_aux) cudaFreeHost(z.h_aux);
+    if (z.d_aux) cudaFree(z.d_aux);
+    if (z.d_parsed) cudaFree(z.d_parsed);
+    if (z.d_lit) cudaFree(z.d_lit);
+    if (z.d_descs) cudaFree(z.d_descs);
+    if (z.d_tf) cudaFree(z.d_tf);
+    z = Zstd2();
+}
+
+// h_comp: the batch's compressed bytes on the HOST (the frames' headers say how many descriptors each frame
+// can produce: zstd::count_descriptors, header arithmetic only), h_desc: its descriptors.
+int zstd2_launch(Zstd2& z, const unsigned char* h_comp, const Lz4BlockDesc* h_desc, const unsigned char* d_comp,
+                 unsigned char* d_raw, const Lz4BlockDesc* d_desc, int* d_status, uint32_t n, cudaStream_t st)
+{
+    int dev = 0;
+    DeviceInfo* di = nullptr;
+    CK(cudaGetDevice(&dev));
+    const int irc = device_info(dev, &di);
+    if (irc) return irc;
+    if (n > z.blk_cap) {
+        if (z.h_aux) cudaFreeHost(z.h_aux);
+        if (z.d_aux) cudaFree(z.d_aux);
+        if (z.d_parsed) cudaFree(z.d_parsed);
+        z.h_aux = nullptr; z.d_aux = nullptr; z.d_parsed = nullptr;
+        z.blk_cap = 0;
+        const size_t cap = (size_t)n + n / 4 + 16;
+        CK(cudaMallocHost(&z.h_aux, cap * sizeof(ZstdFrameAux)));
+        CK(cudaMalloc(&z.d_aux, cap * sizeof(ZstdFrameAux)));
+        CK(cudaMalloc(&z.d_parsed, cap * sizeof(ZstdParsed)));
+        z.blk_cap = cap;
+    }
+    size_t descs = 0, lits = 0;
+    uint32_t max_raw = 0;
+    for (uint32_t b = 0; b < n; ++b) {
+        const uint64_t cnt = zstd::count_descriptors(h_comp + h_desc[b].comp_off, h_desc[b].comp_size, h_desc[b].raw_size);
+        const uint32_t lit_cap = h_desc[b].raw_size + zstd::kBlockMax + 64u;
+        z.h_aux[b] = ZstdFrameAux{descs, lits, (uint32_t)cnt, lit_cap};
+        descs += (size_t)cnt;
+        lits += ((size_t)lit_cap + 15u) & ~(size_t)15u;
+        if (h_desc[b].raw_size > max_raw) max_raw = h_desc[b].raw_size;
+    }
+    if (descs > z.desc_cap) {
+        if (z.d_descs) cudaFree(z.d_descs);
+        z.d_descs = nullptr;
+        z.desc_cap = 0;
+        const size_t cap = descs + descs / 4 + 1024;
+        CK(cudaMalloc(&z.d_descs, cap * sizeof(L4Desc)));
+        z.desc_cap = cap;
+    }
+    if (lits > z.lit_cap) {
+        if (z.d_lit) cudaFree(z.d_lit);
+        z.d_lit = nullptr;
+        z.lit_cap = 0;
+        const size_t cap = lits + lits / 8 + 4096;
+        CK(cudaMalloc(&z.d_lit, cap));
+        z.lit_cap = cap;
+    }
+    const unsigned grid = lz4_cta_grid(n, di->sms);
+    const uint32_t tf_stride = (max_raw + 15u) / kL4Tile + 8u;
+    if ((size_t)grid * tf_stride > z.tf_cap) {
+        if (z.d_tf) cudaFree(z.d_tf);
+        z.d_tf = nullptr;
+        z.tf_cap = 0;
+        const size_t cap = (size_t)2 * di->sms * tf_stride * 2;
+        CK(cudaMalloc(&z.d_tf, cap * sizeof(uint32_t)));
+        z.tf_cap = cap;
+    }
+    CK(cudaMemcpyAsync(z.d_aux, z.h_aux, n * sizeof(ZstdFrameAux), cudaMemcpyHostToDevice, st));
+    zstd_parse_kernel<<<(n + kZstdFramesPerCta - 1) / kZstdFramesPerCta, 32 * kZstdFramesPerCta, kZstdParseSmem, st>>>(
+        d_comp, d_desc, z.d_aux, n, z.d_lit, z.d_descs, z.d_parsed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    zstd_copy_kernel<<<grid, kL4Threads, kL4Smem, st>>>(d_raw, d_desc, z.d_aux, z.d_parsed, d_status, n, z.d_lit,
+                                                        z.d_descs, z.d_tf, tf_stride);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 struct BlockInfo {
     uint64_t src_off;  // payload position in the file / memory image
     uint32_t comp, raw;
@@ -223,7 +322,8 @@ struct Lz4Lane {
     Lz4BlockDesc* d_desc = nullptr;
     int* h_status = nullptr;           // pinned
     int* d_status = nullptr;
-    zstd::Work* d_work = nullptr;      // Zstd only: one workspace per block of the batch
+    zstd::Work* d_work = nullptr;      // Zstd, first version only: one workspace per block of the batch
+    Zstd2 z2;                          // Zstd (default): descriptors, literals, per-frame results
     Lz4Scratch scratch;                // LZ4 CTA decoder: descriptor scratch
     uint32_t max_comp = 0, max_raw = 0;  // largest block of the batch in flight
     size_t comp_cap = 0, raw_cap = 0;
@@ -244,6 +344,7 @@ void lz4_lane_free(Lz4Lane& l)
     if (l.h_status) cudaFreeHost(l.h_status);
     if (l.d_status) cudaFree(l.d_status);
     if (l.d_work) cudaFree(l.d_work);
+    zstd2_free(l.z2);
     if (l.scratch.d) cudaFree(l.scratch.d);
     if (l.st) cudaStreamDestroy(l.st);
     l = Lz4Lane();
@@ -252,7 +353,7 @@ void lz4_lane_free(Lz4Lane& l)
 int lz4_lane_reserve(Lz4Lane& l, size_t comp_bytes, size_t raw_bytes, int blocks, int codec)
 {
     if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
-    if (codec == kCodecZstd && blocks > l.work_cap) {
+    if (codec == kCodecZstd && zstd_variant() == 0 && blocks > l.work_cap) {
         if (l.d_work) cudaFree(l.d_work);
         l.d_work = nullptr;
         l.work_cap = 0;
@@ -321,7 +422,9 @@ int lz4_lane_ship(int mode, int codec, Lz4Lane& l, size_t comp_bytes, size_t raw
         CK(cudaEventRecord(dbg.e0, l.st));
     }
     int rc = codec == kCodecZstd
-                 ? zstd_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.d_work, l.st)
+                 ? (zstd_variant() == 0
+                        ? zstd_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.d_work, l.st)
+                        : zstd2_launch(l.z2, l.h_comp, l.h_desc, l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st))
                  : lz4_launch(l.d_comp, l.d_raw, l.d_desc, l.d_status, (uint32_t)l.n, l.st, l.scratch, l.max_comp,
                               l.max_raw);
     if (rc) return rc;
@@ -824,6 +927,7 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
     Lz4BlockDesc* d_desc = nullptr;
     int* d_status = nullptr;
     zstd::Work* d_work = nullptr;
+    Zstd2 z2;
     Lz4Scratch scratch;
     uint32_t max_comp = 0, max_raw = 0;
     for (uint32_t b = 0; b < n_blocks; ++b) {
@@ -839,7 +943,11 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
         if ((rc = (int)cudaMemcpy(d_comp, comp, comp_bytes, cudaMemcpyHostToDevice))) break;
         if ((rc = (int)cudaMemset(d_raw, 0, raw_total ? raw_total : 1))) break;
         if ((rc = (int)cudaMemcpy(d_desc, desc.data(), n_blocks * sizeof(Lz4BlockDesc), cudaMemcpyHostToDevice))) break;
-        if (codec == kCodecZstd) {
+        if (codec == kCodecZstd && zstd_variant() != 0) {
+            if ((rc = zstd2_launch(z2, static_cast<const unsigned char*>(comp), desc.data(), d_comp, d_raw, d_desc,
+                                   d_status, n_blocks, nullptr)))
+                break;
+        } else if (codec == kCodecZstd) {
             if ((rc = (int)cudaMalloc(&d_work, (size_t)n_blocks * sizeof(zstd::Work)))) break;
             if ((rc = zstd_launch(d_comp, d_raw, d_desc, d_status, n_blocks, d_work, nullptr))) break;
         } else if ((rc = lz4_launch(d_comp, d_raw, d_desc, d_status, n_blocks, nullptr, scratch, max_comp, max_raw))) {
@@ -853,6 +961,8 @@ static int decode_blocks(int codec, const void* comp, uint64_t comp_bytes, const
     cudaFree(d_desc);
     cudaFree(d_status);
     cudaFree(d_work);
+    if (rc == 0 || z2.h_aux) cudaDeviceSynchronize();  // (the aux upload is asynchronous: nothing may be in flight when it is freed)
+    zstd2_free(z2);
     cudaFree(scratch.d);
     return rc;
     });

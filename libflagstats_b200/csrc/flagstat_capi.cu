@@ -272,6 +272,11 @@ int device_info(int dev, DeviceInfo** out)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4GroupSmem));
         CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(lz4_decode_cta_kernel),
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
+        // ... and the two kernels of the Zstd decoder (zstd_block.cuh)
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(zstd_parse_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZstdParseSmem));
+        CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(zstd_copy_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
 #ifdef FSB_ALL_VARIANTS
         for (int c = 0; c < 2; ++c)
             for (int m = 0; m < 3; ++m) {

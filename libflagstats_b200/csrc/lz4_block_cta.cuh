@@ -573,11 +573,13 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
 }
 
 // Phase B for one block: nseq descriptors -> out[0, total).  Returns total or a negative error.
+// max_off: the largest offset the format allows (LZ4: 65535; the Zstd frames of zstd_block.cuh, whose
+// sequences come through here too: the frame).
 // (desc and tile_first were written by this CTA: no const / __restrict__, so that they are never read through
 // the non-coherent path, which may hold the previous block's lines)
 __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t* out, uint32_t total,
                        L4Desc* desc, uint32_t nseq, uint32_t* tile_first,
-                       uint8_t* ring, uint16_t* P, L4Shared* sh, L4Long* longs, L4Desc* dsm)
+                       uint8_t* ring, uint16_t* P, L4Shared* sh, L4Long* longs, L4Desc* dsm, uint32_t max_off)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // v-space: v = out_pos + ga, so that 16-byte chunks of the ring and of global memory line up
@@ -673,7 +675,7 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 }
             }
             if (ml == 0u) continue;
-            if (off == 0u || off > 0xFFFFu || off > m - ga) {
+            if (off == 0u || off > max_off || off > m - ga) {
                 atomicCAS(&sh->err, 0, -4);
                 break;
             }
@@ -809,7 +811,7 @@ lz4_decode_cta_kernel(const uint8_t* __restrict__ comp, uint8_t* raw, const Lz4B
             r = nseq;
             if (nseq >= 0)
                 r = l4_copy(comp + d.comp_off, d.comp_size, raw + d.raw_off, total, desc, (uint32_t)nseq, tile_first,
-                            ring, P, sh, longs, dsm);
+                            ring, P, sh, longs, dsm, 0xFFFFu);
         }
         __syncthreads();
         if (threadIdx.x == 0) status[b] = r;

@@ -9,10 +9,15 @@
 // weights), sequences (predefined / RLE / FSE / repeat tables, backward bitstream), repeat
 // offsets, sequence execution.  No dictionaries; the content checksum is skipped.
 //
-// First version, correctness first: ONE THREAD decodes one frame, start to end (the file has
-// ~1600 independent frames of 1,024,000 bytes, so a launch still keeps every SM busy; the
-// compressed bytes are what crosses PCIe).  All state lives in a per-frame workspace in
-// global memory; there is no allocation, no recursion and no unaligned multi-byte access.
+// Two ways to run it, one code path (the sequence loop hands every sequence to an EXECUTOR):
+//   * decode_frame: ONE THREAD decodes one frame start to end, the executor copies at once
+//     (first version; all state in a per-frame workspace in global memory);
+//   * parse_frame (second version, what the library runs): entropy decoding only -- one lane
+//     per frame, tables in shared memory, a 64-bit bit window in registers -- and the executor
+//     RECORDS every sequence as a 16-byte descriptor {output position, literal position,
+//     literal length, offset}; the copies are then done by a whole CTA per frame with the
+//     machinery of the LZ4 decoder (lz4_block_cta.cuh, l4_copy: parents + pointer jumping).
+// There is no allocation, no recursion and no unaligned multi-byte access.
 // The whole decoder is FSB_HD (__host__ __device__): tests/test_zstd_frame_host.py compiles
 // this very file with g++ and holds it to the real libzstd on the CPU; the GPU tests then only
 // have to show that the same code gives the same bytes on the device.  The host instantiation
@@ -50,15 +55,26 @@ struct HufTab {
     uint8_t sym[1 << kHufMaxBits];
     uint8_t len[1 << kHufMaxBits];
 };
-// per-frame workspace (global memory on the device)
-struct Work {
+// per-frame tables (second version: shared memory, one set per warp)
+struct Tables {
     FseTab ll, of, ml, wt;  // wt: the table of FSE-compressed Huffman weights
     HufTab huf;
     uint64_t rep[3];
     int16_t freq[256];
     uint16_t next[256];
     uint8_t w[260];
+};
+// per-frame workspace of the first version (global memory on the device)
+struct Work {
+    Tables t;
     uint8_t lit[kBlockMax + 32];
+};
+// what parse_frame writes per sequence (same layout as L4Desc of lz4_block_cta.cuh)
+struct SeqDesc {
+    uint32_t out_pos;  // first output byte of the sequence (its literals)
+    uint32_t lit_pos;  // position of its first literal byte in the frame's literal buffer
+    uint32_t lit;      // literal bytes; the match follows and ends where the next sequence starts
+    uint32_t off;      // match offset (0: literals only)
 };
 
 FSB_HD int highbit(uint32_t v)  // floor(log2(v)), v > 0
@@ -137,26 +153,42 @@ struct Fwd {
 };
 
 // backward stream: the last byte carries a 1 above the payload; reads walk towards byte 0
-// and bits "before" the stream are zeros
+// and bits "before" the stream are zeros.  Bits [wlo, wlo + 64) of the stream are kept in a
+// register window (eight byte loads per refill, every ~40 bits) so that the six reads of a
+// sequence are shifts, not memory round trips.
 struct Back {
     const uint8_t* p;
     int64_t pos;
+    int64_t wlo;   // bit index of the window's bit 0 (a multiple of 8); the window is empty if wlo > pos
+    uint64_t win;
     FSB_HD bool init(const uint8_t* q, uint64_t n)
     {
         if (n == 0 || q[n - 1] == 0) return false;
         p = q;
         pos = (int64_t)(n - 1) * 8 + highbit(q[n - 1]);
+        wlo = pos + 1;  // nothing loaded yet
+        win = 0;
         return true;
     }
     FSB_HD uint32_t read(int n)  // n <= 32
     {
         pos -= n;
         if (n == 0) return 0u;
+        if (pos >= wlo) {  // (reads only ever move down: pos + n <= wlo + 64 holds since the refill)
+            return (uint32_t)((win >> (pos - wlo)) & (((uint64_t)1 << n) - 1u));
+        }
         if (pos >= 0) {
-            // bits [pos, pos + n) lie inside bytes [pos >> 3, (pos + n - 1) >> 3], at most 5 of them,
-            // all below the end marker's byte
+            // refill so that the window ENDS with the byte that holds bit pos + n - 1 (all bytes below
+            // the end marker's byte, all inside the stream) and reaches 64 bits down from there
+            const int64_t top = (pos + n - 1) >> 3;  // last byte needed
+            if (top >= 7) {
+                wlo = (top - 7) * 8;
+                win = le(p + (top - 7), 8);
+                return (uint32_t)((win >> (pos - wlo)) & (((uint64_t)1 << n) - 1u));
+            }
+            // within the first bytes of the stream: bits [pos, pos + n) lie inside at most 5 bytes
             const int64_t b = pos >> 3;
-            const int nb = (int)(((pos + n - 1) >> 3) - b) + 1;
+            const int nb = (int)(top - b) + 1;
             const uint64_t v = le(p + b, nb) >> (pos & 7);
             return (uint32_t)(v & (((uint64_t)1 << n) - 1u));
         }
@@ -202,7 +234,7 @@ FSB_HDN int fse_build(FseTab& t, const int16_t* freq, int nsym, int log, uint16_
 }
 
 // table description -> table; returns bytes consumed or < 0
-FSB_HDN int64_t fse_read(FseTab& t, const uint8_t* p, uint64_t n, int max_log, int max_sym, Work& w)
+FSB_HDN int64_t fse_read(FseTab& t, const uint8_t* p, uint64_t n, int max_log, int max_sym, Tables& w)
 {
     Fwd b{p, n * 8, 0};
     const int log = 5 + (int)b.read(4);
@@ -273,7 +305,7 @@ FSB_HDN int huf_build(HufTab& h, uint8_t* wt, int n)  // wt[0..n-1] given, wt[n]
 }
 
 // tree description; returns bytes consumed or < 0
-FSB_HDN int64_t huf_read_tree(Work& w, const uint8_t* p, uint64_t n)
+FSB_HDN int64_t huf_read_tree(Tables& w, const uint8_t* p, uint64_t n)
 {
     if (n < 1) return kErrTrunc;
     const int hb = p[0];
@@ -356,7 +388,7 @@ FSB_HD int16_t of_default(int s) { return s <= 5 ? 1 : s <= 8 ? 2 : s <= 23 ? 1 
 
 // one of the three tables of a sequences section; which: 0 = LL, 1 = OF, 2 = ML.
 // Returns bytes consumed or < 0.
-FSB_HDN int64_t seq_table(FseTab& t, int mode, const uint8_t* p, uint64_t n, int which, Work& w)
+FSB_HDN int64_t seq_table(FseTab& t, int mode, const uint8_t* p, uint64_t n, int which, Tables& w)
 {
     const int def_n = which == 0 ? 36 : which == 1 ? 29 : 53;
     const int def_log = which == 1 ? 5 : 6;
@@ -380,8 +412,75 @@ FSB_HDN int64_t seq_table(FseTab& t, int mode, const uint8_t* p, uint64_t n, int
     return t.log < 0 ? kErrSeq : 0;  // repeat: the previous table must exist
 }
 
-// a compressed block: literals + sequences -> out[op..]; returns the new op or < 0
-FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t* out, uint64_t op, uint64_t cap)
+// ---- executors: what happens to a decoded sequence -----------------------------------------
+
+// first version: copy at once into out[op..]
+struct ExecCopy {
+    static constexpr bool kKeepLiterals = false;  // literals may be used where they lie (input, block buffer)
+    uint8_t* out;
+    uint64_t op, cap;
+    // ll literal bytes at lit, then a match of ml bytes from `off` back (ml == 0: literals only)
+    FSB_HD int seq(uint64_t ll, uint64_t ml, uint64_t off, const uint8_t* lit, uint64_t /*lit_pos*/)
+    {
+        if (ll > cap - op || ml > cap - op - ll) return kErrOut;
+        copy16(out + op, lit, ll);
+        op += ll;
+        if (ml) {
+            if (off == 0 || off > op) return kErrSeq;
+            copy_match(out + op, off, ml);
+            op += ml;
+        }
+        return 0;
+    }
+    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* /*litbuf*/, uint64_t /*lit_pos*/)  // an RLE block
+    {
+        if (n > cap - op) return kErrOut;
+        for (uint64_t k = 0; k < n; ++k) out[op + k] = v;
+        op += n;
+        return 0;
+    }
+};
+
+// second version: record the sequence; the copies are another kernel's business.  Every literal byte
+// of the frame ends up in ONE literal buffer (a literal byte is an output byte, so raw-size bytes
+// are enough), which is what the descriptors index.
+struct ExecRecord {
+    static constexpr bool kKeepLiterals = true;
+    SeqDesc* d;
+    uint32_t nd, cap_d;
+    uint64_t op, cap;
+    FSB_HD int seq(uint64_t ll, uint64_t ml, uint64_t off, const uint8_t* /*lit*/, uint64_t lit_pos)
+    {
+        if (ll > cap - op || ml > cap - op - ll) return kErrOut;
+        if (ll == 0 && ml == 0) return 0;
+        if (ml && (off == 0 || off > op + ll)) return kErrSeq;
+        if (nd && d[nd - 1u].off == 0u && (uint64_t)d[nd - 1u].lit_pos + d[nd - 1u].lit == lit_pos &&
+            (uint64_t)d[nd - 1u].out_pos + d[nd - 1u].lit == op) {
+            // the descriptor before was literals only (a block's tail, a raw block) and these literals follow
+            // them in the buffer: one descriptor.  Every descriptor but the last then carries a match of
+            // >= 3 bytes, so cap / 3 + 2 descriptors are always enough.
+            d[nd - 1u].lit += (uint32_t)ll;
+            d[nd - 1u].off = ml ? (uint32_t)off : 0u;
+        } else {
+            if (nd >= cap_d) return kErrOut;
+            d[nd++] = SeqDesc{(uint32_t)op, (uint32_t)lit_pos, (uint32_t)ll, ml ? (uint32_t)off : 0u};
+        }
+        op += ll + ml;
+        return 0;
+    }
+    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* litbuf, uint64_t lit_pos)  // an RLE block: one literal + a run
+    {
+        if (n == 0) return 0;
+        litbuf[0] = v;
+        return seq(1, n - 1, 1, litbuf, lit_pos);
+    }
+};
+
+// a compressed block: literals + sequences -> the executor; returns the literal bytes the block
+// regenerated (they start at litbuf[0] = literal position lit_pos of the frame) or < 0.
+// litbuf has room for kBlockMax + 32 bytes.
+template <class Exec>
+FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, const uint8_t* p, uint64_t n, Exec& ex)
 {
     // ---- literals section ----
     if (n < 1) return kErrTrunc;
@@ -395,13 +494,18 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
         if (regen > kBlockMax) return kErrLiterals;
         if (ltype == 0) {
             if (n < hdr + regen) return kErrTrunc;
-            lit = p + hdr;
+            if (Exec::kKeepLiterals) {
+                copy16(litbuf, p + hdr, regen);
+                lit = litbuf;
+            } else {
+                lit = p + hdr;
+            }
             comp = regen;
         } else {
             if (n < hdr + 1) return kErrTrunc;
             const uint8_t v = p[hdr];
-            for (uint64_t i = 0; i < regen; ++i) c.lit[i] = v;
-            lit = c.lit;
+            for (uint64_t i = 0; i < regen; ++i) litbuf[i] = v;
+            lit = litbuf;
             comp = 1;
         }
     } else {  // Huffman-compressed / treeless
@@ -440,7 +544,7 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
             return kErrHuf;  // treeless without a previous tree
         }
         if (streams == 1) {
-            const int rc = huf_stream(c.huf, q, left, c.lit, regen);
+            const int rc = huf_stream(c.huf, q, left, litbuf, regen);
             if (rc) return rc;
         } else {
             if (left < 6) return kErrLiterals;
@@ -450,12 +554,12 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
             const uint64_t each = (regen + 3) / 4;
             if (3 * each > regen) return kErrLiterals;
             int rc;
-            if ((rc = huf_stream(c.huf, q + 6, s1, c.lit, each))) return rc;
-            if ((rc = huf_stream(c.huf, q + 6 + s1, s2, c.lit + each, each))) return rc;
-            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2, s3, c.lit + 2 * each, each))) return rc;
-            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2 + s3, s4, c.lit + 3 * each, regen - 3 * each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6, s1, litbuf, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1, s2, litbuf + each, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2, s3, litbuf + 2 * each, each))) return rc;
+            if ((rc = huf_stream(c.huf, q + 6 + s1 + s2 + s3, s4, litbuf + 3 * each, regen - 3 * each))) return rc;
         }
-        lit = c.lit;
+        lit = litbuf;
     }
     p += hdr + comp;
     n -= hdr + comp;
@@ -483,6 +587,7 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
         Back b;
         if (!b.init(p, n)) return kErrSeq;
         uint32_t sl = b.read(c.ll.log), so = b.read(c.of.log), sm = b.read(c.ml.log);
+        uint64_t rep0 = c.rep[0], rep1 = c.rep[1], rep2 = c.rep[2];
         for (uint64_t i = 0; i < nseq; ++i) {
             const int oc = c.of.sym[so], mc = c.ml.sym[sm], lc = c.ll.sym[sl];
             if (oc > 31 || mc > 52 || lc > 35) return kErrSeq;
@@ -499,36 +604,42 @@ FSB_HDN int64_t block_compressed(Work& c, const uint8_t* p, uint64_t n, uint8_t*
             uint64_t off;
             if (ov > 3) {
                 off = ov - 3;
-                c.rep[2] = c.rep[1]; c.rep[1] = c.rep[0]; c.rep[0] = off;
+                rep2 = rep1; rep1 = rep0; rep0 = off;
             } else {
                 const uint64_t idx = ov - 1 + (ll == 0 ? 1 : 0);
                 if (idx == 0) {
-                    off = c.rep[0];
+                    off = rep0;
                 } else {
-                    off = idx < 3 ? c.rep[idx] : c.rep[0] - 1;
-                    if (idx > 1) c.rep[2] = c.rep[1];
-                    c.rep[1] = c.rep[0];
-                    c.rep[0] = off;
+                    off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+                    if (idx > 1) rep2 = rep1;
+                    rep1 = rep0;
+                    rep0 = off;
                 }
             }
             // execute: literals, then the match (which may overlap its own output)
-            if (ll > regen - lp || ll + ml > cap - op) return kErrOut;
-            copy16(out + op, lit + lp, ll);
-            op += ll;
+            if (ll > regen - lp) return kErrOut;
+            if (off == 0) return kErrSeq;
+            const int rc = ex.seq(ll, ml, off, lit + lp, lit_pos + lp);
+            if (rc) return rc;
             lp += ll;
-            if (off == 0 || off > op) return kErrSeq;
-            copy_match(out + op, off, ml);
-            op += ml;
         }
+        c.rep[0] = rep0; c.rep[1] = rep1; c.rep[2] = rep2;
         if (b.pos != 0) return kErrSeq;
     }
-    if (regen - lp > cap - op) return kErrOut;
-    copy16(out + op, lit + lp, regen - lp);
-    return (int64_t)(op + (regen - lp));
+    {
+        const int rc = ex.seq(regen - lp, 0, 0, lit + lp, lit_pos + lp);
+        if (rc) return rc;
+    }
+    return (int64_t)regen;
 }
 
-// One frame; returns bytes produced or < 0.  `w` is scratch, its contents on entry do not matter.
-FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, Work& w)
+// One frame through an executor; returns the output bytes (ex.op) or < 0.  c: tables, contents on
+// entry do not matter.  lit / lit_cap: literal buffer -- for ExecCopy one block's worth
+// (kBlockMax + 32, reused by every block), for ExecRecord the whole frame's (>= cap + 32: every
+// literal byte is an output byte).
+template <class Exec>
+FSB_HDN int64_t run_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& c, uint8_t* lit, uint64_t lit_cap, Exec& ex,
+                          uint64_t* lit_used)
 {
     if (n < 6) return kErrTrunc;
     if (le(in, 4) != 0xFD2FB528u) return kErrMagic;
@@ -550,35 +661,42 @@ FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64
     ip += (uint64_t)fcs_bytes;
     if (fcs_bytes && fcs > cap) return kErrOut;
 
-    w.ll.log = w.of.log = w.ml.log = w.wt.log = -1;
-    w.huf.bits = 0;
-    w.rep[0] = 1; w.rep[1] = 4; w.rep[2] = 8;
-    uint64_t op = 0;
+    c.ll.log = c.of.log = c.ml.log = c.wt.log = -1;
+    c.huf.bits = 0;
+    c.rep[0] = 1; c.rep[1] = 4; c.rep[2] = 8;
+    uint64_t lpos = 0;  // literal bytes kept so far (ExecRecord); ExecCopy reuses the buffer
     for (;;) {
         if (n < ip + 3) return kErrTrunc;
         const uint32_t bh = (uint32_t)le(in + ip, 3);
         ip += 3;
         const int last = (int)(bh & 1u), type = (int)((bh >> 1) & 3u);
         const uint64_t size = bh >> 3;
+        if (Exec::kKeepLiterals && lit_cap - lpos < kBlockMax + 32u) return kErrOut;  // (cannot happen with lit_cap >= cap + block)
+        uint8_t* lb = Exec::kKeepLiterals ? lit + lpos : lit;
         if (type == 0) {
             if (n < ip + size) return kErrTrunc;
-            if (size > cap - op) return kErrOut;
-            copy16(out + op, in + ip, size);
-            op += size;
+            if (size > cap - ex.op) return kErrOut;  // (hence size <= lit_cap - lpos: a literal byte is an output byte)
+            const uint8_t* src = in + ip;
+            if (Exec::kKeepLiterals) {
+                copy16(lb, src, size);
+                src = lb;
+            }
+            const int rc = ex.seq(size, 0, 0, src, lpos);
+            if (rc) return rc;
+            if (Exec::kKeepLiterals) lpos += size;
             ip += size;
         } else if (type == 1) {
             if (n < ip + 1) return kErrTrunc;
-            if (size > cap - op) return kErrOut;
-            const uint8_t v = in[ip];
-            for (uint64_t k = 0; k < size; ++k) out[op + k] = v;
-            op += size;
+            const int rc = ex.fill(in[ip], size, lb, lpos);
+            if (rc) return rc;
+            if (Exec::kKeepLiterals && size) lpos += 1;
             ip += 1;
         } else if (type == 2) {
             if (size > kBlockMax) return kErrBlock;
             if (n < ip + size) return kErrTrunc;
-            const int64_t r = block_compressed(w, in + ip, size, out, op, cap);
+            const int64_t r = block_compressed(c, lb, lpos, in + ip, size, ex);
             if (r < 0) return r;
-            op = (uint64_t)r;
+            if (Exec::kKeepLiterals) lpos += (uint64_t)r;
             ip += size;
         } else {
             return kErrBlock;
@@ -589,8 +707,105 @@ FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64
         if (n < ip + 4) return kErrTrunc;
         ip += 4;  // xxh64 of the content, low 32 bits: not verified
     }
-    if (fcs_bytes && fcs != op) return kErrOut;
-    return (int64_t)op;
+    if (fcs_bytes && fcs != ex.op) return kErrOut;
+    if (lit_used) *lit_used = lpos;
+    return (int64_t)ex.op;
+}
+
+// First version.  One frame; returns bytes produced or < 0.  `w` is scratch, its contents on entry do not matter.
+FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, Work& w)
+{
+    ExecCopy ex{out, 0, cap};
+    return run_frame(in, n, cap, w.t, w.lit, sizeof(w.lit), ex, nullptr);
+}
+
+// Second version, entropy stage.  One frame -> descriptors d[0, *nd) (at most cap_d) and the frame's
+// literal bytes lit[0, *lit_used) (lit_cap >= cap + kBlockMax + 64); returns the bytes the descriptors
+// produce or < 0.
+FSB_HDN int64_t parse_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& t, uint8_t* lit, uint64_t lit_cap,
+                            SeqDesc* d, uint32_t cap_d, uint32_t* nd, uint64_t* lit_used)
+{
+    ExecRecord ex{d, 0u, cap_d, 0, cap};
+    const int64_t r = run_frame(in, n, cap, t, lit, lit_cap, ex, lit_used);
+    *nd = ex.nd;
+    return r;
+}
+
+// How many descriptors parse_frame can write for this frame, from the block headers alone (no entropy
+// decoding: frame header, block headers, literals-section and sequences-section headers): the sum of the
+// blocks' sequence counts + one literals-only descriptor per block + 2.  The library sizes each frame's slice
+// of the descriptor scratch with it (the worst case, cap / 3 + 2, is 5.5 MB for a 1,024,000-byte frame of
+// which FLAG data uses a seventh).  Anything odd in the headers: the worst case, and parse_frame reports it.
+FSB_HDN uint64_t count_descriptors(const uint8_t* in, uint64_t n, uint64_t cap)
+{
+    const uint64_t worst = cap / 3u + 2u;
+    if (n < 6 || le(in, 4) != 0xFD2FB528u) return worst;
+    const int fhd = in[4];
+    const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, dict = fhd & 3;
+    uint64_t ip = 5 + (single ? 0 : 1) + (uint64_t)(dict == 3 ? 4 : dict);
+    ip += (uint64_t)(fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8);
+    uint64_t total = 2;
+    for (;;) {
+        if (n < ip + 3) return worst;
+        const uint32_t bh = (uint32_t)le(in + ip, 3);
+        ip += 3;
+        const int last = (int)(bh & 1u), type = (int)((bh >> 1) & 3u);
+        const uint64_t size = bh >> 3;
+        if (type == 3) return worst;
+        total += 1;
+        if (type == 1) {
+            ip += 1;
+        } else {
+            if (n < ip + size) return worst;
+            if (type == 2) {
+                const uint8_t* p = in + ip;
+                if (size < 1) return worst;
+                const int ltype = p[0] & 3, sf = (p[0] >> 2) & 3;
+                uint64_t hdr, comp;
+                if (ltype < 2) {
+                    uint64_t regen;
+                    if (sf == 0 || sf == 2) { hdr = 1; regen = p[0] >> 3; }
+                    else if (sf == 1) { if (size < 2) return worst; hdr = 2; regen = le(p, 2) >> 4; }
+                    else { if (size < 3) return worst; hdr = 3; regen = le(p, 3) >> 4; }
+                    comp = ltype == 0 ? regen : 1;
+                } else {
+                    if (sf == 0 || sf == 1) { if (size < 3) return worst; hdr = 3; comp = (le(p, 3) >> 14) & 0x3FF; }
+                    else if (sf == 2) { if (size < 4) return worst; hdr = 4; comp = (le(p, 4) >> 18) & 0x3FFF; }
+                    else { if (size < 5) return worst; hdr = 5; comp = (le(p, 5) >> 22) & 0x3FFFF; }
+                }
+                if (size < hdr + comp + 1) return worst;
+                const uint8_t* q = p + hdr + comp;
+                const uint64_t left = size - hdr - comp;
+                uint64_t nseq;
+                if (q[0] < 128) nseq = q[0];
+                else if (q[0] < 255) { if (left < 2) return worst; nseq = ((uint64_t)(q[0] - 128) << 8) + q[1]; }
+                else { if (left < 3) return worst; nseq = (uint64_t)q[1] + ((uint64_t)q[2] << 8) + 0x7F00; }
+                total += nseq;
+            }
+            ip += size;
+        }
+        if (total >= worst) return worst;
+        if (last) break;
+    }
+    return total;
+}
+
+// What the copy stage does, sequentially (host tests; the device runs l4_copy of lz4_block_cta.cuh over
+// the same descriptors): out[0, total) from descriptors and literals.  Returns total or < 0.
+FSB_HDN int64_t apply_descriptors(const SeqDesc* d, uint32_t nd, const uint8_t* lit, uint64_t lit_used, uint8_t* out,
+                                  uint64_t total)
+{
+    for (uint32_t k = 0; k < nd; ++k) {
+        const uint64_t o = d[k].out_pos, oe = k + 1u < nd ? d[k + 1u].out_pos : total;
+        if (oe < o || oe > total || d[k].lit > oe - o || (uint64_t)d[k].lit_pos + d[k].lit > lit_used) return kErrOut;
+        copy16(out + o, lit + d[k].lit_pos, d[k].lit);
+        const uint64_t m = o + d[k].lit, ml = oe - m;
+        if (ml) {
+            if (d[k].off == 0 || d[k].off > m) return kErrSeq;
+            copy_match(out + m, d[k].off, ml);
+        }
+    }
+    return (int64_t)total;
 }
 
 }  // namespace zstd

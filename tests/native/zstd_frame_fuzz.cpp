@@ -63,6 +63,25 @@ int main()
                 CHECK(o);
                 const int64_t got = fsb200::zstd::decode_frame(f, cut, o, ocap, *w);
                 CHECK(got <= (int64_t)ocap);
+                {   // second version: exact-size literal buffer and descriptor array, same verdict, same bytes
+                    using namespace fsb200::zstd;
+                    const uint64_t lit_cap = ocap + kBlockMax + 64;
+                    const uint32_t cap_d = (uint32_t)count_descriptors(f, cut, ocap);
+                    uint8_t* lit = (uint8_t*)std::malloc(lit_cap);
+                    SeqDesc* d = (SeqDesc*)std::malloc(sizeof(SeqDesc) * cap_d);
+                    uint8_t* o2 = (uint8_t*)std::malloc(ocap ? ocap : 1);
+                    CHECK(lit && d && o2);
+                    uint32_t nd = 0;
+                    uint64_t lit_used = 0;
+                    int64_t got2 = parse_frame(f, cut, ocap, w->t, lit, lit_cap, d, cap_d, &nd, &lit_used);
+                    CHECK(nd <= cap_d && lit_used <= lit_cap);
+                    if (got2 >= 0) got2 = apply_descriptors(d, nd, lit, lit_used, o2, (uint64_t)got2);
+                    CHECK((got2 < 0) == (got < 0));
+                    if (got >= 0) CHECK(got2 == got && std::memcmp(o, o2, (size_t)got) == 0);
+                    std::free(o2);
+                    std::free(d);
+                    std::free(lit);
+                }
                 std::free(o);
                 std::free(f);
             }

@@ -242,8 +242,17 @@ def _zstd_columns():
 needs_libzstd = pytest.mark.skipif(O.libzstd() is None, reason="no libzstd.so.1 to write the frames with")
 
 
+@pytest.fixture(params=["two-stage (default)", "one thread per frame"])
+def zstd_variant(request, monkeypatch):
+    """Both Zstd decoders of the library: entropy stage + the LZ4 copy phase (default), and the first
+    version (one thread decodes a frame start to end), kept for A/B behind FLAGSTAT_CUDA_ZSTD_VARIANT=0."""
+    if request.param != "two-stage (default)":
+        monkeypatch.setenv("FLAGSTAT_CUDA_ZSTD_VARIANT", "0")
+    return request.param
+
+
 @needs_libzstd
-def test_gpu_zstd_decode_matches_original(cuda_lib):
+def test_gpu_zstd_decode_matches_original(cuda_lib, zstd_variant):
     """Frames written by the real libzstd at the levels of the reference's table
     (README.md:148-175) decode on the GPU to the original bytes (the same source file is held to
     libzstd on the CPU in tests/test_zstd_frame_host.py)."""
@@ -260,7 +269,7 @@ def test_gpu_zstd_decode_matches_original(cuda_lib):
 
 
 @needs_libzstd
-def test_gpu_zstd_decode_rejects_malformed_frames(cuda_lib):
+def test_gpu_zstd_decode_rejects_malformed_frames(cuda_lib, zstd_variant):
     from libflagstats_b200 import blockfile
     raw = O.synth_hiseqx(0, 100_000, 1, 0).tobytes()
     good = O.libzstd_compress(raw, 3)
@@ -287,7 +296,7 @@ def test_gpu_zstd_decode_rejects_malformed_frames(cuda_lib):
 
 @needs_libzstd
 @pytest.mark.parametrize("level,batch", [(1, None), (19, None), (3, "2")])
-def test_zstd_container_counts_match_the_column(cuda_lib, level, batch, monkeypatch, tmp_path):
+def test_zstd_container_counts_match_the_column(cuda_lib, level, batch, monkeypatch, tmp_path, zstd_variant):
     """zstd_decompress() of the reference (benchmark/flagstats.cpp:636-676) on the GPU: container
     in memory and on disk, plain and samtools counters, several batches."""
     from libflagstats_b200 import blockfile
@@ -313,6 +322,51 @@ def test_zstd_container_counts_match_the_column(cuda_lib, level, batch, monkeypa
     with pytest.raises(cuda_lib.FlagstatCudaError):
         blockfile.flagstat_container(bytes(bad), blockfile.ZSTD, flags=f)
     assert f.tolist() == [7] * 32
+
+
+@needs_libzstd
+def test_gpu_zstd_far_offsets_odd_sizes_and_packed_outputs(cuda_lib, zstd_variant):
+    """What the LZ4 copy phase never saw before it was given Zstd sequences: offsets beyond 64 KiB (a long
+    period: the source lies outside the shared-memory history ring), matches of 3 bytes, long literal runs
+    (noise), frames of odd length packed back to back so that the output bases are unaligned."""
+    from libflagstats_b200 import blockfile
+    rng = np.random.default_rng(21)
+    noise = rng.integers(0, 256, 150_000, dtype=np.uint8).tobytes()
+    period = rng.integers(0, 256, 70_001, dtype=np.uint8).tobytes()       # repeats at a distance > 65535
+    raws = [
+        period * 9 + period[:12_345],
+        noise + noise[:100_000] + noise[37:90_000],                         # far matches inside noise
+        bytes(rng.integers(0, 3, 333_333, dtype=np.uint8)),                 # very short matches, Huffman literals
+        (b"abc" * 50_000)[:149_999],
+        O.synth_hiseqx(0, 400_001, 3, 777).tobytes()[:-1],                  # odd length
+        b"x",
+        noise[:131_073],                                                    # raw blocks, one byte into the second
+    ]
+    frames = [O.libzstd_compress(r, lvl) for r, lvl in zip(raws, (3, 19, 1, 5, 1, 1, 1))]
+    out, status = blockfile.zstd_decode(frames, [len(r) for r in raws])
+    assert status == [len(r) for r in raws]
+    assert all(o == r for o, r in zip(out, raws))
+    # the same frames packed back to back: no alignment of either side
+    import ctypes as C
+
+    from libflagstats_b200 import _capi
+    nb = len(raws)
+    comp_off = np.zeros(nb, np.uint64); raw_off = np.zeros(nb, np.uint64)
+    c = r = 0
+    for i in range(nb):
+        comp_off[i] = c; c += len(frames[i])
+        raw_off[i] = r; r += len(raws[i])
+    comp = np.frombuffer(b"".join(frames), np.uint8).copy()
+    raw = np.zeros(r, np.uint8)
+    st = np.zeros(nb, np.int32)
+    comp_size = np.array([len(x) for x in frames], np.uint32)
+    raw_size = np.array([len(x) for x in raws], np.uint32)
+    cuda_lib.check(cuda_lib.lib().FLAGSTAT_cuda_zstd_decode(
+        comp.ctypes.data, c, comp_off.ctypes.data_as(_capi.u64p), comp_size.ctypes.data_as(_capi.u32p),
+        raw_off.ctypes.data_as(_capi.u64p), raw_size.ctypes.data_as(_capi.u32p), nb, raw.ctypes.data, r,
+        st.ctypes.data_as(C.POINTER(C.c_int))), "zstd_decode")
+    assert st.tolist() == [len(x) for x in raws]
+    assert raw.tobytes() == b"".join(raws)
 
 
 def test_lz4_container_on_a_second_device_after_the_first(cuda_lib):

@@ -27,17 +27,28 @@ def host(tmp_path_factory):
            os.path.join(ROOT, "tests", "native", "zstd_frame_host.cpp"), "-o", str(so)]
     subprocess.check_call(cmd)
     lib = C.CDLL(str(so))
-    lib.zstd_frame_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
-    lib.zstd_frame_host.restype = C.c_int64
+    for name in ("zstd_frame_host", "zstd_frame_host_v2"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        getattr(lib, name).restype = C.c_int64
     lib.zstd_frame_work_bytes.restype = C.c_uint64
+    lib.zstd_frame_tables_bytes.restype = C.c_uint64
     return lib
 
 
 def _decode(lib, frame: bytes, cap: int):
+    """Both versions of the product decoder: decode_frame (one thread copies as it goes) and parse_frame +
+    apply_descriptors (entropy stage into descriptors, what the library runs on the device with the copies
+    done by l4_copy).  They must agree with each other on every input; the first one's result is returned."""
     src = (C.c_ubyte * max(len(frame), 1)).from_buffer_copy(frame or b"\0")
     dst = (C.c_ubyte * max(cap, 1))()
     r = lib.zstd_frame_host(src, len(frame), dst, cap)
-    return r, bytes(dst[: max(r, 0)])
+    out = bytes(dst[: max(r, 0)])
+    dst2 = (C.c_ubyte * max(cap, 1))()
+    r2 = lib.zstd_frame_host_v2(src, len(frame), dst2, cap)
+    assert (r2 < 0) == (r < 0), (r, r2)
+    if r >= 0:
+        assert r2 == r and bytes(dst2[:r]) == out
+    return r, out
 
 
 def _columns():
@@ -56,6 +67,8 @@ def _columns():
 
 def test_workspace_is_what_the_library_allocates_per_frame(host):
     assert 130_000 < host.zstd_frame_work_bytes() < 160_000
+    # second version: the tables of one frame live in shared memory, sixteen frames per SM
+    assert host.zstd_frame_tables_bytes() * 16 <= 227 * 1024
 
 
 @pytest.mark.parametrize("name,col", list(_columns()))
