@@ -449,22 +449,30 @@ struct ExecRecord {
     SeqDesc* d;
     uint32_t nd, cap_d;
     uint64_t op, cap;
+    // the last descriptor, if it is literals only: kept HERE, not read back from d[] (on the device that
+    // read was a global-memory round trip per sequence -- 1700 cycles of a 1900-cycle sequence)
+    bool open = false;
+    uint32_t open_lit = 0;      // its literal bytes so far
+    uint64_t open_lit_end = 0;  // position behind them in the literal buffer
     FSB_HD int seq(uint64_t ll, uint64_t ml, uint64_t off, const uint8_t* /*lit*/, uint64_t lit_pos)
     {
         if (ll > cap - op || ml > cap - op - ll) return kErrOut;
         if (ll == 0 && ml == 0) return 0;
         if (ml && (off == 0 || off > op + ll)) return kErrSeq;
-        if (nd && d[nd - 1u].off == 0u && (uint64_t)d[nd - 1u].lit_pos + d[nd - 1u].lit == lit_pos &&
-            (uint64_t)d[nd - 1u].out_pos + d[nd - 1u].lit == op) {
-            // the descriptor before was literals only (a block's tail, a raw block) and these literals follow
-            // them in the buffer: one descriptor.  Every descriptor but the last then carries a match of
-            // >= 3 bytes, so cap / 3 + 2 descriptors are always enough.
-            d[nd - 1u].lit += (uint32_t)ll;
+        if (open && open_lit_end == lit_pos) {
+            // the descriptor before was literals only (a block's tail, a raw block; it ends at op by
+            // construction) and these literals follow them in the buffer: one descriptor.  Every descriptor
+            // but the last then carries a match of >= 3 bytes, so cap / 3 + 2 descriptors are always enough.
+            open_lit += (uint32_t)ll;
+            d[nd - 1u].lit = open_lit;
             d[nd - 1u].off = ml ? (uint32_t)off : 0u;
         } else {
             if (nd >= cap_d) return kErrOut;
             d[nd++] = SeqDesc{(uint32_t)op, (uint32_t)lit_pos, (uint32_t)ll, ml ? (uint32_t)off : 0u};
+            open_lit = (uint32_t)ll;
         }
+        open = ml == 0;
+        open_lit_end = lit_pos + ll;
         op += ll + ml;
         return 0;
     }
@@ -725,7 +733,8 @@ FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64
 FSB_HDN int64_t parse_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& t, uint8_t* lit, uint64_t lit_cap,
                             SeqDesc* d, uint32_t cap_d, uint32_t* nd, uint64_t* lit_used)
 {
-    ExecRecord ex{d, 0u, cap_d, 0, cap};
+    ExecRecord ex;
+    ex.d = d; ex.nd = 0u; ex.cap_d = cap_d; ex.op = 0; ex.cap = cap;
     const int64_t r = run_frame(in, n, cap, t, lit, lit_cap, ex, lit_used);
     *nd = ex.nd;
     return r;
