@@ -55,9 +55,20 @@ struct HufTab {
     uint8_t sym[1 << kHufMaxBits];
     uint8_t len[1 << kHufMaxBits];
 };
+// One state of a sequence table (LL / OF / ML), everything the sequence loop needs in one 8-byte load:
+// bits 0-31 the base VALUE of the state's symbol (literal length, match length, 1 << offset code), 32-39
+// the symbol's extra bits, 40-47 the bits to read for the next state, 48-63 the next state's base.
+// Symbols are validated when the table is packed, not per sequence.
+template <int MAXLOG>
+struct SeqTab {
+    int log;  // accuracy log; -1 = no table yet
+    uint64_t st[1 << MAXLOG];
+};
 // per-frame tables (second version: shared memory, one set per warp)
 struct Tables {
-    FseTab ll, of, ml, wt;  // wt: the table of FSE-compressed Huffman weights
+    SeqTab<9> ll, ml;  // accuracy logs <= 9 (LL, ML), <= 8 (OF): RFC 8878 3.1.1.3.2.1
+    SeqTab<8> of;
+    FseTab wt;  // FSE-compressed Huffman weights; also where a sequence table is built before it is packed
     HufTab huf;
     uint64_t rep[3];
     int16_t freq[256];
@@ -386,30 +397,45 @@ FSB_HD int16_t ll_default(int s)
 FSB_HD int16_t ml_default(int s) { return s == 0 ? 1 : s == 1 ? 4 : s == 2 ? 3 : s <= 8 ? 2 : s <= 45 ? 1 : -1; }
 FSB_HD int16_t of_default(int s) { return s <= 5 ? 1 : s <= 8 ? 2 : s <= 23 ? 1 : -1; }
 
-// one of the three tables of a sequences section; which: 0 = LL, 1 = OF, 2 = ML.
-// Returns bytes consumed or < 0.
-FSB_HDN int64_t seq_table(FseTab& t, int mode, const uint8_t* p, uint64_t n, int which, Tables& w)
+// one of the three tables of a sequences section; which: 0 = LL, 1 = OF, 2 = ML.  The FSE table is
+// built in w.wt (free at this point: the literals are done) and packed into t.  Returns bytes consumed or < 0.
+template <class Tab>
+FSB_HDN int64_t seq_table(Tab& t, int mode, const uint8_t* p, uint64_t n, int which, Tables& w)
 {
     const int def_n = which == 0 ? 36 : which == 1 ? 29 : 53;
     const int def_log = which == 1 ? 5 : 6;
     const int max_log = which == 1 ? 8 : 9;
     const int max_sym = which == 0 ? 35 : which == 1 ? 31 : 52;
+    int64_t used = 0;
+    FseTab& f = w.wt;
     if (mode == 0) {
         for (int s = 0; s < def_n; ++s) w.freq[s] = which == 0 ? ll_default(s) : which == 1 ? of_default(s) : ml_default(s);
-        const int rc = fse_build(t, w.freq, def_n, def_log, w.next);
-        return rc ? rc : 0;
-    }
-    if (mode == 1) {
+        const int rc = fse_build(f, w.freq, def_n, def_log, w.next);
+        if (rc) return rc;
+    } else if (mode == 1) {
         if (n < 1) return kErrTrunc;
         if (p[0] > max_sym) return kErrSeq;
-        t.log = 0;
-        t.sym[0] = p[0];
-        t.nbits[0] = 0;
-        t.base[0] = 0;
-        return 1;
+        f.log = 0;
+        f.sym[0] = p[0];
+        f.nbits[0] = 0;
+        f.base[0] = 0;
+        used = 1;
+    } else if (mode == 2) {
+        used = fse_read(f, p, n, max_log, max_sym, w);
+        if (used < 0) return used;
+    } else {
+        return t.log < 0 ? kErrSeq : 0;  // repeat: the previous table must exist
     }
-    if (mode == 2) return fse_read(t, p, n, max_log, max_sym, w);
-    return t.log < 0 ? kErrSeq : 0;  // repeat: the previous table must exist
+    const int size = 1 << f.log;
+    for (int i = 0; i < size; ++i) {
+        const int c = f.sym[i];
+        if (c > max_sym) return kErrSeq;
+        const uint32_t value = which == 0 ? ll_base(c) : which == 1 ? (uint32_t)1 << c : ml_base(c);
+        const uint32_t extra = (uint32_t)(which == 0 ? ll_bits(c) : which == 1 ? c : ml_bits(c));
+        t.st[i] = (uint64_t)value | ((uint64_t)extra << 32) | ((uint64_t)f.nbits[i] << 40) | ((uint64_t)f.base[i] << 48);
+    }
+    t.log = f.log;
+    return used;
 }
 
 // ---- executors: what happens to a decoded sequence -----------------------------------------
@@ -597,15 +623,14 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, c
         uint32_t sl = b.read(c.ll.log), so = b.read(c.of.log), sm = b.read(c.ml.log);
         uint64_t rep0 = c.rep[0], rep1 = c.rep[1], rep2 = c.rep[2];
         for (uint64_t i = 0; i < nseq; ++i) {
-            const int oc = c.of.sym[so], mc = c.ml.sym[sm], lc = c.ll.sym[sl];
-            if (oc > 31 || mc > 52 || lc > 35) return kErrSeq;
-            const uint64_t ov = ((uint64_t)1 << oc) + b.read(oc);
-            const uint64_t ml = ml_base(mc) + b.read(ml_bits(mc));
-            const uint64_t ll = ll_base(lc) + b.read(ll_bits(lc));
+            const uint64_t eo = c.of.st[so], em = c.ml.st[sm], el = c.ll.st[sl];
+            const uint64_t ov = (uint64_t)(uint32_t)eo + b.read((int)((eo >> 32) & 0xFF));
+            const uint64_t ml = (uint64_t)(uint32_t)em + b.read((int)((em >> 32) & 0xFF));
+            const uint64_t ll = (uint64_t)(uint32_t)el + b.read((int)((el >> 32) & 0xFF));
             if (i + 1 < nseq) {
-                sl = c.ll.base[sl] + b.read(c.ll.nbits[sl]);
-                sm = c.ml.base[sm] + b.read(c.ml.nbits[sm]);
-                so = c.of.base[so] + b.read(c.of.nbits[so]);
+                sl = (uint32_t)(el >> 48) + b.read((int)((el >> 40) & 0xFF));
+                sm = (uint32_t)(em >> 48) + b.read((int)((em >> 40) & 0xFF));
+                so = (uint32_t)(eo >> 48) + b.read((int)((eo >> 40) & 0xFF));
             }
             if (b.pos < 0) return kErrSeq;
             // repeat offsets, RFC 8878 3.1.1.5
