@@ -166,17 +166,19 @@ struct Fwd {
 // backward stream: the last byte carries a 1 above the payload; reads walk towards byte 0
 // and bits "before" the stream are zeros.  Bits [wlo, wlo + 64) of the stream are kept in a
 // register window (eight byte loads per refill, every ~40 bits) so that the six reads of a
-// sequence are shifts, not memory round trips.
+// sequence are a compare, a shift and a mask each; everything else (refill, the first bytes of
+// the stream, reads that run off its start) is ONE out-of-line function, which keeps the
+// sequence loop small enough to stay in the instruction cache with a frame per warp.
 struct Back {
     const uint8_t* p;
-    int64_t pos;
-    int64_t wlo;   // bit index of the window's bit 0 (a multiple of 8); the window is empty if wlo > pos
+    int32_t pos;
+    int32_t wlo;   // bit index of the window's bit 0 (a multiple of 8); the window is empty if wlo > pos
     uint64_t win;
     FSB_HD bool init(const uint8_t* q, uint64_t n)
     {
-        if (n == 0 || q[n - 1] == 0) return false;
+        if (n == 0 || n > ((uint64_t)1 << 27) || q[n - 1] == 0) return false;  // (streams live inside 128 KiB blocks)
         p = q;
-        pos = (int64_t)(n - 1) * 8 + highbit(q[n - 1]);
+        pos = (int32_t)(n - 1) * 8 + highbit(q[n - 1]);
         wlo = pos + 1;  // nothing loaded yet
         win = 0;
         return true;
@@ -184,28 +186,31 @@ struct Back {
     FSB_HD uint32_t read(int n)  // n <= 32
     {
         pos -= n;
+        // (reads only ever move down: pos + n <= wlo + 64 holds since the refill)
+        if (pos >= wlo) return (uint32_t)(win >> (pos - wlo)) & (uint32_t)(((uint64_t)1 << n) - 1u);
+        return slow(n);
+    }
+    FSB_HDN uint32_t slow(int n)  // pos has been moved already
+    {
         if (n == 0) return 0u;
-        if (pos >= wlo) {  // (reads only ever move down: pos + n <= wlo + 64 holds since the refill)
-            return (uint32_t)((win >> (pos - wlo)) & (((uint64_t)1 << n) - 1u));
-        }
+        const uint32_t mask = (uint32_t)(((uint64_t)1 << n) - 1u);
         if (pos >= 0) {
             // refill so that the window ENDS with the byte that holds bit pos + n - 1 (all bytes below
             // the end marker's byte, all inside the stream) and reaches 64 bits down from there
-            const int64_t top = (pos + n - 1) >> 3;  // last byte needed
+            const int32_t top = (pos + n - 1) >> 3;  // last byte needed
             if (top >= 7) {
                 wlo = (top - 7) * 8;
                 win = le(p + (top - 7), 8);
-                return (uint32_t)((win >> (pos - wlo)) & (((uint64_t)1 << n) - 1u));
+                return (uint32_t)(win >> (pos - wlo)) & mask;
             }
             // within the first bytes of the stream: bits [pos, pos + n) lie inside at most 5 bytes
-            const int64_t b = pos >> 3;
+            const int32_t b = pos >> 3;
             const int nb = (int)(top - b) + 1;
-            const uint64_t v = le(p + b, nb) >> (pos & 7);
-            return (uint32_t)(v & (((uint64_t)1 << n) - 1u));
+            return (uint32_t)(le(p + b, nb) >> (pos & 7)) & mask;
         }
         uint32_t v = 0;
         for (int i = 0; i < n; ++i) {
-            const int64_t q = pos + i;
+            const int32_t q = pos + i;
             if (q >= 0) v |= (uint32_t)((p[q >> 3] >> (q & 7)) & 1u) << i;
         }
         return v;
