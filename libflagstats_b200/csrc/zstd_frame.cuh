@@ -187,7 +187,16 @@ struct Back {
     {
         pos -= n;
         // (reads only ever move down: pos + n <= wlo + 64 holds since the refill)
-        if (pos >= wlo) return (uint32_t)(win >> (pos - wlo)) & (uint32_t)(((uint64_t)1 << n) - 1u);
+        const uint32_t mask = (uint32_t)(((uint64_t)1 << n) - 1u);
+        if (pos >= wlo) return (uint32_t)(win >> (pos - wlo)) & mask;
+        if (pos >= 56) {  // the usual refill, in line: the window ends with the byte that holds bit pos + n - 1
+            const int32_t top = (pos + (n ? n - 1 : 0)) >> 3;  // >= 7
+            wlo = (top - 7) * 8;
+            const uint8_t* q = p + (top - 7);
+            win = (uint64_t)q[0] | ((uint64_t)q[1] << 8) | ((uint64_t)q[2] << 16) | ((uint64_t)q[3] << 24) |
+                  ((uint64_t)q[4] << 32) | ((uint64_t)q[5] << 40) | ((uint64_t)q[6] << 48) | ((uint64_t)q[7] << 56);
+            return (uint32_t)(win >> (pos - wlo)) & mask;
+        }
         return slow(n);
     }
     FSB_HDN uint32_t slow(int n)  // pos has been moved already
@@ -451,7 +460,7 @@ struct ExecCopy {
     uint8_t* out;
     uint64_t op, cap;
     // ll literal bytes at lit, then a match of ml bytes from `off` back (ml == 0: literals only)
-    FSB_HD int seq(uint64_t ll, uint64_t ml, uint64_t off, const uint8_t* lit, uint64_t /*lit_pos*/)
+    FSB_HD int seq(uint32_t ll, uint32_t ml, uint32_t off, const uint8_t* lit, uint32_t /*lit_pos*/)
     {
         if (ll > cap - op || ml > cap - op - ll) return kErrOut;
         copy16(out + op, lit, ll);
@@ -463,7 +472,7 @@ struct ExecCopy {
         }
         return 0;
     }
-    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* /*litbuf*/, uint64_t /*lit_pos*/)  // an RLE block
+    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* /*litbuf*/, uint32_t /*lit_pos*/)  // an RLE block
     {
         if (n > cap - op) return kErrOut;
         for (uint64_t k = 0; k < n; ++k) out[op + k] = v;
@@ -479,39 +488,40 @@ struct ExecRecord {
     static constexpr bool kKeepLiterals = true;
     SeqDesc* d;
     uint32_t nd, cap_d;
-    uint64_t op, cap;
+    uint32_t op, cap;  // (32-bit on purpose: this runs once per sequence on ONE lane, every instruction is latency)
     // the last descriptor, if it is literals only: kept HERE, not read back from d[] (on the device that
-    // read was a global-memory round trip per sequence -- 1700 cycles of a 1900-cycle sequence)
+    // read would be a global-memory round trip per sequence)
     bool open = false;
     uint32_t open_lit = 0;      // its literal bytes so far
-    uint64_t open_lit_end = 0;  // position behind them in the literal buffer
-    FSB_HD int seq(uint64_t ll, uint64_t ml, uint64_t off, const uint8_t* /*lit*/, uint64_t lit_pos)
+    uint32_t open_lit_end = 0;  // position behind them in the literal buffer
+    FSB_HD int seq(uint32_t ll, uint32_t ml, uint32_t off, const uint8_t* /*lit*/, uint32_t lit_pos)
     {
         if (ll > cap - op || ml > cap - op - ll) return kErrOut;
-        if (ll == 0 && ml == 0) return 0;
-        if (ml && (off == 0 || off > op + ll)) return kErrSeq;
+        if ((ll | ml) == 0u) return 0;
+        if (ml && (off == 0u || off > op + ll)) return kErrSeq;
         if (open && open_lit_end == lit_pos) {
             // the descriptor before was literals only (a block's tail, a raw block; it ends at op by
             // construction) and these literals follow them in the buffer: one descriptor.  Every descriptor
             // but the last then carries a match of >= 3 bytes, so cap / 3 + 2 descriptors are always enough.
-            open_lit += (uint32_t)ll;
+            open_lit += ll;
             d[nd - 1u].lit = open_lit;
-            d[nd - 1u].off = ml ? (uint32_t)off : 0u;
+            d[nd - 1u].off = ml ? off : 0u;
         } else {
             if (nd >= cap_d) return kErrOut;
-            d[nd++] = SeqDesc{(uint32_t)op, (uint32_t)lit_pos, (uint32_t)ll, ml ? (uint32_t)off : 0u};
-            open_lit = (uint32_t)ll;
+            d[nd++] = SeqDesc{op, lit_pos, ll, ml ? off : 0u};
+            open_lit = ll;
         }
-        open = ml == 0;
+        open = ml == 0u;
         open_lit_end = lit_pos + ll;
         op += ll + ml;
         return 0;
     }
-    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* litbuf, uint64_t lit_pos)  // an RLE block: one literal + a run
+    FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* litbuf, uint32_t lit_pos)  // an RLE block: one literal + a run
     {
         if (n == 0) return 0;
+        if (n > cap - op) return kErrOut;
         litbuf[0] = v;
-        return seq(1, n - 1, 1, litbuf, lit_pos);
+        return seq(1u, (uint32_t)n - 1u, 1u, litbuf, lit_pos);
     }
 };
 
@@ -519,7 +529,7 @@ struct ExecRecord {
 // regenerated (they start at litbuf[0] = literal position lit_pos of the frame) or < 0.
 // litbuf has room for kBlockMax + 32 bytes.
 template <class Exec>
-FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, const uint8_t* p, uint64_t n, Exec& ex)
+FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, const uint8_t* p, uint64_t n, Exec& ex)
 {
     // ---- literals section ----
     if (n < 1) return kErrTrunc;
@@ -610,7 +620,8 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, c
     else if (p[0] < 128) { nseq = p[0]; p += 1; n -= 1; }
     else if (p[0] < 255) { if (n < 2) return kErrTrunc; nseq = ((uint64_t)(p[0] - 128) << 8) + p[1]; p += 2; n -= 2; }
     else { if (n < 3) return kErrTrunc; nseq = (uint64_t)p[1] + ((uint64_t)p[2] << 8) + 0x7F00; p += 3; n -= 3; }
-    uint64_t lp = 0;  // literals consumed
+    uint32_t lp = 0;  // literals consumed
+    const uint32_t nlit = (uint32_t)regen;
     if (nseq) {
         if (n < 1) return kErrTrunc;
         const int modes = p[0];
@@ -626,37 +637,40 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, c
         Back b;
         if (!b.init(p, n)) return kErrSeq;
         uint32_t sl = b.read(c.ll.log), so = b.read(c.of.log), sm = b.read(c.ml.log);
-        uint64_t rep0 = c.rep[0], rep1 = c.rep[1], rep2 = c.rep[2];
-        for (uint64_t i = 0; i < nseq; ++i) {
+        // 32-bit arithmetic throughout the loop: one lane runs it, every instruction is a full pipeline latency
+        uint32_t rep0 = (uint32_t)c.rep[0], rep1 = (uint32_t)c.rep[1], rep2 = (uint32_t)c.rep[2];
+        const uint32_t ns = (uint32_t)nseq;
+        for (uint32_t i = 0; i < ns; ++i) {
             const uint64_t eo = c.of.st[so], em = c.ml.st[sm], el = c.ll.st[sl];
-            const uint64_t ov = (uint64_t)(uint32_t)eo + b.read((int)((eo >> 32) & 0xFF));
-            const uint64_t ml = (uint64_t)(uint32_t)em + b.read((int)((em >> 32) & 0xFF));
-            const uint64_t ll = (uint64_t)(uint32_t)el + b.read((int)((el >> 32) & 0xFF));
-            if (i + 1 < nseq) {
-                sl = (uint32_t)(el >> 48) + b.read((int)((el >> 40) & 0xFF));
-                sm = (uint32_t)(em >> 48) + b.read((int)((em >> 40) & 0xFF));
-                so = (uint32_t)(eo >> 48) + b.read((int)((eo >> 40) & 0xFF));
+            const uint32_t eoh = (uint32_t)(eo >> 32), emh = (uint32_t)(em >> 32), elh = (uint32_t)(el >> 32);
+            const uint32_t ov = (uint32_t)eo + b.read((int)(eoh & 0xFFu));  // (1 << code) + code bits: < 2^32
+            const uint32_t ml = (uint32_t)em + b.read((int)(emh & 0xFFu));
+            const uint32_t ll = (uint32_t)el + b.read((int)(elh & 0xFFu));
+            if (i + 1u < ns) {
+                sl = (elh >> 16) + b.read((int)((elh >> 8) & 0xFFu));
+                sm = (emh >> 16) + b.read((int)((emh >> 8) & 0xFFu));
+                so = (eoh >> 16) + b.read((int)((eoh >> 8) & 0xFFu));
             }
             if (b.pos < 0) return kErrSeq;
             // repeat offsets, RFC 8878 3.1.1.5
-            uint64_t off;
-            if (ov > 3) {
-                off = ov - 3;
+            uint32_t off;
+            if (ov > 3u) {
+                off = ov - 3u;
                 rep2 = rep1; rep1 = rep0; rep0 = off;
             } else {
-                const uint64_t idx = ov - 1 + (ll == 0 ? 1 : 0);
-                if (idx == 0) {
+                const uint32_t idx = ov - 1u + (ll == 0u ? 1u : 0u);
+                if (idx == 0u) {
                     off = rep0;
                 } else {
-                    off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-                    if (idx > 1) rep2 = rep1;
+                    off = idx == 1u ? rep1 : idx == 2u ? rep2 : rep0 - 1u;
+                    if (idx > 1u) rep2 = rep1;
                     rep1 = rep0;
                     rep0 = off;
                 }
             }
             // execute: literals, then the match (which may overlap its own output)
-            if (ll > regen - lp) return kErrOut;
-            if (off == 0) return kErrSeq;
+            if (ll > nlit - lp) return kErrOut;
+            if (off == 0u) return kErrSeq;
             const int rc = ex.seq(ll, ml, off, lit + lp, lit_pos + lp);
             if (rc) return rc;
             lp += ll;
@@ -665,7 +679,7 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint64_t lit_pos, c
         if (b.pos != 0) return kErrSeq;
     }
     {
-        const int rc = ex.seq(regen - lp, 0, 0, lit + lp, lit_pos + lp);
+        const int rc = ex.seq(nlit - lp, 0u, 0u, lit + lp, lit_pos + lp);
         if (rc) return rc;
     }
     return (int64_t)regen;
@@ -719,20 +733,20 @@ FSB_HDN int64_t run_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& c
                 copy16(lb, src, size);
                 src = lb;
             }
-            const int rc = ex.seq(size, 0, 0, src, lpos);
+            const int rc = ex.seq((uint32_t)size, 0u, 0u, src, (uint32_t)lpos);
             if (rc) return rc;
             if (Exec::kKeepLiterals) lpos += size;
             ip += size;
         } else if (type == 1) {
             if (n < ip + 1) return kErrTrunc;
-            const int rc = ex.fill(in[ip], size, lb, lpos);
+            const int rc = ex.fill(in[ip], size, lb, (uint32_t)lpos);
             if (rc) return rc;
             if (Exec::kKeepLiterals && size) lpos += 1;
             ip += 1;
         } else if (type == 2) {
             if (size > kBlockMax) return kErrBlock;
             if (n < ip + size) return kErrTrunc;
-            const int64_t r = block_compressed(c, lb, lpos, in + ip, size, ex);
+            const int64_t r = block_compressed(c, lb, (uint32_t)lpos, in + ip, size, ex);
             if (r < 0) return r;
             if (Exec::kKeepLiterals) lpos += (uint64_t)r;
             ip += size;
@@ -763,8 +777,9 @@ FSB_HDN int64_t decode_frame(const uint8_t* in, uint64_t n, uint8_t* out, uint64
 FSB_HDN int64_t parse_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& t, uint8_t* lit, uint64_t lit_cap,
                             SeqDesc* d, uint32_t cap_d, uint32_t* nd, uint64_t* lit_used)
 {
+    if (cap > 0xFFFFFFFFull) return kErrOut;
     ExecRecord ex;
-    ex.d = d; ex.nd = 0u; ex.cap_d = cap_d; ex.op = 0; ex.cap = cap;
+    ex.d = d; ex.nd = 0u; ex.cap_d = cap_d; ex.op = 0u; ex.cap = (uint32_t)cap;
     const int64_t r = run_frame(in, n, cap, t, lit, lit_cap, ex, lit_used);
     *nd = ex.nd;
     return r;
