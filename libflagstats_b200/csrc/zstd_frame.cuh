@@ -197,22 +197,17 @@ struct Back {
                   ((uint64_t)q[4] << 32) | ((uint64_t)q[5] << 40) | ((uint64_t)q[6] << 48) | ((uint64_t)q[7] << 56);
             return (uint32_t)(win >> (pos - wlo)) & mask;
         }
-        return slow(n);
+        return slow(p, pos, n);
     }
-    FSB_HDN uint32_t slow(int n)  // pos has been moved already
+    // (a static function of VALUES: a member taking `this` would force the reader out of its registers and
+    // into local memory -- measured: every read then goes through the stack, ~100 cycles each)
+    FSB_HDN static uint32_t slow(const uint8_t* p, int32_t pos, int n)  // pos has been moved already
     {
         if (n == 0) return 0u;
         const uint32_t mask = (uint32_t)(((uint64_t)1 << n) - 1u);
         if (pos >= 0) {
-            // refill so that the window ENDS with the byte that holds bit pos + n - 1 (all bytes below
-            // the end marker's byte, all inside the stream) and reaches 64 bits down from there
+            // within the first bytes of the stream (pos < 56): bits [pos, pos + n) lie inside at most 5 bytes
             const int32_t top = (pos + n - 1) >> 3;  // last byte needed
-            if (top >= 7) {
-                wlo = (top - 7) * 8;
-                win = le(p + (top - 7), 8);
-                return (uint32_t)(win >> (pos - wlo)) & mask;
-            }
-            // within the first bytes of the stream: bits [pos, pos + n) lie inside at most 5 bytes
             const int32_t b = pos >> 3;
             const int nb = (int)(top - b) + 1;
             return (uint32_t)(le(p + b, nb) >> (pos & 7)) & mask;
@@ -640,6 +635,7 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
         // 32-bit arithmetic throughout the loop: one lane runs it, every instruction is a full pipeline latency
         uint32_t rep0 = (uint32_t)c.rep[0], rep1 = (uint32_t)c.rep[1], rep2 = (uint32_t)c.rep[2];
         const uint32_t ns = (uint32_t)nseq;
+        Exec e = ex;  // (a copy the loop keeps in registers; `ex` itself lives in the caller's frame)
         for (uint32_t i = 0; i < ns; ++i) {
             const uint64_t eo = c.of.st[so], em = c.ml.st[sm], el = c.ll.st[sl];
             const uint32_t eoh = (uint32_t)(eo >> 32), emh = (uint32_t)(em >> 32), elh = (uint32_t)(el >> 32);
@@ -671,10 +667,11 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
             // execute: literals, then the match (which may overlap its own output)
             if (ll > nlit - lp) return kErrOut;
             if (off == 0u) return kErrSeq;
-            const int rc = ex.seq(ll, ml, off, lit + lp, lit_pos + lp);
+            const int rc = e.seq(ll, ml, off, lit + lp, lit_pos + lp);
             if (rc) return rc;
             lp += ll;
         }
+        ex = e;
         c.rep[0] = rep0; c.rep[1] = rep1; c.rep[2] = rep2;
         if (b.pos != 0) return kErrSeq;
     }
