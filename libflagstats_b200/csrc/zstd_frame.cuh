@@ -639,13 +639,46 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
         for (uint32_t i = 0; i < ns; ++i) {
             const uint64_t eo = c.of.st[so], em = c.ml.st[sm], el = c.ll.st[sl];
             const uint32_t eoh = (uint32_t)(eo >> 32), emh = (uint32_t)(em >> 32), elh = (uint32_t)(el >> 32);
-            const uint32_t ov = (uint32_t)eo + b.read((int)(eoh & 0xFFu));  // (1 << code) + code bits: < 2^32
-            const uint32_t ml = (uint32_t)em + b.read((int)(emh & 0xFFu));
-            const uint32_t ll = (uint32_t)el + b.read((int)(elh & 0xFFu));
-            if (i + 1u < ns) {
-                sl = (elh >> 16) + b.read((int)((elh >> 8) & 0xFFu));
-                sm = (emh >> 16) + b.read((int)((emh >> 8) & 0xFFu));
-                so = (eoh >> 16) + b.read((int)((eoh >> 8) & 0xFFu));
+            const bool more = i + 1u < ns;
+            // the six bit fields of a sequence, in stream order: offset, match length, literal length extra
+            // bits, then the bits of the next LL, ML, OF states (none behind the last sequence)
+            const int n1 = (int)(eoh & 0xFFu), n2 = (int)(emh & 0xFFu), n3 = (int)(elh & 0xFFu);
+            const int n4 = more ? (int)((elh >> 8) & 0xFFu) : 0, n5 = more ? (int)((emh >> 8) & 0xFFu) : 0,
+                      n6 = more ? (int)((eoh >> 8) & 0xFFu) : 0;
+            const int total = n1 + n2 + n3 + n4 + n5 + n6;
+            uint32_t ov, ml, ll;
+            if (total <= 57 && b.pos >= 57) {
+                // All six at once: the counts are known from the table entries, so the six positions are a
+                // prefix sum and the six extractions are independent of one another -- one lane runs this
+                // loop, and what it waits for is the LENGTH of the dependent chain, not the instruction count.
+                if (b.pos - total < b.wlo) {  // window: the 64 bits that end with the byte holding bit pos - 1
+                    const int32_t top = (b.pos - 1) >> 3;  // >= 7
+                    const uint8_t* q = b.p + (top - 7);
+                    b.wlo = (top - 7) * 8;  // <= pos - 57 <= pos - total
+                    b.win = (uint64_t)q[0] | ((uint64_t)q[1] << 8) | ((uint64_t)q[2] << 16) | ((uint64_t)q[3] << 24) |
+                            ((uint64_t)q[4] << 32) | ((uint64_t)q[5] << 40) | ((uint64_t)q[6] << 48) | ((uint64_t)q[7] << 56);
+                }
+                const int32_t base = b.pos - b.wlo;
+                const int p1 = base - n1, p2 = p1 - n2, p3 = p2 - n3, p4 = p3 - n4, p5 = p4 - n5, p6 = p5 - n6;
+                const uint64_t w = b.win;  // (a position is 64 only in front of an empty field: masked to 0 bits)
+                ov = (uint32_t)eo + ((uint32_t)(w >> (p1 & 63)) & ((1u << n1) - 1u));  // (every count <= 31 here)
+                ml = (uint32_t)em + ((uint32_t)(w >> (p2 & 63)) & ((1u << n2) - 1u));
+                ll = (uint32_t)el + ((uint32_t)(w >> (p3 & 63)) & ((1u << n3) - 1u));
+                if (more) {
+                    sl = (elh >> 16) + ((uint32_t)(w >> (p4 & 63)) & ((1u << n4) - 1u));
+                    sm = (emh >> 16) + ((uint32_t)(w >> (p5 & 63)) & ((1u << n5) - 1u));
+                    so = (eoh >> 16) + ((uint32_t)(w >> (p6 & 63)) & ((1u << n6) - 1u));
+                }
+                b.pos -= total;
+            } else {  // long offset codes, the first bytes of the stream, streams that run dry: one read at a time
+                ov = (uint32_t)eo + b.read(n1);  // (1 << code) + code bits: < 2^32
+                ml = (uint32_t)em + b.read(n2);
+                ll = (uint32_t)el + b.read(n3);
+                if (more) {
+                    sl = (elh >> 16) + b.read(n4);
+                    sm = (emh >> 16) + b.read(n5);
+                    so = (eoh >> 16) + b.read(n6);
+                }
             }
             if (b.pos < 0) return kErrSeq;
             // repeat offsets, RFC 8878 3.1.1.5
