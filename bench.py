@@ -340,7 +340,7 @@ def strong_scaling_leg(args, fs, sharded, synth, xchg, overlap, dev, stream, wor
     shard = synth.hiseqx_device(hi - lo, start=lo, device=dev)
     out = torch.zeros(32, dtype=torch.int64, device=dev)
     torch.cuda.synchronize(dev)
-    deferred = xchg is not None and overlap and not args.no_deferred
+    deferred = xchg is not None and overlap and args.deferred
 
     def run(k, d):
         for _ in range(k):
@@ -539,16 +539,17 @@ def ours(args) -> int:
         fs.flagstat_device(data, out=counters, stream=stream)
         sharded.allreduce_counters(counters)
 
-    deferred = xchg is not None and overlap and not args.no_deferred
+    deferred = xchg is not None and overlap and args.deferred
 
     def step_fused():
         # ONE kernel launch per rank: count the shard, push the 32 totals into every
         # peer's exchange buffer over NVLink, write the global counters (overwrite mode: no
-        # memset either).  Deferred collection (default): the launch does not wait for the
-        # peers' totals of THIS step -- the next step's launch first collects them (and the
-        # last step's are collected by xchg.collect() inside the timed region), so a rank only
-        # ever waits for its peers' PREVIOUS step and per-step jitter between GPUs stays off
-        # the critical path.
+        # memset either).  By default the launch's last CTA also waits for the peers' totals of
+        # this step (they arrive while the NEXT step's CTAs are already streaming: overlapped
+        # launches).  --deferred: the launch only pushes, the next step's launch collects (and the
+        # last step's are collected by xchg.collect() inside the timed region).  Both orders are
+        # measured in every multi-GPU run; on the 8-GPU box of session r7b waiting in the launch
+        # was the faster one at N = 8 (231.3 vs 234.8 us per step), at N = 2 and 4 they tie.
         xchg.flagstat(data, out=counters, accumulate=False, stream=stream, deferred=deferred)
 
     def finish_steps():
@@ -1004,8 +1005,10 @@ def main() -> int:
                     help="extra warm-up under load before the timed steps (seconds)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="launch consecutive fused steps strictly serialised (no programmatic dependent launch)")
-    ap.add_argument("--no-deferred", action="store_true",
-                    help="fused steps wait for the peers' totals in the same launch (round-1 behaviour)")
+    ap.add_argument("--deferred", action="store_true",
+                    help="headline steps with deferred collection (push only; the next launch collects) instead of "
+                         "waiting for the peers' totals in the same launch; the other order is always measured too")
+    ap.add_argument("--no-deferred", action="store_true", help="(the default since session r7b; accepted and ignored)")
     ap.add_argument("--no-strong", action="store_true", help="skip the 2^34-record strong-scaling leg (configs[3])")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the N=1 extra legs (100 M in-memory config, FLAG files, drop-in block loop, CPU kernel set)")
