@@ -179,14 +179,16 @@ int FLAGSTAT_cuda_stream_selftime(FLAGSTAT_cuda_stream* s, uint32_t n_blocks, ui
  *       blocks through the pinned ring (flagstat_raw, flagstats.cpp:415-468).
  * _LZ4: the container lz4f()/lz4hc() write (:110-186) and lz4_decompress() reads
  *       (:288-358): repeated [int32 raw_size][int32 comp_size][LZ4 block].  The
- *       blocks cross PCIe COMPRESSED and are decoded on the GPU (one warp per
- *       block), then counted from HBM.  N = raw_size >> 1 records per block like
- *       :323.
+ *       blocks cross PCIe COMPRESSED and are decoded on the GPU (one CTA per
+ *       block; FLAGSTAT_cuda_set_lz4_variant), then counted from HBM.  N = raw_size >> 1
+ *       records per block like :323.
  * _ZSTD: the container zstd() writes (:192-215) and zstd_decompress() reads (:636-676): the
  *       same records around one Zstandard FRAME each (ZSTD_compress / ZSTD_decompress,
  *       :90-98).  Shipped compressed, decoded on the GPU (RFC 8878: Huffman / FSE / repeat
- *       offsets; no dictionaries, checksum not verified; first version: one thread per
- *       frame, ~1600 frames per file in flight), counted from HBM.
+ *       offsets; no dictionaries, checksum not verified; an entropy stage with one lane
+ *       per frame writes sequence descriptors, a CTA per frame then executes them with the
+ *       copy phase of the LZ4 decoder; environment FLAGSTAT_CUDA_ZSTD_VARIANT=0 selects the
+ *       first version, one thread per frame start to end, for A/B), counted from HBM.
  * flags[32] is accumulated into; *n_records (may be NULL) receives the number of
  * records counted.  Runs on the current device; synchronous. */
 #define FLAGSTAT_CUDA_FILE_RAW 0
