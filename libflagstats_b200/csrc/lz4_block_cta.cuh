@@ -515,6 +515,9 @@ __device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t 
 // u16 pairs; pointer jumping, two hops per round, a PAIR at a time -- a pair whose parents do not move any more
 // sits on roots (P[x] < x for every byte that is not one) and drops out; a round reads P[], then (behind a
 // barrier) every owner stores its entries --; then root -> byte.  rb[j] receives pair j's two final bytes.
+#ifndef FSB_L4_HOPS
+#define FSB_L4_HOPS 2  // hops per pointer-jumping round (3: A/B builds, tools/gpu_r8a.sh)
+#endif
 constexpr uint32_t kL4Pairs = kL4ByteChunk / 2u;                 // 8
 constexpr uint32_t kL4PairStride = 2u * kL4Threads;              // 1024 bytes between a thread's pairs
 __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t tid, uint32_t (&rb)[kL4Pairs])
@@ -543,7 +546,10 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
 #pragma unroll
         for (uint32_t j = 0; j < kL4Pairs; ++j) {
             if (act & (1u << j)) {
-                const uint32_t q = hop(hop(pp[j]));
+                uint32_t q = hop(hop(pp[j]));
+#if FSB_L4_HOPS == 3
+                q = hop(q);
+#endif
                 if (q != pp[j]) {
                     pp[j] = q;
                     changed |= 1u << j;

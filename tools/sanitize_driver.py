@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for compute-sanitizer: every kernel variant, both modes, ragged / unaligned
-inputs, the fused exchange at world 1 and the block stream, on small inputs."""
+inputs, the fused exchange at world 1, the block stream, the LZ4 and Zstd decoders, on small inputs."""
 import os
 import sys
 
@@ -107,6 +107,31 @@ for v in (2, 1, 0):
     f, n = blockfile.flagstat_container(blob, blockfile.LZ4)
     assert n == cols[0].size and f.tolist() == O.numpy_flagstat(cols[0]).tolist(), v
 lib.FLAGSTAT_cuda_set_lz4_variant(2)
+# Zstd frames, both decoders (two-stage default; one thread per frame): well-formed frames of several shapes
+# (far offsets, noise = raw blocks, tiny), corrupted frames, a container
+if O.libzstd() is not None:
+    noise = rng.integers(0, 256, 70_001, dtype=np.uint8).tobytes()
+    zraws = [c.tobytes() for c in cols[:3]] + [noise * 3 + noise[:999], bytes(rng.integers(0, 3, 50_001, dtype=np.uint8)), b"xyz"]
+    zframes = [O.libzstd_compress(r, lvl) for r, lvl in zip(zraws, (1, 3, 19, 3, 1, 1))]
+    zbad = []
+    for f in zframes[:4]:
+        for k in range(6):
+            b = bytearray(f)
+            if k % 2 == 0:
+                b[int(rng.integers(4, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            else:
+                b = b[: int(rng.integers(1, len(b)))]
+            zbad.append(bytes(b))
+    for variant in ("1", "0"):
+        os.environ["FLAGSTAT_CUDA_ZSTD_VARIANT"] = variant
+        out, status = blockfile.zstd_decode(zframes, [len(r) for r in zraws])
+        assert status == [len(r) for r in zraws], (variant, status)
+        assert all(o == r for o, r in zip(out, zraws)), variant
+        blockfile.zstd_decode(zbad, [len(zraws[i // 6]) for i in range(len(zbad))])
+        blob = O.write_zstd_container(cols[0], 1)
+        f, n = blockfile.flagstat_container(blob, blockfile.ZSTD)
+        assert n == cols[0].size and f.tolist() == O.numpy_flagstat(cols[0]).tolist(), variant
+    os.environ["FLAGSTAT_CUDA_ZSTD_VARIANT"] = "1"
 # pageable host arrays: threaded staging
 a = O.synth_hiseqx(0, 6_000_001, 4, 5000)
 assert fs.flagstat_u64(a).tolist() == O.flagstat_simd(a).tolist()
