@@ -542,16 +542,23 @@ int consume_lz4(int mode, int codec, ByteSource& src, uint64_t* totals, uint64_t
     const int T = gather_threads();
     const bool nt = staging_nt();
     int batch_blocks = kBatchBlocks;
-    if (codec == kCodecLz4 && lz4_variant() == 2) {
+    if ((codec == kCodecLz4 && lz4_variant() == 2) || (codec == kCodecZstd && zstd_variant() != 0)) {
         // The CTA decoder works on 2 x SMs blocks at a time (one wave); batches of that size let the
         // gather and the H2D copy of batch k + 1 run while batch k is being decoded -- a file of
-        // 1601 blocks used to be ONE batch: gather, copy, decode and count back to back.
+        // 1601 blocks used to be ONE batch: gather, copy, decode and count back to back.  A file of a
+        // few hundred blocks is cut finer (one CTA per SM per batch: two batches decode side by side
+        // and the first one starts after a 1.5 ms gather instead of 3 ms): 401 blocks 6.0 -> 5.3 ms at
+        // ratio 5.2, 10.3 -> 8.1 ms at ratio 2.2; at 1601 blocks the wave-sized batch is the faster one.
+        // Zstd frames: the entropy stage of a batch takes ~25 ms whatever the batch holds, so batches
+        // are large (4 x SMs) and the stages of up to three of them overlap.
+        // (profiles/r8d_container_batch_sweep.txt)
         int dev = 0;
         DeviceInfo* di = nullptr;
         CK(cudaGetDevice(&dev));
         const int irc = device_info(dev, &di);
         if (irc) return irc;
-        batch_blocks = 2 * di->sms;
+        if (codec == kCodecZstd) batch_blocks = 4 * di->sms;
+        else batch_blocks = idx.size() <= (size_t)4 * (size_t)di->sms ? di->sms : 2 * di->sms;
         if (batch_blocks > kBatchBlocks) batch_blocks = kBatchBlocks;
     }
     if (const char* e = std::getenv("FLAGSTAT_CUDA_LZ4_BATCH")) {  // tests: force several batches
