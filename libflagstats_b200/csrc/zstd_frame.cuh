@@ -452,8 +452,10 @@ FSB_HDN int64_t seq_table(Tab& t, int mode, const uint8_t* p, uint64_t n, int wh
 // first version: copy at once into out[op..]
 struct ExecCopy {
     static constexpr bool kKeepLiterals = false;  // literals may be used where they lie (input, block buffer)
+    static constexpr bool kDeferChecks = false;   // it writes the output: every sequence is checked before it is executed
     uint8_t* out;
     uint64_t op, cap;
+    uint32_t bad = 0;  // (unused: interface of the sequence loop)
     // ll literal bytes at lit, then a match of ml bytes from `off` back (ml == 0: literals only)
     FSB_HD int seq(uint32_t ll, uint32_t ml, uint32_t off, const uint8_t* lit, uint32_t /*lit_pos*/)
     {
@@ -467,6 +469,7 @@ struct ExecCopy {
         }
         return 0;
     }
+    FSB_HD int check() const { return 0; }
     FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* /*litbuf*/, uint32_t /*lit_pos*/)  // an RLE block
     {
         if (n > cap - op) return kErrOut;
@@ -481,9 +484,15 @@ struct ExecCopy {
 // are enough), which is what the descriptors index.
 struct ExecRecord {
     static constexpr bool kKeepLiterals = true;
+    // It only WRITES DESCRIPTORS (bounded by cap_d), so nothing a corrupt sequence says can reach memory: the
+    // sequence loop runs without early exits -- violations are OR-ed into `bad` and looked at once per block.
+    // One lane runs that loop; a compare-and-branch per check was a fifth of its instructions and most of its
+    // branch stalls.
+    static constexpr bool kDeferChecks = true;
     SeqDesc* d;
     uint32_t nd, cap_d;
     uint32_t op, cap;  // (32-bit on purpose: this runs once per sequence on ONE lane, every instruction is latency)
+    uint32_t bad = 0;  // sticky: a sequence overran the output, pointed in front of it, or d[] is full
     // the last descriptor, if it is literals only: kept HERE, not read back from d[] (on the device that
     // read would be a global-memory round trip per sequence)
     bool open = false;
@@ -491,9 +500,9 @@ struct ExecRecord {
     uint32_t open_lit_end = 0;  // position behind them in the literal buffer
     FSB_HD int seq(uint32_t ll, uint32_t ml, uint32_t off, const uint8_t* /*lit*/, uint32_t lit_pos)
     {
-        if (ll > cap - op || ml > cap - op - ll) return kErrOut;
+        const uint64_t m = (uint64_t)op + ll, end = m + ml;
+        bad |= (uint32_t)(end > cap) | (uint32_t)(ml != 0u && (off == 0u || off > m));
         if ((ll | ml) == 0u) return 0;
-        if (ml && (off == 0u || off > op + ll)) return kErrSeq;
         if (open && open_lit_end == lit_pos) {
             // the descriptor before was literals only (a block's tail, a raw block; it ends at op by
             // construction) and these literals follow them in the buffer: one descriptor.  Every descriptor
@@ -501,16 +510,19 @@ struct ExecRecord {
             open_lit += ll;
             d[nd - 1u].lit = open_lit;
             d[nd - 1u].off = ml ? off : 0u;
-        } else {
-            if (nd >= cap_d) return kErrOut;
+        } else if (nd < cap_d) {
             d[nd++] = SeqDesc{op, lit_pos, ll, ml ? off : 0u};
             open_lit = ll;
+        } else {
+            bad |= 1u;
+            return 0;  // (`open` keeps implying that d[nd - 1] exists)
         }
         open = ml == 0u;
         open_lit_end = lit_pos + ll;
-        op += ll + ml;
+        op = (uint32_t)end;  // (meaningless once bad is set; nothing is addressed with it)
         return 0;
     }
+    FSB_HD int check() const { return bad ? kErrSeq : 0; }
     FSB_HD int fill(uint8_t v, uint64_t n, uint8_t* litbuf, uint32_t lit_pos)  // an RLE block: one literal + a run
     {
         if (n == 0) return 0;
@@ -680,7 +692,8 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
                     so = (eoh >> 16) + b.read(n6);
                 }
             }
-            if (b.pos < 0) return kErrSeq;
+            if (Exec::kDeferChecks) e.bad |= (uint32_t)(b.pos < 0);  // (reads in front of the stream give zeros)
+            else if (b.pos < 0) return kErrSeq;
             // repeat offsets, RFC 8878 3.1.1.5
             uint32_t off;
             if (ov > 3u) {
@@ -698,19 +711,26 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
                 }
             }
             // execute: literals, then the match (which may overlap its own output)
-            if (ll > nlit - lp) return kErrOut;
-            if (off == 0u) return kErrSeq;
-            const int rc = e.seq(ll, ml, off, lit + lp, lit_pos + lp);
-            if (rc) return rc;
+            if (Exec::kDeferChecks) {
+                e.bad |= (uint32_t)(ll > nlit - lp) | (uint32_t)(off == 0u);
+                e.seq(ll, ml, off, lit + lp, lit_pos + lp);  // (lit + lp is not dereferenced by this executor)
+            } else {
+                if (ll > nlit - lp) return kErrOut;
+                if (off == 0u) return kErrSeq;
+                const int rc = e.seq(ll, ml, off, lit + lp, lit_pos + lp);
+                if (rc) return rc;
+            }
             lp += ll;
         }
         ex = e;
+        if (ex.check()) return ex.check();
         c.rep[0] = rep0; c.rep[1] = rep1; c.rep[2] = rep2;
         if (b.pos != 0) return kErrSeq;
     }
     {
         const int rc = ex.seq(nlit - lp, 0u, 0u, lit + lp, lit_pos + lp);
         if (rc) return rc;
+        if (ex.check()) return ex.check();
     }
     return (int64_t)regen;
 }
@@ -789,6 +809,7 @@ FSB_HDN int64_t run_frame(const uint8_t* in, uint64_t n, uint64_t cap, Tables& c
         if (n < ip + 4) return kErrTrunc;
         ip += 4;  // xxh64 of the content, low 32 bits: not verified
     }
+    if (ex.check()) return ex.check();
     if (fcs_bytes && fcs != ex.op) return kErrOut;
     if (lit_used) *lit_used = lpos;
     return (int64_t)ex.op;
