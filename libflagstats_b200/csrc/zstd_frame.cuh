@@ -648,8 +648,7 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
         uint32_t rep0 = (uint32_t)c.rep[0], rep1 = (uint32_t)c.rep[1], rep2 = (uint32_t)c.rep[2];
         const uint32_t ns = (uint32_t)nseq;
         Exec e = ex;  // (a copy the loop keeps in registers; `ex` itself lives in the caller's frame)
-        // decode: the bit fields of sequence i and the next states -- the loop-carried, dependent chain
-        auto decode = [&](uint32_t i, uint32_t& ov, uint32_t& ml, uint32_t& ll) {
+        for (uint32_t i = 0; i < ns; ++i) {
             const uint64_t eo = c.of.st[so], em = c.ml.st[sm], el = c.ll.st[sl];
             const uint32_t eoh = (uint32_t)(eo >> 32), emh = (uint32_t)(em >> 32), elh = (uint32_t)(el >> 32);
             const bool more = i + 1u < ns;
@@ -659,6 +658,7 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
             const int n4 = more ? (int)((elh >> 8) & 0xFFu) : 0, n5 = more ? (int)((emh >> 8) & 0xFFu) : 0,
                       n6 = more ? (int)((eoh >> 8) & 0xFFu) : 0;
             const int total = n1 + n2 + n3 + n4 + n5 + n6;
+            uint32_t ov, ml, ll;
             if (total <= 57 && b.pos >= 57) {
                 // All six at once: the counts are known from the table entries, so the six positions are a
                 // prefix sum and the six extractions are independent of one another -- one lane runs this
@@ -692,9 +692,9 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
                     so = (eoh >> 16) + b.read(n6);
                 }
             }
-        };
-        // consume: repeat offsets (RFC 8878 3.1.1.5) and the executor -- bookkeeping nothing in decode waits for
-        auto consume = [&](uint32_t ov, uint32_t ml, uint32_t ll) -> int {
+            if (Exec::kDeferChecks) e.bad |= (uint32_t)(b.pos < 0);  // (reads in front of the stream give zeros)
+            else if (b.pos < 0) return kErrSeq;
+            // repeat offsets, RFC 8878 3.1.1.5
             uint32_t off;
             if (ov > 3u) {
                 off = ov - 3u;
@@ -721,31 +721,6 @@ FSB_HDN int64_t block_compressed(Tables& c, uint8_t* litbuf, uint32_t lit_pos, c
                 if (rc) return rc;
             }
             lp += ll;
-            return 0;
-        };
-        if (Exec::kDeferChecks) {
-            // Software pipeline: the fields of sequence i are decoded while sequence i - 1 is consumed.  The
-            // two are independent, so the compiler can fill the latency slots of the decode chain with the
-            // bookkeeping -- on one in-order lane that is the only overlap there is.
-            uint32_t pov, pml, pll;
-            decode(0u, pov, pml, pll);
-            e.bad |= (uint32_t)(b.pos < 0);  // (reads in front of the stream give zeros)
-            for (uint32_t i = 1; i < ns; ++i) {
-                uint32_t ov, ml, ll;
-                decode(i, ov, ml, ll);
-                e.bad |= (uint32_t)(b.pos < 0);
-                consume(pov, pml, pll);
-                pov = ov; pml = ml; pll = ll;
-            }
-            consume(pov, pml, pll);
-        } else {
-            for (uint32_t i = 0; i < ns; ++i) {
-                uint32_t ov, ml, ll;
-                decode(i, ov, ml, ll);
-                if (b.pos < 0) return kErrSeq;
-                const int rc = consume(ov, ml, ll);
-                if (rc) return rc;
-            }
         }
         ex = e;
         if (ex.check()) return ex.check();
