@@ -548,8 +548,8 @@ def ours(args) -> int:
         # this step (they arrive while the NEXT step's CTAs are already streaming: overlapped
         # launches).  --deferred: the launch only pushes, the next step's launch collects (and the
         # last step's are collected by xchg.collect() inside the timed region).  Both orders are
-        # measured in every multi-GPU run; on the 8-GPU box of session r7b waiting in the launch
-        # was the faster one at N = 8 (231.3 vs 234.8 us per step), at N = 2 and 4 they tie.
+        # measured in every multi-GPU run; they tie at N = 2, 4 and 8 (whichever leg is measured
+        # first comes out ~1 % slower at N = 8: profiles/r7b_*, r9e_*), so the simpler one leads.
         xchg.flagstat(data, out=counters, accumulate=False, stream=stream, deferred=deferred)
 
     def finish_steps():

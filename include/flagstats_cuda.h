@@ -274,9 +274,9 @@ int POSPOPCNT_cuda_device_allreduce(FLAGSTAT_cuda_xchg* x, const uint16_t* d_dat
  * handle (which first collects what its predecessor left pending, then pushes its own totals)
  * or by FLAGSTAT_cuda_xchg_collect -- so d_flags must stay valid until then.  For back-to-back
  * steps: a rank waits only for its peers' PREVIOUS step and may run one step ahead of the
- * slowest rank.  Measured on 2, 4 and 8 B200s with overlapped steps it ties with, or is a little
- * slower than, waiting in the same launch: use it where the caller's own
- * schedule benefits from counters that arrive one call late, not for speed.  Every rank must
+ * slowest rank.  Measured on 2, 4 and 8 B200s with overlapped steps it ties with waiting in the
+ * same launch: use it where the caller's own schedule benefits from
+ * counters that arrive one call late, not for speed.  Every rank must
  * issue the same sequence of deferred / immediate / collect calls.  With one rank d_flags is
  * written at once. */
 int FLAGSTAT_cuda_device_allreduce_deferred(FLAGSTAT_cuda_xchg* x, const uint16_t* d_array,
