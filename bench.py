@@ -578,6 +578,13 @@ def ours(args) -> int:
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
+    # nvidia-smi must have reached its steady polling state BEFORE the settle loop, not between it and
+    # the timed region: on an 8-GPU box its start-up takes seconds, during which the GPUs would sit idle,
+    # and the first timed leg then came out ~1 % slower than the same steps measured later
+    # (profiles/r7b_*, r9e_*: whichever collection order was measured first lost)
+    if rank == 0:
+        sampler.wait_first_sample(5.0)
+    fence()
     # (the decision to keep going is taken collectively: every rank must issue the same number
     # of steps, or the epochs of the fused exchange would drift apart between ranks)
     tw = time.perf_counter()
@@ -616,12 +623,6 @@ def ours(args) -> int:
             fence()
 
     # ---- device-resident timed region: exactly K steps ---------------------
-    if rank == 0:
-        sampler.wait_first_sample(3.0)  # nvidia-smi is in its steady polling state
-    fence()
-    # the wait above idled the GPUs: a few steps bring them back to the state the settle loop left
-    for _ in range(max(args.warmup, 3)):
-        step()
     if xchg is not None:
         finish_steps()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
