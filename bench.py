@@ -548,8 +548,9 @@ def ours(args) -> int:
         # this step (they arrive while the NEXT step's CTAs are already streaming: overlapped
         # launches).  --deferred: the launch only pushes, the next step's launch collects (and the
         # last step's are collected by xchg.collect() inside the timed region).  Both orders are
-        # measured in every multi-GPU run; they tie at N = 2, 4 and 8 (whichever leg is measured
-        # first comes out ~1 % slower at N = 8: profiles/r7b_*, r9e_*), so the simpler one leads.
+        # measured in every multi-GPU run; they tie at N = 2, 4 and 8 (the headline leg, measured
+        # right after the settle loop, is the ~1 % slower one at N = 8 whichever order it uses:
+        # profiles/r7b_*, r9e_*, r9f_*), so the simpler one leads.
         xchg.flagstat(data, out=counters, accumulate=False, stream=stream, deferred=deferred)
 
     def finish_steps():
@@ -579,9 +580,10 @@ def ours(args) -> int:
         step()
     fence()
     # nvidia-smi must have reached its steady polling state BEFORE the settle loop, not between it and
-    # the timed region: on an 8-GPU box its start-up takes seconds, during which the GPUs would sit idle,
-    # and the first timed leg then came out ~1 % slower than the same steps measured later
-    # (profiles/r7b_*, r9e_*: whichever collection order was measured first lost)
+    # the timed region (on an 8-GPU box its start-up takes seconds, during which the GPUs would sit
+    # idle): the K timed steps follow the settle loop directly and see the sustained, power-capped
+    # clocks.  (The comparison legs further down run 20 steps each after short host-side pauses and
+    # come out up to ~1 % faster at N = 8 for that reason: profiles/r7b_*, r9e_*, r9f_*.)
     if rank == 0:
         sampler.wait_first_sample(5.0)
     fence()
