@@ -29,7 +29,11 @@
 #if defined(__CUDACC__)
 #define FSB_HD __host__ __device__ __forceinline__
 #define FSB_HDN __host__ __device__ __noinline__
+#if defined(__CUDA_ARCH__)
 #define FSB_UNROLL _Pragma("unroll")
+#else
+#define FSB_UNROLL  // (the host pass of nvcc is g++: it does not know the pragma)
+#endif
 #else
 #define FSB_HD inline
 #define FSB_HDN inline
