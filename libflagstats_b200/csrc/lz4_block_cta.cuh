@@ -537,7 +537,9 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
     // have even offsets, and only ~2 % of the sequences start or end on an odd byte
     auto hop = [&](uint32_t w) -> uint32_t {
         const uint32_t p0 = w & 0xFFFFu;
+#ifndef FSB_L4_HOP_BYTES  // (A/B: always two 16-bit look-ups, no test -- tools/gpu_r9g.sh)
         if (w == (w & 0xFFFEu) * 0x10001u + 0x10000u) return *reinterpret_cast<const uint32_t*>(P + p0);
+#endif
         return (uint32_t)P[p0] | ((uint32_t)P[w >> 16] << 16);
     };
     for (;;) {
