@@ -532,16 +532,11 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
         pp[j] = *reinterpret_cast<const uint32_t*>(P + x);
         if (pp[j] != (x | ((x + 1u) << 16))) act |= 1u << j;
     }
-    // parents of the two bytes p0 = w & 0xFFFF, p1 = w >> 16: ONE 32-bit load when they are an aligned pair
-    // themselves (p1 = p0 + 1, p0 even) -- nearly always: FLAG words are two bytes, matches between them
-    // have even offsets, and only ~2 % of the sequences start or end on an odd byte
-    auto hop = [&](uint32_t w) -> uint32_t {
-        const uint32_t p0 = w & 0xFFFFu;
-#ifndef FSB_L4_HOP_BYTES  // (A/B: always two 16-bit look-ups, no test -- tools/gpu_r9g.sh)
-        if (w == (w & 0xFFFEu) * 0x10001u + 0x10000u) return *reinterpret_cast<const uint32_t*>(P + p0);
-#endif
-        return (uint32_t)P[p0] | ((uint32_t)P[w >> 16] << 16);
-    };
+    // parents of the two bytes p0 = w & 0xFFFF, p1 = w >> 16: two 16-bit look-ups, no case distinction.  (One
+    // 32-bit look-up when the two are an aligned pair themselves was measured: slower by 8 - 12 % -- a pair
+    // stops being aligned as soon as its chain passes one odd-aligned match, the lanes of a warp then
+    // disagree and the warp pays for the test AND both paths; profiles/r9g_lz4_hop_ab.txt.)
+    auto hop = [&](uint32_t w) -> uint32_t { return (uint32_t)P[w & 0xFFFFu] | ((uint32_t)P[w >> 16] << 16); };
     for (;;) {
         L4P_COUNT(15, 1);  // rounds
         uint32_t changed = 0u;  // bit j: pair j has new parents
