@@ -703,43 +703,29 @@ __device__ int l4_copy(const uint8_t* __restrict__ in, uint32_t in_size, uint8_t
                 x = he - tlo;
             }
             if (x >= y) continue;
-            if (off >= ml && x >= off) {
-                // the common case, a plain copy whose source lies inside this tile: parent(v) = v - off,
-                // two parents per 32-bit store
-                uint32_t par = x - off;
+            const bool wraps = off < ml;  // a repeating match: a run of equal FLAG words is offset 2
+            if (wraps ? (m - off >= tlo && a == m && (off == 1u || ((off | x) & 1u) == 0u)) : x >= off) {
+                // The common cases, ONE path for both (the lanes of a warp hold a mix of them): a plain copy
+                // whose source lies inside this tile, parent(v) = v - off, and a repeating match whose first
+                // period lies inside it, parent(v) = first period + (v - m) mod off -- its chain is one hop long
+                // whatever the length.  Byte d = v - m of the match has parent s0 + (d mod period); the period of
+                // a plain copy is never reached.  Two parents per 32-bit store.
+                const uint32_t s0 = m - off - tlo;          // (as a 32-bit sum with r: never negative)
+                uint32_t r = x + tlo - m;                   // d of the first byte (0 for a repeating match)
+                const uint32_t lim = wraps ? off : 0xFFFFFFFFu;
+                const uint32_t inc = (wraps && off == 1u) ? 0u : 1u;  // offset 1: every byte copies the same one
                 if (x & 1u) {
-                    P[x] = (uint16_t)par;
+                    P[x] = (uint16_t)(s0 + r);
                     ++x;
-                    ++par;
+                    r += inc;
                 }
-                for (; x + 2u <= y; x += 2u, par += 2u) *reinterpret_cast<uint32_t*>(P + x) = par | ((par + 1u) << 16);
-                if (x < y) P[x] = (uint16_t)par;
-            } else if (off < ml && m - off >= tlo && a == m && (off == 1u || (off & 1u) == 0u)) {
-                // a repeating match (a run of equal FLAG words: offset 2) whose first period lies inside this
-                // tile: parent(v) = first period + (v - m) mod off -- the chain is one hop long whatever the
-                // length --, again two parents per store
-                const uint32_t s0 = m - off - tlo;
-                uint32_t r = 0u;
-                if (off == 1u) {
-                    if (x & 1u) P[x++] = (uint16_t)s0;
-                    for (; x + 2u <= y; x += 2u) *reinterpret_cast<uint32_t*>(P + x) = s0 | (s0 << 16);
-                    if (x < y) P[x] = (uint16_t)s0;
-                } else {
-                    if (x & 1u) {  // odd start, even offset: single parents (pairs would straddle the period)
-                        for (; x < y; ++x) {
-                            P[x] = (uint16_t)(s0 + r);
-                            if (++r == off) r = 0u;
-                        }
-                    } else {
-                        for (; x + 2u <= y; x += 2u) {
-                            const uint32_t par = s0 + r;
-                            *reinterpret_cast<uint32_t*>(P + x) = par | ((par + 1u) << 16);
-                            r += 2u;
-                            if (r == off) r = 0u;
-                        }
-                        if (x < y) P[x] = (uint16_t)(s0 + r);
-                    }
+                for (; x + 2u <= y; x += 2u) {
+                    const uint32_t par = s0 + r;
+                    *reinterpret_cast<uint32_t*>(P + x) = (par & 0xFFFFu) | ((par + inc) << 16);
+                    r += 2u * inc;
+                    if (r >= lim) r -= lim;
                 }
+                if (x < y) P[x] = (uint16_t)(s0 + r);
             } else {
                 l4_match_bytes(a, b, m, off, off < ml, 0u, 1u, tlo, ga, ring, P, out);
             }
