@@ -518,6 +518,9 @@ __device__ __forceinline__ void l4_match_bytes(uint32_t a, uint32_t b, uint32_t 
 #ifndef FSB_L4_HOPS
 #define FSB_L4_HOPS 2  // hops per pointer-jumping round (3: A/B builds, tools/gpu_r8a.sh)
 #endif
+#ifndef FSB_L4_EARLY_ROOT
+#define FSB_L4_EARLY_ROOT 0  // 1: a pair stops as soon as it knows that it sits on roots (A/B: tools/gpu_r11a.sh)
+#endif
 constexpr uint32_t kL4Pairs = kL4ByteChunk / 2u;                 // 8
 constexpr uint32_t kL4PairStride = 2u * kL4Threads;              // 1024 bytes between a thread's pairs
 __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uint32_t tlo, uint32_t tid, uint32_t (&rb)[kL4Pairs])
@@ -543,6 +546,29 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
 #pragma unroll
         for (uint32_t j = 0; j < kL4Pairs; ++j) {
             if (act & (1u << j)) {
+#if FSB_L4_EARLY_ROOT
+                // A pair leaves as soon as it KNOWS its parents are roots: after the first hop if they did not
+                // move (roots already), after the second if the first hop's result did not move (the parents'
+                // parents are roots: final once stored).  Without this every pair spends one more whole round
+                // -- two hops -- on finding out that nothing changes any more.
+                const uint32_t h1 = hop(pp[j]);
+                if (h1 == pp[j]) {
+                    act &= ~(1u << j);
+                } else {
+                    uint32_t h2 = hop(h1);
+                    bool fin = h2 == h1;
+#if FSB_L4_HOPS == 3
+                    if (!fin) {
+                        const uint32_t h3 = hop(h2);
+                        fin = h3 == h2;
+                        h2 = h3;
+                    }
+#endif
+                    pp[j] = h2;
+                    changed |= 1u << j;
+                    if (fin) act &= ~(1u << j);
+                }
+#else
                 uint32_t q = hop(hop(pp[j]));
 #if FSB_L4_HOPS == 3
                 q = hop(q);
@@ -553,13 +579,18 @@ __device__ __forceinline__ void l4_resolve(uint16_t* P, const uint8_t* ring, uin
                 } else {
                     act &= ~(1u << j);  // both parents are roots
                 }
+#endif
             }
         }
         __syncthreads();  // every thread has read what it needs from P[]: owners may store now (no data race)
 #pragma unroll
         for (uint32_t j = 0; j < kL4Pairs; ++j)
             if (changed & (1u << j)) *reinterpret_cast<uint32_t*>(P + x0 + j * kL4PairStride) = pp[j];
+#if FSB_L4_EARLY_ROOT
+        if (!__syncthreads_or((int)act)) break;  // (a round without a change leaves nobody active)
+#else
         if (!__syncthreads_or((int)changed)) break;
+#endif
     }
     L4P(7);  // B3: pointer jumping
     // root -> byte.  Roots are literal / history bytes: final since B1.
