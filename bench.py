@@ -852,6 +852,9 @@ def ours(args) -> int:
             "gbs_per_gpu": blocks * 1.024e-3 / sec_s, "pcie_h2d_probe_gbs": pcie_gbs,
             "frac_of_pcie_probe": blocks * 1.024e-3 / sec_s / pcie_gbs,
             "verified": f_s.tolist() == [laps * int(x) for x in f_ring],
+            "note": "blocks are ALREADY in the pinned slots (FLAGSTAT_cuda_stream_selftime resubmits the ring): the "
+                    "producer's fill is not in this number; with a host memcpy per block into the slot it was "
+                    "9 - 11 GB/s on one thread (profiles/r1d_sweep.jsonl, r1h_sweep_tma_variants.jsonl: gbs_with_host_memcpy)",
         }
     except Exception as exc:  # the headline numbers must survive a failure of this extra leg
         stream_info = {"error": repr(exc)}
