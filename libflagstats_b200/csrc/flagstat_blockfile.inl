@@ -6,12 +6,13 @@
 //   FLAGSTAT_CUDA_FILE_LZ4  [int32 raw_size][int32 comp_size][LZ4 block] records
 //                           (written :110-186, read :288-358)
 //
-// Raw files go through the pinned block ring (file -> pinned slot -> DMA ->
-// kernel).  LZ4 containers are shipped COMPRESSED: payloads are gathered into a
-// pinned staging buffer, one DMA per batch of blocks, lz4_decode_kernel (one
-// warp per block) expands them in HBM and the flagstat kernel reads the decoded
-// records from there.  Two batches are in flight (host gather of batch k+1
-// overlaps DMA + decode + count of batch k).
+// Raw files: T reader threads pread() groups of blocks straight into private pinned slots, one DMA +
+// one kernel launch per slot (raw_ctx / consume_raw below).  LZ4 and Zstd containers are shipped
+// COMPRESSED: the payloads of a batch are gathered into a pinned staging buffer by every CPU of the
+// affinity mask, cross PCIe in one DMA, are expanded in HBM -- LZ4 blocks by one CTA per block
+// (lz4_block_cta.cuh), Zstd frames by an entropy stage + the same copy phase (zstd_block.cuh) -- and the
+// flagstat kernel reads the decoded records from there.  Three staging lanes: batch k is decoded while
+// k + 1 crosses PCIe and k + 2 is gathered on the host.
 
 namespace {
 
@@ -44,8 +45,9 @@ struct ByteSource {
 
 constexpr uint32_t kRefBlockBytes = 1024000u;          // benchmark/flagstats.cpp:119
 constexpr uint32_t kMaxRawBlock = 8u << 20;            // sanity bound on a header's raw_size
-// One decode launch needs thousands of blocks to fill the GPU (one warp per block, 12 warps
-// per SM): a batch is up to kBatchBlocks blocks / kBatchRawCap decoded bytes.
+// Upper bounds of a batch: kBatchBlocks blocks / kBatchRawCap decoded bytes.  (The warp-per-block A/B
+// decoders need thousands of blocks per launch to fill the GPU and take batches of this size; the CTA
+// decoder and the Zstd stages get wave-sized batches, see consume_lz4.)
 constexpr int kBatchBlocks = 2048;
 constexpr size_t kBatchRawCap = (size_t)1 << 31;
 
@@ -147,7 +149,7 @@ struct Lz4Scratch {
 
 unsigned lz4_cta_grid(uint32_t n_blocks, int sms)
 {
-    const unsigned full = 2u * (unsigned)sms;  // two CTAs of 94 KB shared memory per SM
+    const unsigned full = 2u * (unsigned)sms;  // two CTAs (kL4Smem = 112,896 bytes of shared memory each) per SM
     return n_blocks < full ? n_blocks : full;
 }
 
